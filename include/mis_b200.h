@@ -1,0 +1,166 @@
+/*
+ * mis_b200.h -- C ABI of the B200-native SSL hot path (libmis_b200.so).
+ *
+ * The reference (EthanHaque/medical_image_segmentation) is pure Python and has no FFI or
+ * operator registry for this path: its "interface" is two Python callables,
+ *   BYOLRGBDataTransforms.__call__(x) -> [view1, view2]
+ *       medical_image_segmentation/train/data_loaders/lightning_module.py:39-64
+ *   BYOL.cosine_similarity_loss(preds, targets) -> scalar
+ *       medical_image_segmentation/train/model/byol_pytorch.py:181-198 (called :217)
+ * The entry points below are what a ctypes binding of those two call sites binds
+ * (INTEGRATION.md shows the stub); each one names the reference arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a raw device pointer unless it says "host";
+ *   - the caller allocates and owns every buffer (including scratch);
+ *   - every launch goes to the caller's stream (a cudaStream_t / CUstream passed as void*),
+ *     asynchronously, with no internal synchronisation;
+ *   - return value 0 = success, otherwise one of MIS_ERR_*; mis_last_error() gives the text
+ *     (thread-local).  Nothing throws across the ABI.
+ */
+#ifndef MIS_B200_H_
+#define MIS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIS_ABI_VERSION 1
+
+enum {
+  MIS_OK = 0,
+  MIS_ERR_INVALID_ARG = 1,   /* null pointer, non-positive size, bad enum            */
+  MIS_ERR_UNSUPPORTED = 2,   /* valid request outside what the kernels implement     */
+  MIS_ERR_CUDA = 3           /* a CUDA runtime / driver call failed                  */
+};
+
+enum { MIS_DTYPE_BF16 = 0, MIS_DTYPE_F32 = 1 };
+
+/* flags of MisViewParams */
+#define MIS_VIEW_FLIP   1u   /* RandomHorizontalFlip fired   (torchvision v2/_transform.py:181) */
+#define MIS_VIEW_JITTER 2u   /* RandomApply(ColorJitter) fired (v2/_container.py:104)           */
+
+/*
+ * One augmented view = one record (48 bytes).  Filled on the host by the RNG replay of
+ * torchvision's draw order (RandomResizedCrop.make_params v2/_geometry.py:272-308,
+ * ColorJitter.make_params v2/_color.py:146-154) -- see mis_draw_two_view_params().
+ */
+typedef struct MisViewParams {
+  int32_t img;            /* index of the source slice in the batch                         */
+  int32_t top, left;      /* crop box origin  (rows, cols)                                  */
+  int32_t h, w;           /* crop box size                                                  */
+  uint32_t flags;         /* MIS_VIEW_*                                                     */
+  uint8_t order[4];       /* ColorJitter fn_idx: 0 brightness, 1 contrast, 2 sat, 3 hue     */
+  float brightness;       /* factors; meaningful only when MIS_VIEW_JITTER is set           */
+  float contrast;
+  float saturation;       /* drawn (RNG parity) but identity for C == 1                     */
+  float hue;
+  int32_t reserved;
+} MisViewParams;
+
+int mis_version(void);
+const char* mis_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side RNG replay (no GPU work).
+ *
+ * Replaces the per-sample Python RNG calls of the transform chain
+ * (lightning_module.py:47-61 -> torchvision make_params / RandomApply / _RandomApplyTransform):
+ * consumes a torch CPU mt19937 generator state exactly as `n_images` calls of
+ * BYOLRGBDataTransforms.__call__ would (view 1 completely, then view 2) and writes
+ * 2*n_images records, image-major: out[2*i + v].
+ *
+ *   rng_state      host, the byte blob of torch.get_rng_state() (read and advanced in place)
+ *   rng_state_len  its length (5056 for torch's CPUGeneratorImpl)
+ *   blur_prob / solarize_prob  host float[2]; only 0.0 is implemented on the device side, the
+ *                  draws are still consumed for parity (lightning_module.py:53-54)
+ *   n_done         host, out: number of images completed.  n_done < n_images means image
+ *                  img0+n_done has a crop box that depends on the last bit of torch.exp (SLEEF
+ *                  vs libm expf); the generator is left at that image's first draw and the caller
+ *                  draws that one image with torch itself, then calls again for the rest.
+ * ------------------------------------------------------------------------------------------ */
+int mis_draw_two_view_params(uint8_t* rng_state, int64_t rng_state_len, int n_images, int img0,
+                             int H, int W, const float* blur_prob, const float* solarize_prob,
+                             MisViewParams* out, int* n_done);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused two-view augmentation (kernel K1).
+ *
+ * Replaces, per view, the chain RandomResizedCrop (crop_image + antialiased bilinear
+ * resize_image, torchvision v2/functional/_geometry.py:1785-1800, 271-340) ->
+ * horizontal flip (:56-57) -> ColorJitter brightness/contrast in fn_idx order
+ * (functional/_color.py:114-125, 190-205, _blend :92-97) -> ToDtype(float32, scale=True)
+ * (functional/_misc.py:304) -> Normalize (functional/_misc.py:37-67), i.e.
+ * lightning_module.py:47-58 with blur_prob = solarize_prob = 0.
+ *
+ *   src        uint16 [n_images, C, H, W], plane stride H*W, image stride img_stride elements.
+ *              W must be even; the allocation must be readable up to the next 16-byte boundary
+ *              past its last element (any cudaMalloc / torch allocation is).
+ *   params     device array of n_views records (params[v].img selects the source slice)
+ *   win_lo, win_hi   intensity window: x = clamp((u16 - lo) / (hi - lo), 0, 1); (0, 65535) is
+ *              the reference's plain 1/65535 scaling
+ *   mean,std   host float[C]
+ *   out        [n_views, C, s, s] in out_dtype (MIS_DTYPE_BF16 or MIS_DTYPE_F32), NCHW
+ *   s          output crop size, 8 <= s <= 256
+ *   use_tma    1: stage crop rows through shared memory with cp.async.bulk (TMA) -- default
+ *              0: read crop rows through L1/L2 with plain loads (debug / A-B comparison)
+ * ------------------------------------------------------------------------------------------ */
+int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H, int W, int64_t img_stride,
+                     const MisViewParams* params, int n_views, float win_lo, float win_hi,
+                     const float* mean, const float* std, void* out, int s, int out_dtype,
+                     int use_tma, void* stream);
+
+/* Algorithmic bytes K1 moves for a host copy of the params table (crop window read + output
+ * write).  Pure host arithmetic. */
+int64_t mis_aug_algorithmic_bytes(const MisViewParams* params_host, int n_views, int C, int s,
+                                  int out_dtype);
+
+/* ------------------------------------------------------------------------------------------
+ * NT-Xent (SimCLR InfoNCE) forward / backward over all-gathered embeddings (kernels K2/K3).
+ *
+ * Slots in where the reference calls its SSL loss (byol_pytorch.py:217); the reference's own
+ * loss is BYOL (see mis_byol_loss_*), NT-Xent is specified by the north star.
+ *
+ * Layout: a rank owns `rows` = 2*B_local consecutive embedding rows [v1_local; v2_local] that
+ * sit at row offset row0 of the rank-major all-gathered matrix of `cols` = 2N rows.  The
+ * positive of local row i is local row (i + rows/2) mod rows.
+ *
+ *   mis_ntxent_prep      z [rows, D] (f32 or bf16) -> u = z/max(|z|,1e-12) rounded to TF32
+ *                        (f32 container), rinv = 1/max(|z|,1e-12), pos = <u_i,u_p(i)>/T (fp32)
+ *   mis_ntxent_fwd       lse_i = log sum_{j != g(i)} exp(<u_i,u_j>/T) over all `cols` columns
+ *                        (tcgen05 kind::tf32, accumulators in TMEM; S never leaves the SM) and
+ *                        loss = mean_i (lse_i - pos_i) over the local rows
+ *   mis_ntxent_bwd       dz_local = sum_r' dL_r'/dz_local  (option L: needs the
+ *                        all-gathered lse) scaled by grad_scale; fused recompute of S, the
+ *                        (P + P^T - 2*onehot) tile stays in TMEM as the A operand of the second MMA
+ *
+ * D % 32 == 0, 32 <= D <= 256; rows % 128 == 0; cols % 128 == 0; T >= 0.025.
+ * scratch sizes are returned by mis_ntxent_scratch_bytes().
+ * ------------------------------------------------------------------------------------------ */
+int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D);
+
+int mis_ntxent_prep(const void* z, int z_dtype, int rows, int D, float inv_T, float* u,
+                    float* rinv, float* pos, void* stream);
+
+int mis_ntxent_fwd(const float* u_all, int cols, int D, int row0, int rows, float inv_T,
+                   const float* pos, float* lse_rows, float* loss, void* scratch,
+                   int64_t scratch_bytes, void* stream);
+
+int mis_ntxent_bwd(const float* u_all, const float* lse_all, const float* rinv_rows, int cols, int D,
+                   int row0, int rows, float inv_T, float grad_scale, const float* grad_out,
+                   void* dz, int dz_dtype, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BYOL cosine loss, fused forward + backward (the loss the reference actually trains with):
+ *   loss = 2 - 2 * mean_i <p_i/|p_i|, t_i/|t_i|>          byol_pytorch.py:196-198
+ *   dpreds = grad_scale * dloss/dpreds (targets carry no gradient, :212-214)
+ * ------------------------------------------------------------------------------------------ */
+int mis_byol_loss_fwd_bwd(const float* preds, const float* targets, int rows, int D, float* loss,
+                          float* dpreds, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIS_B200_H_ */

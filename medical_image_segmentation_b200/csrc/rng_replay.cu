@@ -1,0 +1,209 @@
+// Host-side replay of the random draws of the reference's two-view transform chain.
+//
+// The reference draws every augmentation parameter with per-sample Python calls into torch's
+// global CPU generator (lightning_module.py:47-61 -> torchvision v2: RandomResizedCrop.make_params
+// _geometry.py:272-308, _RandomApplyTransform.forward _transform.py:181, RandomApply.forward
+// _container.py:104, ColorJitter.make_params _color.py:146-154).  ~20 tensor ops per view is three
+// orders of magnitude slower than the GPU consumes views, so the same stream is consumed here
+// natively: the caller hands over the bytes of torch.get_rng_state(), this code advances the
+// mt19937 exactly as torch would and the caller puts the state back with torch.set_rng_state().
+//
+// Restated torch CPU generator semantics (ATen CPUGeneratorImpl / DistributionsHelper.h):
+//   random()             one tempered mt19937 word
+//   uniform_(a,b) f32    fma((random() & (2^24-1)) * 2^-24, b - a, a)          (float, fused)
+//   rand(1)              uniform_(0,1)
+//   randint(0,n)         random() % n                                         (n < 2^32)
+//   randperm(n)          Fisher-Yates: for i < n-1: z = random() % (n-i); swap(r[i], r[i+z])
+//
+// The one operation that cannot be restated bit-for-bit is torch.exp on a float32 tensor (SLEEF
+// vector expf, not libm).  A crop box only depends on it through round(sqrt(area*ratio)); whenever
+// the box would differ for exp(x) one ulp up or down, the image is reported back to the caller
+// (n_done < n_images) who draws that single image with torch itself -- the result is bit-exact
+// always, and native for all but ~1e-5 of the images.
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace mis {
+namespace rng {
+
+constexpr int kN = 624, kM = 397;
+constexpr int64_t kStateLen = 5056;   // sizeof(at::CPUGeneratorImplState)
+
+struct Engine {
+  int32_t left;
+  uint64_t next;
+  uint32_t st[kN];
+
+  static inline uint32_t twist(uint32_t u, uint32_t v) {
+    return (((u & 0x80000000u) | (v & 0x7fffffffu)) >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
+  }
+  void next_state() {
+    uint32_t* p = st;
+    left = kN;
+    next = 0;
+    for (int j = kN - kM + 1; --j; p++) *p = p[kM] ^ twist(p[0], p[1]);
+    for (int j = kM; --j; p++) *p = p[kM - kN] ^ twist(p[0], p[1]);
+    *p = p[kM - kN] ^ twist(p[0], st[0]);
+  }
+  inline uint32_t random() {
+    if (--left == 0) next_state();
+    uint32_t y = st[next++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+  }
+  inline float uniform(float from, float to) {
+    const float x = (float)(random() & ((1u << 24) - 1)) * (1.0f / 16777216.0f);
+    return fmaf(x, to - from, from);   // torch's kernel is built with FMA contraction: one rounding
+  }
+};
+
+// layout of at::CPUGeneratorImplStateLegacy: seed u64 | left i32 | seeded i32 | next u64 | state u64[624] | ...
+static void load(const uint8_t* blob, Engine& e) {
+  memcpy(&e.left, blob + 8, 4);
+  memcpy(&e.next, blob + 16, 8);
+  for (int i = 0; i < kN; ++i) {
+    uint64_t v;
+    memcpy(&v, blob + 24 + 8 * i, 8);
+    e.st[i] = (uint32_t)v;
+  }
+}
+static void store(uint8_t* blob, const Engine& e) {
+  memcpy(blob + 8, &e.left, 4);
+  memcpy(blob + 16, &e.next, 8);
+  for (int i = 0; i < kN; ++i) {
+    const uint64_t v = e.st[i];
+    memcpy(blob + 24 + 8 * i, &v, 8);
+  }
+}
+
+// constants of the reference chain (lightning_module.py:44,49-54)
+constexpr float kScaleLo = 0.08f, kScaleHi = 1.0f;
+constexpr float kLogRatioLo = -0.28768208622932434f;   // torch.log(torch.tensor(3/4))  (float32)
+constexpr float kLogRatioHi = 0.28768211603164673f;    // torch.log(torch.tensor(4/3))  (float32)
+constexpr double kRatioLo = 3.0 / 4.0, kRatioHi = 4.0 / 3.0;
+constexpr float kFlipP = 0.5f, kJitterP = 0.8f, kGrayP = 0.2f;
+
+struct Box {
+  int top, left, h, w;
+  bool ok;
+};
+
+static inline void box_dims(double target_area, float ar, int& w, int& h) {
+  w = (int)std::nearbyint(std::sqrt(target_area * (double)ar));
+  h = (int)std::nearbyint(std::sqrt(target_area / (double)ar));
+}
+
+// returns false when the result depends on the last bit of exp()
+static bool draw_view(Engine& e, int H, int W, float blur_p, float sol_p, MisViewParams& out) {
+  const double area = (double)H * (double)W;
+  bool have = false;
+  int top = 0, left = 0, h = 0, w = 0;
+  for (int t = 0; t < 10; ++t) {
+    const double target_area = area * (double)e.uniform(kScaleLo, kScaleHi);
+    const float lr = e.uniform(kLogRatioLo, kLogRatioHi);
+    const float ar = expf(lr);
+    box_dims(target_area, ar, w, h);
+    int w1, h1, w2, h2;
+    box_dims(target_area, std::nextafterf(ar, 0.f), w1, h1);
+    box_dims(target_area, std::nextafterf(ar, 4.f), w2, h2);
+    if (w1 != w || w2 != w || h1 != h || h2 != h) return false;
+    if (0 < w && w <= W && 0 < h && h <= H) {
+      top = (int)(e.random() % (uint32_t)(H - h + 1));
+      left = (int)(e.random() % (uint32_t)(W - w + 1));
+      have = true;
+      break;
+    }
+  }
+  if (!have) {   // central-crop fallback, _geometry.py:293-306
+    const double in_ratio = (double)W / (double)H;
+    if (in_ratio < kRatioLo) {
+      w = W;
+      h = (int)std::nearbyint((double)w / kRatioLo);
+    } else if (in_ratio > kRatioHi) {
+      h = H;
+      w = (int)std::nearbyint((double)h * kRatioHi);
+    } else {
+      w = W;
+      h = H;
+    }
+    top = (H - h) / 2;
+    left = (W - w) / 2;
+  }
+  out.top = top;
+  out.left = left;
+  out.h = h;
+  out.w = w;
+  out.flags = 0;
+  out.order[0] = 0; out.order[1] = 1; out.order[2] = 2; out.order[3] = 3;
+  out.brightness = 1.f; out.contrast = 1.f; out.saturation = 1.f; out.hue = 0.f;
+  out.reserved = 0;
+  if (!(e.uniform(0.f, 1.f) >= kFlipP)) out.flags |= MIS_VIEW_FLIP;
+  if (!(e.uniform(0.f, 1.f) >= kJitterP)) {
+    out.flags |= MIS_VIEW_JITTER;
+    uint8_t perm[4] = {0, 1, 2, 3};
+    for (int i = 0; i < 3; ++i) {
+      const uint32_t z = e.random() % (uint32_t)(4 - i);
+      const uint8_t sav = perm[i];
+      perm[i] = perm[i + z];
+      perm[i + z] = sav;
+    }
+    memcpy(out.order, perm, 4);
+    out.brightness = e.uniform(0.6f, 1.4f);
+    out.contrast = e.uniform(0.6f, 1.4f);
+    out.saturation = e.uniform(0.8f, 1.2f);
+    out.hue = e.uniform(-0.1f, 0.1f);
+  }
+  (void)e.uniform(0.f, 1.f);                                   // RandomGrayscale(p=0.2): identity at C == 1
+  const bool blur = !(e.uniform(0.f, 1.f) >= blur_p);          // RandomApply([GaussianBlur(23)])
+  if (blur) (void)e.uniform(0.1f, 2.0f);                       //   sigma draw, v2/_misc.py:209-211
+  (void)e.uniform(0.f, 1.f);                                   // RandomSolarize
+  (void)sol_p;
+  (void)kGrayP;
+  return true;
+}
+
+}  // namespace rng
+}  // namespace mis
+
+extern "C" int mis_draw_two_view_params(uint8_t* rng_state, int64_t rng_state_len, int n_images, int img0, int H, int W,
+                                        const float* blur_prob, const float* solarize_prob, MisViewParams* out,
+                                        int* n_done) {
+  using namespace mis;
+  using namespace mis::rng;
+  MIS_REQUIRE(rng_state && out && blur_prob && solarize_prob && n_done, MIS_ERR_INVALID_ARG,
+              "mis_draw_two_view_params: null pointer");
+  MIS_REQUIRE(rng_state_len == kStateLen, MIS_ERR_INVALID_ARG,
+              "mis_draw_two_view_params: rng state is %lld bytes, expected %lld (torch CPUGeneratorImpl)",
+              (long long)rng_state_len, (long long)kStateLen);
+  MIS_REQUIRE(n_images >= 0 && H > 0 && W > 0, MIS_ERR_INVALID_ARG, "mis_draw_two_view_params: bad sizes");
+  for (int v = 0; v < 2; ++v)
+    MIS_REQUIRE(blur_prob[v] >= 0.f && blur_prob[v] <= 1.f && solarize_prob[v] >= 0.f && solarize_prob[v] <= 1.f,
+                MIS_ERR_INVALID_ARG, "mis_draw_two_view_params: probabilities must be in [0,1]");
+  Engine e;
+  load(rng_state, e);
+  MIS_REQUIRE(e.left >= 1 && e.left <= kN && e.next <= (uint64_t)kN, MIS_ERR_INVALID_ARG,
+              "mis_draw_two_view_params: corrupt generator state (left=%d next=%llu)", e.left,
+              (unsigned long long)e.next);
+  *n_done = 0;
+  for (int i = 0; i < n_images; ++i) {
+    const Engine checkpoint = e;
+    bool exact = true;
+    for (int v = 0; v < 2 && exact; ++v) {
+      MisViewParams& p = out[2 * (size_t)i + v];
+      p.img = img0 + i;
+      exact = draw_view(e, H, W, blur_prob[v], solarize_prob[v], p);
+    }
+    if (!exact) {   // hand this image back to the caller, generator rewound to its first draw
+      e = checkpoint;
+      break;
+    }
+    *n_done = i + 1;
+  }
+  store(rng_state, e);
+  return MIS_OK;
+}

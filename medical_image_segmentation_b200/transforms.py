@@ -1,0 +1,143 @@
+"""Drop-in for the reference's two-view transform object, running as one fused CUDA kernel.
+
+Mirrors ``BYOLRGBDataTransforms`` (train/data_loaders/lightning_module.py:39-64): same constructor
+arguments, ``__call__(x) -> [view1, view2]``.  Differences, all forced by moving the chain from a
+per-sample CPU callable to a per-batch GPU kernel:
+
+* ``x`` is a *batch* ``[B, C, H, W]`` (or ``[B, H, W]``) of raw ``torch.uint16`` slices -- on the GPU, or
+  on the host (then it is copied through pinned memory first).  The reference feeds one decoded
+  image at a time to DataLoader workers.
+* the two views come back as ``[B, C, s, s]`` tensors that are the two halves of ONE
+  ``[2B, C, s, s]`` buffer (``.views_buffer``), so the ``torch.cat(views)`` of
+  train/model/byol_pytorch.py:207 is free.
+* random parameters are drawn from torch's global CPU generator in exactly the reference's order
+  (params.py), so ``torch.manual_seed(k)`` gives the same crops / flips / jitter as the reference.
+* GaussianBlur and Solarize (lightning_module.py:53-54) are not implemented on the device yet:
+  ``blur_prob`` / ``solarize_prob`` must be 0 (their RNG draws are still consumed).  The CIFAR data
+  modules of the reference run with exactly this setting (lightning_module.py:482-488).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MIS_DTYPE_BF16, MIS_DTYPE_F32, VIEW_PARAMS_DTYPE
+from .params import draw_two_view_params
+
+_U16_MAX = 65535.0
+
+
+def _as_float_seq(v, n: int, name: str) -> list[float]:
+    if isinstance(v, (int, float)):
+        v = [float(v)] * n
+    v = [float(t) for t in v]
+    if len(v) != n:
+        raise ValueError(f"{name} has {len(v)} entries for {n} channel(s)")
+    return v
+
+
+class FusedTwoViewTransforms:
+    def __init__(self, crop_size: int, mean: Sequence[float], std: Sequence[float],
+                 blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0), *, out_dtype=torch.bfloat16,
+                 window: tuple[float, float] | None = None, use_tma: bool = True):
+        assert len(blur_prob) == 2 and len(solarize_prob) == 2, "atm only 2 views are supported"
+        if any(p != 0 for p in blur_prob) or any(p != 0 for p in solarize_prob):
+            raise NotImplementedError(
+                "GaussianBlur / RandomSolarize are not fused yet (SURVEY 8f N2): pass blur_prob=(0,0), "
+                "solarize_prob=(0,0) as the reference's CIFAR modules do (lightning_module.py:482-488)")
+        if isinstance(crop_size, (tuple, list)):
+            if len(crop_size) != 2 or crop_size[0] != crop_size[1]:
+                raise NotImplementedError("only square crops are implemented")
+            crop_size = crop_size[0]
+        self.crop_size = int(crop_size)
+        self.mean = mean
+        self.std = std
+        self.blur_prob = tuple(float(p) for p in blur_prob)
+        self.solarize_prob = tuple(float(p) for p in solarize_prob)
+        if out_dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("out_dtype must be torch.bfloat16 or torch.float32")
+        self.out_dtype = out_dtype
+        self.window = (0.0, _U16_MAX) if window is None else (float(window[0]), float(window[1]))
+        self.use_tma = bool(use_tma)
+        self.views_buffer: torch.Tensor | None = None
+        self.last_params: np.ndarray | None = None
+        self.launches = 0
+
+    # -- parameters ---------------------------------------------------------------------------
+    def draw_params(self, B: int, H: int, W: int) -> np.ndarray:
+        """Image-major records [2*i+v], drawn like B calls of the reference's __call__."""
+        return draw_two_view_params(B, H, W, self.blur_prob, self.solarize_prob)
+
+    @staticmethod
+    def to_view_major(params: np.ndarray) -> np.ndarray:
+        """[2*i+v] -> [v*B+i]: row order of cat([view1, view2]) (byol_pytorch.py:207)."""
+        B = params.shape[0] // 2
+        return np.ascontiguousarray(params.reshape(B, 2).T.reshape(-1))
+
+    # -- device path --------------------------------------------------------------------------
+    def apply(self, x: torch.Tensor, params_view_major: np.ndarray, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Run K1 for an explicit parameter table.  Returns the [n_views, C, s, s] buffer."""
+        if x.dtype != torch.uint16:
+            raise TypeError(f"expected raw torch.uint16 slices, got {x.dtype}")
+        if not x.is_cuda:
+            raise ValueError("apply() needs a CUDA tensor (use __call__ for host batches)")
+        if x.dim() == 3:
+            x = x[:, None]
+        if x.dim() != 4:
+            raise ValueError(f"expected [B,C,H,W], got {tuple(x.shape)}")
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        mean = _as_float_seq(self.mean, Cc, "mean")
+        std = _as_float_seq(self.std, Cc, "std")
+        n_views = int(params_view_major.shape[0])
+        assert params_view_major.dtype == VIEW_PARAMS_DTYPE
+        s = self.crop_size
+        if out is None:
+            out = torch.empty((n_views, Cc, s, s), dtype=self.out_dtype, device=x.device)
+        else:
+            assert out.is_cuda and out.is_contiguous() and out.dtype == self.out_dtype
+            assert tuple(out.shape) == (n_views, Cc, s, s)
+        host = torch.from_numpy(params_view_major.view(np.uint8).reshape(-1)).pin_memory()
+        dev = host.to(x.device, non_blocking=True)
+        mean_c = (C.c_float * Cc)(*mean)
+        std_c = (C.c_float * Cc)(*std)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = _lib.lib.mis_aug_two_view(
+                x.data_ptr(), B, Cc, H, W, Cc * H * W, dev.data_ptr(), n_views,
+                self.window[0], self.window[1], C.cast(mean_c, C.c_void_p), C.cast(std_c, C.c_void_p),
+                out.data_ptr(), s, MIS_DTYPE_F32 if self.out_dtype == torch.float32 else MIS_DTYPE_BF16,
+                1 if self.use_tma else 0, C.c_void_p(stream))
+        _lib.check(rc, "mis_aug_two_view")
+        self.launches += 1
+        self._keepalive = (dev, host)     # until the next call: the kernel reads `dev` asynchronously
+        return out
+
+    def __call__(self, x) -> list[torch.Tensor]:
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(x)
+        if x.dim() == 2:
+            x = x[None, None]
+        elif x.dim() == 3:
+            x = x[:, None]
+        if not x.is_cuda:
+            if not torch.cuda.is_available():
+                raise RuntimeError("FusedTwoViewTransforms has no CPU path: a CUDA device is required")
+            x = (x if x.is_pinned() else x.pin_memory()).cuda(non_blocking=True)
+        B, _, H, W = x.shape
+        params = self.draw_params(B, H, W)
+        self.last_params = params
+        out = self.apply(x, self.to_view_major(params))
+        self.views_buffer = out
+        return [out[:B], out[B:]]
+
+
+def algorithmic_bytes(params: np.ndarray, C_: int, crop_size: int, out_dtype=torch.bfloat16) -> int:
+    """Bytes K1 must move for this table: u16 crop windows read once + output written once."""
+    p = np.ascontiguousarray(params)
+    return int(_lib.lib.mis_aug_algorithmic_bytes(p.ctypes.data, p.shape[0], C_, crop_size,
+                                                  MIS_DTYPE_F32 if out_dtype == torch.float32 else MIS_DTYPE_BF16))
