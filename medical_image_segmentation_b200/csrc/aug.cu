@@ -46,11 +46,13 @@ struct Args {
   float mean[4], inv_std[4];
   void* out;
   int s;
+  int out_f32;
   int nbands;
-  int kv, kh;       // tap-table strides (>= max taps on that axis)
-  int nch;          // ring depth in chunks
+  int kstride;      // tap-table stride in floats (multiple of 4, >= unrolled tap count)
+  int nch;          // ring depth in chunks (power of two)
+  int nch_log2;
   int pitch;        // ring row pitch in bytes (multiple of 16)
-  int pstr;         // tmp-plane row stride in words (odd)
+  int pstr;         // tmp row stride in words (odd)
   // shared-memory byte offsets
   int off_vw, off_hw, off_tmp, off_ring;
 };
@@ -60,37 +62,236 @@ struct SmemHeader {
   uint64_t empty[kMaxChunks];
   float part[kMaxBands];      // per-CTA partial sums of the contrast mean (written by peers)
   float red[kConsumerWarps];
-  int v_min[kBandRows];
-  int v_size[kBandRows];
+  int4 v_info[kBandRows];     // {first source row, taps, chunks that must have landed, first chunk still needed}
   int h_min[256];
-  int h_size[256];
+  int kv_max, kh_max;         // largest tap count of this band / this view
 };
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FADD2) ---------------------------------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// two packed uint16 -> two exact floats without the (slow, XU-pipe) I2F:
+// 0x4B000000 | v is the float 2^23 + v; subtracting 2^23 is exact.
+__device__ __forceinline__ uint64_t u16x2_to_f32x2(uint32_t p) {
+  const uint32_t lo = (p & 0xffffu) | 0x4B000000u;
+  const uint32_t hi = __byte_perm(p, 0x4B000000u, 0x7632);
+  return fadd2(pack2(__uint_as_float(lo), __uint_as_float(hi)), pack2(-8388608.f, -8388608.f));
+}
+
 // Tap table of one output index.  n = input size, scale = n/m in fp32.
-__device__ __forceinline__ void aa_taps(int i, int n, float scale, float support, float invscale, int kmax,
-                                        int& lo_out, int& size_out, float* w) {
+// Writes kstride weights (zero padded) with element stride `wstep` (2 = duplicated pairs).
+__device__ __forceinline__ void aa_taps(int i, int n, float scale, float support, float invscale, int kstride,
+                                        int wstep, int& lo_out, int& size_out, float* w) {
   const float center = (float)((double)scale * ((double)i + 0.5));
   int lo = (int)((double)center - (double)support + 0.5);
   lo = lo < 0 ? 0 : lo;
   int hi = (int)((double)center + (double)support + 0.5);
   hi = hi > n ? n : hi;
   int size = hi - lo;
-  size = size < 0 ? 0 : (size > kmax ? kmax : size);
+  size = size < 0 ? 0 : (size > kstride ? kstride : size);
   float total = 0.f;
   for (int j = 0; j < size; ++j) {
     const float arg = ((float)(j + lo) - center + 0.5f) * invscale;
     const float wj = fmaxf(0.f, 1.f - fabsf(arg));
-    w[j] = wj;
+    w[j * wstep] = wj;
     total += wj;
   }
-  if (total != 0.f)
-    for (int j = 0; j < size; ++j) w[j] = w[j] / total;
-  for (int j = size; j < kmax; ++j) w[j] = 0.f;
+  for (int j = 0; j < kstride; ++j) {
+    float wj = 0.f;
+    if (j < size) wj = (total != 0.f) ? w[j * wstep] / total : w[j * wstep];
+    for (int t = 0; t < wstep; ++t) w[j * wstep + t] = wj;
+  }
   lo_out = lo;
   size_out = size;
 }
 
-template <bool kBulk, bool kWindow, bool kOutF32>
+struct Ctx {
+  const Args* a;
+  SmemHeader* sh;
+  const float* v_w;     // [32][kstride][2]  duplicated pairs
+  const float* h_w;     // [s][kstride]
+  float* tmp;           // [32][pstr]
+  const uint8_t* ring;
+  const uint16_t* gplane;   // crop (0, -lp) in global memory
+  int tid, lane, warp;
+  int nrows, npairs, lp, w, h, r_lo;
+  int ring_byte0;       // byte offset of pair 0 inside a ring row
+};
+
+// ---- V pass: lanes over source column pairs, K taps unrolled, packed FMAs -----------------------
+template <int K, bool kBulk, bool kWindow>
+__device__ __forceinline__ void v_pass(const Ctx& c) {
+  const Args& a = *c.a;
+  SmemHeader& sh = *c.sh;
+  const int ring_mask = a.nch * kChunkRows - 1;
+  const int npad = min(c.npairs + a.kstride / 2 + 1, a.pstr / 2);  // zero columns the H pass may touch
+  int loaded = 0, released = 0;
+  const uint64_t wsc = pack2(a.win_scale, a.win_scale);
+  const uint64_t wof = pack2(-a.win_lo * a.win_scale, -a.win_lo * a.win_scale);
+  for (int yy = 0; yy < c.nrows; ++yy) {
+    const int4 info = sh.v_info[yy];     // {ymin, n, need, first}
+    if (kBulk) {
+      while (loaded < info.z) {
+        mbar_wait(&sh.full[loaded & (a.nch - 1)], (loaded >> a.nch_log2) & 1);
+        ++loaded;
+      }
+      while (released < info.w) {
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(&sh.empty[released & (a.nch - 1)]);
+        ++released;
+      }
+    }
+    const uint64_t* wrow = reinterpret_cast<const uint64_t*>(c.v_w + yy * a.kstride * 2);
+    float* trow = c.tmp + yy * a.pstr;
+    for (int q = c.tid; q < npad; q += kConsumerThreads) {
+      uint64_t acc = 0ull;   // (+0.f, +0.f)
+      if (q < c.npairs) {
+        uint32_t p[K];
+        if (kBulk) {
+          const uint8_t* base = c.ring + c.ring_byte0 + 4 * q;
+          const int sr0 = info.x - c.r_lo;
+#pragma unroll
+          for (int j = 0; j < K; ++j)
+            p[j] = *reinterpret_cast<const uint32_t*>(base + (size_t)((sr0 + j) & ring_mask) * a.pitch);
+        } else {
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            const int r = min(info.x + j, c.h - 1);
+            p[j] = __ldg(reinterpret_cast<const uint32_t*>(c.gplane + (int64_t)r * a.W) + q);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          uint64_t f = u16x2_to_f32x2(p[j]);
+          if (kWindow) {
+            f = ffma2(f, wsc, wof);
+            float f0, f1;
+            unpack2(f, f0, f1);
+            f = pack2(fminf(fmaxf(f0, 0.f), 1.f), fminf(fmaxf(f1, 0.f), 1.f));
+          }
+          acc = ffma2(f, wrow[j], acc);
+        }
+      }
+      float a0, a1;
+      unpack2(acc, a0, a1);
+      trow[2 * q] = a0;
+      trow[2 * q + 1] = a1;
+    }
+  }
+}
+
+// dynamic-length fallback (tap counts outside the unrolled set)
+template <bool kBulk, bool kWindow>
+__device__ __forceinline__ void v_pass_dyn(const Ctx& c) {
+  const Args& a = *c.a;
+  SmemHeader& sh = *c.sh;
+  const int ring_mask = a.nch * kChunkRows - 1;
+  const int npad = min(c.npairs + a.kstride / 2 + 1, a.pstr / 2);
+  int loaded = 0, released = 0;
+  for (int yy = 0; yy < c.nrows; ++yy) {
+    const int4 info = sh.v_info[yy];
+    if (kBulk) {
+      while (loaded < info.z) {
+        mbar_wait(&sh.full[loaded & (a.nch - 1)], (loaded >> a.nch_log2) & 1);
+        ++loaded;
+      }
+      while (released < info.w) {
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(&sh.empty[released & (a.nch - 1)]);
+        ++released;
+      }
+    }
+    const float* wrow = c.v_w + yy * a.kstride * 2;
+    float* trow = c.tmp + yy * a.pstr;
+    for (int q = c.tid; q < npad; q += kConsumerThreads) {
+      float a0 = 0.f, a1 = 0.f;
+      if (q < c.npairs) {
+        for (int j = 0; j < info.y; ++j) {
+          uint32_t p;
+          if (kBulk)
+            p = *reinterpret_cast<const uint32_t*>(c.ring + c.ring_byte0 + 4 * q +
+                                                   (size_t)((info.x - c.r_lo + j) & ring_mask) * a.pitch);
+          else
+            p = __ldg(reinterpret_cast<const uint32_t*>(c.gplane + (int64_t)(info.x + j) * a.W) + q);
+          float f0, f1;
+          unpack2(u16x2_to_f32x2(p), f0, f1);
+          if (kWindow) {
+            f0 = fminf(fmaxf((f0 - a.win_lo) * a.win_scale, 0.f), 1.f);
+            f1 = fminf(fmaxf((f1 - a.win_lo) * a.win_scale, 0.f), 1.f);
+          }
+          const float w = wrow[2 * j];
+          a0 = fmaf(f0, w, a0);
+          a1 = fmaf(f1, w, a1);
+        }
+      }
+      trow[2 * q] = a0;
+      trow[2 * q + 1] = a1;
+    }
+  }
+}
+
+// ---- H pass: lanes over the band's rows, one warp per 32 output columns, K taps unrolled --------
+template <int K>
+__device__ __forceinline__ void h_pass(const Ctx& c, float (&o)[kSeg], float post) {
+  const Args& a = *c.a;
+  const int x0 = c.warp * kSeg;
+  const float* trow = c.tmp + c.lane * a.pstr + c.lp;
+  constexpr int K4 = (K + 3) / 4;
+#pragma unroll
+  for (int i = 0; i < kSeg; ++i) {
+    const int x = x0 + i;
+    if (x < a.s) {
+      const float* tp = trow + c.sh->h_min[x];
+      const float4* wp = reinterpret_cast<const float4*>(c.h_w + x * a.kstride);
+      float acc = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < K4; ++j4) {
+        const float4 w = wp[j4];
+        acc = fmaf(tp[4 * j4], w.x, acc);
+        if (4 * j4 + 1 < K) acc = fmaf(tp[4 * j4 + 1], w.y, acc);
+        if (4 * j4 + 2 < K) acc = fmaf(tp[4 * j4 + 2], w.z, acc);
+        if (4 * j4 + 3 < K) acc = fmaf(tp[4 * j4 + 3], w.w, acc);
+      }
+      o[i] = acc * post;
+    }
+  }
+}
+
+__device__ __forceinline__ void h_pass_dyn(const Ctx& c, float (&o)[kSeg], float post) {
+  const Args& a = *c.a;
+  const int x0 = c.warp * kSeg;
+  const float* trow = c.tmp + c.lane * a.pstr + c.lp;
+#pragma unroll
+  for (int i = 0; i < kSeg; ++i) {
+    const int x = x0 + i;
+    if (x < a.s) {
+      const float* tp = trow + c.sh->h_min[x];
+      const float* wp = c.h_w + x * a.kstride;
+      float acc = 0.f;
+      for (int j = 0; j < c.sh->kh_max; ++j) acc = fmaf(tp[j], wp[j], acc);
+      o[i] = acc * post;
+    }
+  }
+}
+
+template <bool kBulk, bool kWindow>
 __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
   SmemHeader& sh = *reinterpret_cast<SmemHeader*>(smem);
@@ -114,26 +315,14 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
   const int y0 = band * kBandRows;
   const int nrows = min(kBandRows, s - y0);
   const int lp = P.left & 1;                    // pair alignment of the crop's first column
-  const int npairs = (lp + P.w + 1) >> 1;
   const int64_t plane_base = (int64_t)P.img * a.img_stride + (int64_t)chan * a.H * a.W;
   const int64_t e0 = plane_base + (int64_t)P.top * a.W + P.left;   // element index of crop (0,0)
-  const int e0_lo = (int)(e0 & 7);
 
   // ---- tap tables + barriers ------------------------------------------------------------
-  {
-    const float vscale = (float)P.h / (float)s;
-    const float hscale = (float)P.w / (float)s;
-    const float vsup = vscale >= 1.f ? vscale : 1.f, vinv = vscale >= 1.f ? 1.f / vscale : 1.f;
-    const float hsup = hscale >= 1.f ? hscale : 1.f, hinv = hscale >= 1.f ? 1.f / hscale : 1.f;
-    for (int idx = tid; idx < nrows + s; idx += kThreads) {
-      if (idx < nrows)
-        aa_taps(y0 + idx, P.h, vscale, vsup, vinv, a.kv, sh.v_min[idx], sh.v_size[idx], v_w + idx * a.kv);
-      else {
-        const int x = idx - nrows;
-        aa_taps(x, P.w, hscale, hsup, hinv, a.kh, sh.h_min[x], sh.h_size[x], h_w + x * a.kh);
-      }
-    }
-    if (kBulk && tid == 0) {
+  if (tid == 0) {
+    sh.kv_max = 0;
+    sh.kh_max = 0;
+    if (kBulk) {
       for (int i = 0; i < a.nch; ++i) {
         mbar_init(&sh.full[i], 1);
         mbar_init(&sh.empty[i], kConsumerWarps);
@@ -142,9 +331,48 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
     }
   }
   __syncthreads();
-
-  const int r_lo = sh.v_min[0];
-  const int r_hi = sh.v_min[nrows - 1] + sh.v_size[nrows - 1];
+  {
+    const float vscale = (float)P.h / (float)s;
+    const float hscale = (float)P.w / (float)s;
+    const float vsup = vscale >= 1.f ? vscale : 1.f, vinv = vscale >= 1.f ? 1.f / vscale : 1.f;
+    const float hsup = hscale >= 1.f ? hscale : 1.f, hinv = hscale >= 1.f ? 1.f / hscale : 1.f;
+    for (int idx = tid; idx < nrows + s; idx += kThreads) {
+      int lo, size;
+      if (idx < nrows) {
+        aa_taps(y0 + idx, P.h, vscale, vsup, vinv, a.kstride, 2, lo, size, v_w + idx * a.kstride * 2);
+        sh.v_info[idx] = make_int4(lo, size, 0, 0);
+        atomicMax(&sh.kv_max, size);
+      } else {
+        const int x = idx - nrows;
+        aa_taps(x, P.w, hscale, hsup, hinv, a.kstride, 1, lo, size, h_w + x * a.kstride);
+        sh.h_min[x] = lo;
+        atomicMax(&sh.kh_max, size);
+      }
+    }
+  }
+  __syncthreads();
+  const int r_lo = sh.v_info[0].x;
+  const int r_hi = sh.v_info[nrows - 1].x + sh.v_info[nrows - 1].y;
+  if (tid < nrows) {   // chunk bookkeeping of each band row (uses the unrolled tap count, see below)
+    int4 info = sh.v_info[tid];
+    info.w = (info.x - r_lo) / kChunkRows;
+    sh.v_info[tid] = info;
+  }
+  // unrolled tap counts of this view (uniform over the CTA)
+  auto round_k = [](int k) { return k <= 3 ? 3 : k <= 5 ? 5 : k <= 7 ? 7 : k <= 9 ? 9 : k <= 13 ? 13 : 0; };
+  const int KV = round_k(sh.kv_max);
+  const int KH = round_k(sh.kh_max);
+  const int total_chunks = (r_hi - r_lo + kChunkRows - 1) / kChunkRows;
+  __syncthreads();
+  if (tid < nrows) {
+    int4 info = sh.v_info[tid];
+    // rows [ymin, ymin+KV) are read (zero weights beyond the window): they only need to be *loaded*
+    // when they carry weight, but they must never be overwritten mid-read -> wait for the real window.
+    const int last = info.x + info.y - 1 - r_lo;
+    info.z = min(last / kChunkRows + 1, total_chunks);
+    sh.v_info[tid] = info;
+  }
+  __syncthreads();
 
   float o[kSeg];     // this thread's 32 output pixels (row y0+lane, columns 32*warp ..)
 #pragma unroll
@@ -153,103 +381,57 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
   if (warp == kConsumerWarps) {
     // ================================ producer warp =======================================
     if (kBulk && lane == 0) {
-      const int total_chunks = (r_hi - r_lo + kChunkRows - 1) / kChunkRows;
+      const int ph = (int)(e0 & 7);                          // W % 8 == 0: same phase for every row
+      const uint32_t nb = (uint32_t)((ph + P.w + 7) >> 3) << 4;
       for (int ci = 0; ci < total_chunks; ++ci) {
-        const int slot = ci % a.nch;
-        if (ci >= a.nch) mbar_wait(&sh.empty[slot], ((ci / a.nch) - 1) & 1);
+        const int slot = ci & (a.nch - 1);
+        if (ci >= a.nch) mbar_wait(&sh.empty[slot], ((ci >> a.nch_log2) - 1) & 1);
         const int rbeg = r_lo + ci * kChunkRows;
         const int rend = min(rbeg + kChunkRows, r_hi);
-        uint32_t total = 0;
-        for (int r = rbeg; r < rend; ++r) {
-          const int ph = (e0_lo + r * a.W) & 7;
-          total += (uint32_t)((ph + P.w + 7) >> 3) << 4;
-        }
-        mbar_arrive_expect_tx(&sh.full[slot], total);
-        for (int r = rbeg; r < rend; ++r) {
-          const int64_t e = e0 + (int64_t)r * a.W;
-          const int ph = (int)(e & 7);
-          const uint32_t nb = (uint32_t)((ph + P.w + 7) >> 3) << 4;
-          bulk_g2s(ring + (size_t)(slot * kChunkRows + (r - rbeg)) * a.pitch, a.src + (e - ph), nb, &sh.full[slot]);
-        }
+        mbar_arrive_expect_tx(&sh.full[slot], nb * (uint32_t)(rend - rbeg));
+        for (int r = rbeg; r < rend; ++r)
+          bulk_g2s(ring + (size_t)(slot * kChunkRows + (r - rbeg)) * a.pitch, a.src + (e0 + (int64_t)r * a.W - ph), nb,
+                   &sh.full[slot]);
       }
     }
     __syncwarp();
   } else {
-    // ================================ V pass ==============================================
-    const int ring_rows = a.nch * kChunkRows;
-    float* tmp_e = tmp;
-    float* tmp_o = tmp + kBandRows * a.pstr;
-    const uint16_t* gplane = a.src + (e0 - lp);     // 4-byte aligned (W even)
-    int loaded = 0, released = 0;
-    for (int yy = 0; yy < nrows; ++yy) {
-      const int ymin = sh.v_min[yy];
-      const int n = sh.v_size[yy];
-      int sr0 = 0;
-      if (kBulk) {
-        const int need = (ymin + n - 1 - r_lo) / kChunkRows + 1;
-        while (loaded < need) {
-          mbar_wait(&sh.full[loaded % a.nch], (loaded / a.nch) & 1);
-          ++loaded;
-        }
-        const int first = (ymin - r_lo) / kChunkRows;
-        while (released < first) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sh.empty[released % a.nch]);
-          ++released;
-        }
-        sr0 = (ymin - r_lo) % ring_rows;
-      }
-      const float* wrow = v_w + yy * a.kv;
-      for (int q = tid; q < npairs; q += kConsumerThreads) {
-        float a0 = 0.f, a1 = 0.f;
-        int sr = sr0;
-        for (int j = 0; j < n; ++j) {
-          const int r = ymin + j;
-          uint32_t p;
-          if (kBulk) {
-            const int orow = ((e0_lo + r * a.W) & 7) - lp;      // element offset of pair 0 in the slot row
-            p = *reinterpret_cast<const uint32_t*>(ring + (size_t)sr * a.pitch + 2 * orow + 4 * q);
-            if (++sr == ring_rows) sr = 0;
-          } else {
-            p = __ldg(reinterpret_cast<const uint32_t*>(gplane + (int64_t)r * a.W) + q);
-          }
-          float f0 = (float)(p & 0xffffu);
-          float f1 = (float)(p >> 16);
-          if (kWindow) {
-            f0 = fminf(fmaxf((f0 - a.win_lo) * a.win_scale, 0.f), 1.f);
-            f1 = fminf(fmaxf((f1 - a.win_lo) * a.win_scale, 0.f), 1.f);
-          }
-          const float w = wrow[j];
-          a0 = fmaf(f0, w, a0);
-          a1 = fmaf(f1, w, a1);
-        }
-        tmp_e[yy * a.pstr + q] = a0;
-        tmp_o[yy * a.pstr + q] = a1;
-      }
+    Ctx c;
+    c.a = &a;
+    c.sh = &sh;
+    c.v_w = v_w;
+    c.h_w = h_w;
+    c.tmp = tmp;
+    c.ring = ring;
+    c.gplane = a.src + (e0 - lp);
+    c.tid = tid;
+    c.lane = lane;
+    c.warp = warp;
+    c.nrows = nrows;
+    c.lp = lp;
+    c.npairs = (lp + P.w + 1) >> 1;
+    c.w = P.w;
+    c.h = P.h;
+    c.r_lo = r_lo;
+    c.ring_byte0 = 2 * ((int)(e0 & 7) - lp);
+    switch (KV) {
+      case 3: v_pass<3, kBulk, kWindow>(c); break;
+      case 5: v_pass<5, kBulk, kWindow>(c); break;
+      case 7: v_pass<7, kBulk, kWindow>(c); break;
+      case 9: v_pass<9, kBulk, kWindow>(c); break;
+      case 13: v_pass<13, kBulk, kWindow>(c); break;
+      default: v_pass_dyn<kBulk, kWindow>(c); break;
     }
     bar_sync(1, kConsumerThreads);
-
-    // ================================ H pass ==============================================
-    // lane = band row, warp = 32-column segment; crop column k lives in plane (k+lp)&1 at (k+lp)>>1
-    const int x0 = warp * kSeg;
-    if (x0 < s) {
-      const float* trow_e = tmp_e + lane * a.pstr;
-      const float* trow_o = tmp_o + lane * a.pstr;
+    if (warp * kSeg < s) {
       const float post = kWindow ? 1.f : (1.f / 65535.f);
-#pragma unroll
-      for (int i = 0; i < kSeg; ++i) {
-        const int x = x0 + i;
-        if (x < s) {
-          const int n = sh.h_size[x];
-          int k = sh.h_min[x] + lp;
-          const float* wrow = h_w + x * a.kh;
-          float acc = 0.f;
-          for (int j = 0; j < n; ++j, ++k) {
-            const float v = (k & 1) ? trow_o[k >> 1] : trow_e[k >> 1];
-            acc = fmaf(v, wrow[j], acc);
-          }
-          o[i] = acc * post;
-        }
+      switch (KH) {
+        case 3: h_pass<3>(c, o, post); break;
+        case 5: h_pass<5>(c, o, post); break;
+        case 7: h_pass<7>(c, o, post); break;
+        case 9: h_pass<9>(c, o, post); break;
+        case 13: h_pass<13>(c, o, post); break;
+        default: h_pass_dyn(c, o, post); break;
       }
     }
   }
@@ -304,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
     const bool flip = (P.flags & MIS_VIEW_FLIP) != 0;
     const size_t row_off = ((size_t)plane * s + (y0 + lane)) * s;
     const bool full = (x0 + kSeg <= s) && ((s & 7) == 0);
-    if (kOutF32) {
+    if (a.out_f32) {
       float* out = reinterpret_cast<float*>(a.out) + row_off;
       if (full) {
         if (!flip) {
@@ -353,9 +535,9 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
 
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-template <bool kBulk, bool kWindow, bool kOutF32>
+template <bool kBulk, bool kWindow>
 static int launch(const Args& a, int grid, size_t smem, cudaStream_t stream) {
-  auto* fn = &aug_kernel<kBulk, kWindow, kOutF32>;
+  auto* fn = &aug_kernel<kBulk, kWindow>;
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
@@ -418,41 +600,42 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
   a.out = out;
   a.s = s;
   a.nbands = (s + kBandRows - 1) / kBandRows;
+  a.out_f32 = out_dtype == MIS_DTYPE_F32 ? 1 : 0;
   // worst-case taps per axis: support = max(size/s, 1), K = 2*ceil(support) + 1
   auto kmax = [&](int n) { int sup = (n + s - 1) / s; if (sup < 1) sup = 1; return 2 * sup + 1; };
-  a.kv = kmax(H);
-  a.kh = kmax(W);
-  a.nch = (a.kv + kChunkRows - 1) / kChunkRows + 3;
+  const int kbound = kmax(H) > kmax(W) ? kmax(H) : kmax(W);
+  const int kunroll = kbound <= 3 ? 3 : kbound <= 5 ? 5 : kbound <= 7 ? 7 : kbound <= 9 ? 9 : kbound <= 13 ? 13 : kbound;
+  a.kstride = align_up(kunroll, 4);
+  // ring: the widest read window (kunroll rows) plus the chunk being filled; power of two for cheap wrap
+  int nch = 4;
+  while (nch * kChunkRows < kunroll + 2 * kChunkRows) nch *= 2;
+  a.nch = nch;
+  a.nch_log2 = 0;
+  while ((1 << a.nch_log2) < nch) ++a.nch_log2;
   MIS_REQUIRE(a.nch <= kMaxChunks, MIS_ERR_UNSUPPORTED,
               "mis_aug_two_view: H/s = %d/%d needs a %d-chunk ring (max %d)", H, s, a.nch, kMaxChunks);
+  // TMA staging needs one 16-byte phase for all rows of a crop (W % 8 == 0); otherwise plain loads
+  const bool bulk = use_tma && (W % 8 == 0) && (img_stride % 8 == 0);
   a.pitch = align_up(2 * W + 32, 16);
-  a.pstr = (W / 2 + 1) | 1;
+  a.pstr = (W + 2 + a.kstride + 2) | 1;
   int off = align_up((int)sizeof(SmemHeader), 16);
   a.off_vw = off;
-  off += align_up(kBandRows * a.kv * 4, 16);
+  off += align_up(kBandRows * a.kstride * 2 * 4, 16);
   a.off_hw = off;
-  off += align_up(s * a.kh * 4, 16);
+  off += align_up(s * a.kstride * 4, 16);
   a.off_tmp = off;
-  off += align_up(2 * kBandRows * a.pstr * 4, 128);
+  off += align_up(kBandRows * a.pstr * 4, 128);
   a.off_ring = off;
-  if (use_tma) off += a.nch * kChunkRows * a.pitch;
+  if (bulk) off += a.nch * kChunkRows * a.pitch;
   const size_t smem = (size_t)off;
   MIS_REQUIRE(smem <= 227 * 1024, MIS_ERR_UNSUPPORTED,
               "mis_aug_two_view: needs %zu B of shared memory per CTA (H=%d W=%d s=%d)", smem, H, W, s);
 
   const bool window = !(win_lo == 0.f && win_hi == 65535.f);
-  const bool f32 = out_dtype == MIS_DTYPE_F32;
   const int grid = a.nbands * n_views * C;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define MIS_AUG_DISPATCH(B, Wd, F) return launch<B, Wd, F>(a, grid, smem, st)
-  if (use_tma) {
-    if (window) { if (f32) MIS_AUG_DISPATCH(true, true, true); else MIS_AUG_DISPATCH(true, true, false); }
-    else        { if (f32) MIS_AUG_DISPATCH(true, false, true); else MIS_AUG_DISPATCH(true, false, false); }
-  } else {
-    if (window) { if (f32) MIS_AUG_DISPATCH(false, true, true); else MIS_AUG_DISPATCH(false, true, false); }
-    else        { if (f32) MIS_AUG_DISPATCH(false, false, true); else MIS_AUG_DISPATCH(false, false, false); }
-  }
-#undef MIS_AUG_DISPATCH
+  if (bulk) return window ? launch<true, true>(a, grid, smem, st) : launch<true, false>(a, grid, smem, st);
+  return window ? launch<false, true>(a, grid, smem, st) : launch<false, false>(a, grid, smem, st);
 }
 
 extern "C" int64_t mis_aug_algorithmic_bytes(const MisViewParams* p, int n_views, int C, int s, int out_dtype) {

@@ -143,7 +143,10 @@ def test_argument_errors_mirror_reference_style():
         t(torch.zeros(1, 1, 64, 64, dtype=torch.float32).cuda())
     with pytest.raises(NotImplementedError):          # odd width
         t(torch.zeros(1, 1, 64, 63, dtype=torch.uint16).cuda())
+    from medical_image_segmentation_b200.transforms import FusedTwoViewTransforms
     with pytest.raises(NotImplementedError):          # 3 channels
+        FusedTwoViewTransforms(32, (0.5,) * 3, (0.2,) * 3)(torch.zeros(1, 3, 64, 64, dtype=torch.uint16).cuda())
+    with pytest.raises(ValueError):                   # mean/std length must match the channel count
         t(torch.zeros(1, 3, 64, 64, dtype=torch.uint16).cuda())
     with pytest.raises(NotImplementedError):
         _mk(300)(torch.zeros(1, 1, 64, 64, dtype=torch.uint16).cuda())
