@@ -127,38 +127,40 @@ int64_t mis_aug_algorithmic_bytes(const MisViewParams* params_host, int n_views,
  * sit at row offset row0 of the rank-major all-gathered matrix of `cols` = 2N rows.  The
  * positive of local row i is local row (i + rows/2) mod rows.
  *
- *   mis_ntxent_prep      z [rows, D] (f32 or bf16) -> u = z/max(|z|,1e-12) rounded to TF32
- *                        (f32 container), rinv = 1/max(|z|,1e-12), pos = <u_i,u_p(i)>/T (fp32)
- *   mis_ntxent_fwd       lse_i = log sum_{j != g(i)} exp(<u_i,u_j>/T) over all `cols` columns
- *                        (tcgen05 kind::tf32, accumulators in TMEM; S never leaves the SM) and
- *                        loss = mean_i (lse_i - pos_i) over the local rows
- *   mis_ntxent_bwd       dz_local = sum_r' dL_r'/dz_local  (option L: needs the
- *                        all-gathered lse) scaled by grad_scale; fused recompute of S, the
- *                        (P + P^T - 2*onehot) tile stays in TMEM as the A operand of the second MMA
+ *   mis_ntxent_prep   z [rows, D] (f32 or bf16) -> u = z/max(|z|,1e-12) rounded to TF32 (f32
+ *                     container) and rinv = 1/max(|z|,1e-12).  u is what gets all-gathered.
+ *   mis_ntxent_fwd    lse_i = log sum_{j != g(i)} exp(<u_i,u_j>/T) over all `cols` columns (tcgen05
+ *                     kind::tf32, accumulators in TMEM; S never leaves the SM);
+ *                     loss[0] = mean_i (lse_i - <u_i,u_p(i)>/T) over the local rows.
+ *   mis_ntxent_bwd    dz_local = grad_out[0] * grad_scale * sum_r' dL_r'/dz_local  (SURVEY A.5,
+ *                     option L: uses the all-gathered lse instead of a D-wide gradient exchange).
+ *                     S is recomputed tile by tile; W = P + P^T is rounded to TF32 and stays in
+ *                     TMEM as the A operand of the second MMA; dU (128 x D fp32) stays in TMEM for
+ *                     the whole column walk.  grad_out may be NULL (= 1).  dz has z's dtype.
  *
- * D % 32 == 0, 32 <= D <= 256; rows % 128 == 0; cols % 128 == 0; T >= 0.025.
- * scratch sizes are returned by mis_ntxent_scratch_bytes().
+ * rows, cols, row0 multiples of 128; D a multiple of 32, 32 <= D <= 256; T >= 0.025.
+ * `scratch` must hold mis_ntxent_scratch_bytes(rows, cols, D) bytes.
  * ------------------------------------------------------------------------------------------ */
 int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D);
 
-int mis_ntxent_prep(const void* z, int z_dtype, int rows, int D, float inv_T, float* u,
-                    float* rinv, float* pos, void* stream);
+int mis_ntxent_prep(const void* z, int z_dtype, int rows, int D, float* u, float* rinv, void* stream);
 
 int mis_ntxent_fwd(const float* u_all, int cols, int D, int row0, int rows, float inv_T,
-                   const float* pos, float* lse_rows, float* loss, void* scratch,
-                   int64_t scratch_bytes, void* stream);
+                   float* lse_rows, float* loss, void* scratch, int64_t scratch_bytes, void* stream);
 
-int mis_ntxent_bwd(const float* u_all, const float* lse_all, const float* rinv_rows, int cols, int D,
-                   int row0, int rows, float inv_T, float grad_scale, const float* grad_out,
-                   void* dz, int dz_dtype, void* scratch, int64_t scratch_bytes, void* stream);
+int mis_ntxent_bwd(const float* u_all, const float* lse_all, const void* z_rows, int z_dtype,
+                   const float* rinv_rows, int cols, int D, int row0, int rows, float inv_T,
+                   float grad_scale, const float* grad_out, void* dz, void* scratch,
+                   int64_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * BYOL cosine loss, fused forward + backward (the loss the reference actually trains with):
- *   loss = 2 - 2 * mean_i <p_i/|p_i|, t_i/|t_i|>          byol_pytorch.py:196-198
- *   dpreds = grad_scale * dloss/dpreds (targets carry no gradient, :212-214)
+ *   loss[0] = 2 - 2 * mean_i <p_i/|p_i|, t_i/|t_i|>        byol_pytorch.py:196-198
+ *   dpreds  = dloss/dpreds (may be NULL; targets carry no gradient, byol_pytorch.py:212-214)
+ *   scratch_rows: `rows` floats.
  * ------------------------------------------------------------------------------------------ */
 int mis_byol_loss_fwd_bwd(const float* preds, const float* targets, int rows, int D, float* loss,
-                          float* dpreds, void* stream);
+                          float* dpreds, float* scratch_rows, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,14 +36,14 @@ EXPORTS = {
                                    C.c_int, C.c_void_p]),
     "mis_aug_algorithmic_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mis_ntxent_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
-    "mis_ntxent_prep": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
-                                  C.c_void_p, C.c_void_p]),
+    "mis_ntxent_prep": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mis_ntxent_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    "mis_ntxent_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-                                 C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+                                 C.c_void_p, C.c_int64, C.c_void_p]),
+    "mis_ntxent_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                 C.c_void_p]),
     "mis_byol_loss_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                        C.c_void_p]),
+                                        C.c_void_p, C.c_void_p]),
 }
 
 

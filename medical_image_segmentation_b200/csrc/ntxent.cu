@@ -1,17 +1,704 @@
-// placeholder -- replaced by the tcgen05 kernels
+// K2/K3 -- NT-Xent (SimCLR InfoNCE) forward and backward on tcgen05 tensor cores (sm_100a).
+//
+// The 2N x 2N similarity matrix is never written to HBM.  One CTA owns a 128-row tile of the
+// local rows and walks a range of 128-column tiles of the all-gathered matrix:
+//
+//   warp 0   TMA producer: 128B-swizzled K-major boxes of U (and, for the backward, of U^T) into a
+//            shared-memory ring, one mbarrier pair per stage;
+//   warp 1   MMA issuer (one thread): S = U_I . U_J^T with tcgen05.mma kind::tf32, accumulator in
+//            TMEM (double buffered, 2 x 128 columns); backward only: dU_I += W . U_J with the A
+//            operand W read straight from TMEM and dU_I (128 x D fp32) resident in TMEM columns
+//            256.. for the whole column walk;
+//   warps 2-5 epilogue, lane == row (tcgen05.ld 32x32b): exp2 with the fixed max 1/T, diagonal mask;
+//            forward: thread-local row sums (no shuffles);  backward: W_ij = E_ij (c_i + c_j) rounded
+//            to TF32 and stored back over S with tcgen05.st, so the tile never leaves the SM.
+//
+// Math (oracle/loss_oracle.py):  u = z/max(|z|,1e-12), S = u u^T / T,
+//   lse_i = log sum_{j != i} exp S_ij,   L_r = mean_{i in rank r} (lse_i - S_{i,p(i)}),
+//   dU_i = (g/(T rows)) [ sum_j (exp(S_ij - lse_i) + exp(S_ij - lse_j)) u_j  -  2 u_p(i) ],
+//   dz_i = (dU_i - u_i <u_i,dU_i>) / max(|z_i|,1e-12).
+// With E_ij = exp(S_ij - 1/T) and c_j = exp(1/T - lse_j):  exp(S_ij - lse_i) + exp(S_ij - lse_j)
+// = E_ij (c_i + c_j): one exp per element.  S_ij <= 1/T always, so 1/T is a valid fixed maximum
+// (requires exp(-2/T) to stay normal in fp32: T >= 0.025).
+//
+// Operand precision: U is rounded to TF32 (round-to-nearest) once by the prep kernel, products
+// accumulate in fp32; positives, the one-hot term and the normalisation Jacobian are done in
+// plain fp32.  Measured gradient error vs the fp64 oracle ~2e-4 relative (bf16 operands would
+// give 1.6e-3 and miss the 1e-3 gate).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
 #include "common.cuh"
+
+namespace mis {
+namespace ntx {
+
+constexpr int kTile = 128;             // rows per CTA tile, columns per S tile
+constexpr int kKBlock = 32;            // fp32 elements per 128-byte swizzle row
+constexpr int kStageBytes = 32 * 1024; // A k-block (16 KB) + B k-block (16 KB), or one U^T k-block (D*128 B)
+constexpr int kStages = 6;
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kTmemCols = 512;
+constexpr int kDuCol = 256;            // TMEM column where the dU accumulator starts
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct TileArgs {
+  int rows, cols, D, row0;
+  int col_tiles, tiles_per_split;
+  float k1;                // log2(e) / T
+  const float* cexp;       // [cols] exp(1/T - lse_j)            (backward)
+  float* partial;          // fwd: [nsplit][rows]   bwd: [nsplit][rows][D]
+};
+
+struct Bars {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full[2];
+  uint64_t epi_done[2];
+  uint64_t du_full;
+  uint32_t tmem_ptr;
+  uint32_t pad;
+  float cj[2][kTile];
+};
+
+// ---- tcgen05 / TMA wrappers -----------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc(const void* smem_ptr) {
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fffu);        // start address            bits [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset       bits [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// fp32 accumulate, TF32 x TF32, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
+  return y;
+}
+
+template <bool kBwd>
+__global__ void __launch_bounds__(kThreads, 1)
+ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_ut,
+                   const TileArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Bars& bars = *reinterpret_cast<Bars*>(smem + kStages * kStageBytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row_tile = blockIdx.x, split = blockIdx.y;
+  const int t_begin = split * a.tiles_per_split;
+  const int T = min(a.tiles_per_split, a.col_tiles - t_begin);
+  const int KB = a.D / kKBlock;
+  const int g_row_tile0 = a.row0 + row_tile * kTile;   // global row index of this tile's first row
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_u);
+    if (kBwd) prefetch_tmap(&map_ut);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kStages; ++i) {
+        mbar_init(&bars.full[i], 1);
+        mbar_init(&bars.empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars.tmem_full[i], 1);
+        mbar_init(&bars.epi_done[i], kEpiThreads);
+      }
+      mbar_init(&bars.du_full, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_ptr)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      auto advance = [&]() {
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      auto push_s = [&](int t) {   // operands of S = U_I . U_J^T, one stage per 32-wide k-block
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&bars.empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          mbar_arrive_expect_tx(&bars.full[stage], 2 * kTile * 128);
+          tma_load_2d(sa, &map_u, kb * kKBlock, g_row_tile0, &bars.full[stage]);
+          tma_load_2d(sa + kTile * 128, &map_u, kb * kKBlock, (t_begin + t) * kTile, &bars.full[stage]);
+          advance();
+        }
+      };
+      auto push_g = [&](int t) {   // U^T boxes [D x 32 columns] for dU += W . U_J
+        for (int kb = 0; kb < kTile / kKBlock; ++kb) {
+          mbar_wait(&bars.empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bars.full[stage], a.D * 128);
+          tma_load_2d(smem + stage * kStageBytes, &map_ut, (t_begin + t) * kTile + kb * kKBlock, 0, &bars.full[stage]);
+          advance();
+        }
+      };
+      for (int t = 0; t < T; ++t) {
+        push_s(t);
+        if (kBwd && t >= 1) push_g(t - 1);
+      }
+      if (kBwd) push_g(T - 1);
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ========================================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      auto advance = [&]() {
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      const uint32_t idesc_s = make_idesc(kTile, kTile);
+      const uint32_t idesc_g = make_idesc(kTile, a.D);
+      auto mma_g = [&](int t) {    // dU += W(t) . U_J(t);  W lives in TMEM where S(t) was
+        const int pb = t & 1;
+        mbar_wait(&bars.epi_done[pb], (t >> 1) & 1);
+        tc_fence_after();
+        for (int kb = 0; kb < kTile / kKBlock; ++kb) {
+          mbar_wait(&bars.full[stage], phase);
+          tc_fence_after();
+          const uint64_t bd = make_desc(smem + stage * kStageBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ts(tmem + kDuCol, tmem + pb * kTile + kb * kKBlock + k * 8, bd + (uint64_t)(k * 2), idesc_g,
+                   (uint32_t)((t | kb | k) != 0));
+          tc_commit(&bars.empty[stage]);
+          advance();
+        }
+      };
+      for (int t = 0; t < T; ++t) {
+        const int buf = t & 1;
+        if (!kBwd && t >= 2) {     // forward: S[buf] is free once the epilogue of tile t-2 has read it
+          mbar_wait(&bars.epi_done[buf], ((t - 2) >> 1) & 1);
+          tc_fence_after();
+        }
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&bars.full[stage], phase);
+          tc_fence_after();
+          const uint8_t* sa = smem + stage * kStageBytes;
+          const uint64_t ad = make_desc(sa), bd = make_desc(sa + kTile * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ss(tmem + buf * kTile, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_s, (uint32_t)((kb | k) != 0));
+          tc_commit(&bars.empty[stage]);
+          advance();
+        }
+        tc_commit(&bars.tmem_full[buf]);
+        if (kBwd && t >= 1) mma_g(t - 1);
+      }
+      if (kBwd) {
+        mma_g(T - 1);
+        tc_commit(&bars.du_full);
+      }
+    }
+  } else {
+    // ===================================== epilogue ==========================================
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int r_in = quad * 32 + lane;               // row inside the tile == TMEM lane
+    const int etid = tid - 64;
+    const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+    const float ci = kBwd ? a.cexp[g_row_tile0 + r_in] : 0.f;
+    const float k1 = a.k1;
+    const int il = row_tile * kTile + r_in;                       // local row index
+    const int pos_col = a.row0 + (il + (a.rows >> 1)) % a.rows;   // global column of this row's positive
+    float rowsum = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int buf = t & 1;
+      const int col0 = (t_begin + t) * kTile;
+      if (kBwd) {
+        bars.cj[buf][etid] = a.cexp[col0 + etid];
+        bar_sync(2, kEpiThreads);
+      }
+      mbar_wait(&bars.tmem_full[buf], (t >> 1) & 1);
+      tc_fence_after();
+      // special tiles: the diagonal (self-similarity is excluded) and, for the backward, the tile(s)
+      // holding this row's positive -- its one-hot is folded into W *before* the TF32 rounding, so
+      // the cancellation P_ip + P_pi - 2 keeps full relative precision.
+      const bool diag = (col0 == g_row_tile0);
+      const int jpos = kBwd ? (pos_col - col0) : -1;
+      const bool special = diag || (jpos >= 0 && jpos < kTile);
+#pragma unroll 1
+      for (int c = 0; c < kTile / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + tlane + (uint32_t)(buf * kTile + c * 32);
+        tmem_ld32(taddr, v);
+        tmem_wait_ld();
+        if (!special) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float e = ex2f(fmaf(__uint_as_float(v[j]), k1, -k1));
+            if (kBwd)
+              v[j] = to_tf32(e * (ci + bars.cj[buf][c * 32 + j]));
+            else
+              rowsum += e;
+          }
+        } else {
+          const int jd = diag ? (r_in - c * 32) : -1;   // position of the diagonal inside this chunk
+          const int jp = jpos - c * 32;                 // position of the positive inside this chunk
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float e = ex2f(fmaf(__uint_as_float(v[j]), k1, -k1));
+            if (j == jd) e = 0.f;
+            if (kBwd) {
+              float w = e * (ci + bars.cj[buf][c * 32 + j]);
+              if (j == jp) w -= 2.f;
+              v[j] = to_tf32(w);
+            } else {
+              rowsum += e;
+            }
+          }
+        }
+        if (kBwd) tmem_st32(taddr, v);
+      }
+      if (kBwd) tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars.epi_done[buf]);
+    }
+    if (!kBwd) {
+      a.partial[(size_t)split * a.rows + row_tile * kTile + r_in] = rowsum;
+    } else {
+      mbar_wait(&bars.du_full, 0);
+      tc_fence_after();
+      float* dst = a.partial + ((size_t)split * a.rows + row_tile * kTile + r_in) * a.D;
+      for (int c = 0; c < a.D / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem + tlane + (uint32_t)(kDuCol + c * 32), v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<uint4*>(dst + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---- small kernels ------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float load_as_f32(const T* p, size_t i);
+template <>
+__device__ __forceinline__ float load_as_f32<float>(const float* p, size_t i) { return p[i]; }
+template <>
+__device__ __forceinline__ float load_as_f32<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) { return __bfloat162float(p[i]); }
+
+// one warp per row: rinv = 1/max(|z|,1e-12), u = tf32(z * rinv)
+template <typename T>
+__global__ void prep_kernel(const T* __restrict__ z, int rows, int D, float* __restrict__ u, float* __restrict__ rinv) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = load_as_f32(z, (size_t)row * D + d);
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float r = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int d = lane; d < D; d += 32)
+    u[(size_t)row * D + d] = __uint_as_float(to_tf32(load_as_f32(z, (size_t)row * D + d) * r));
+  if (lane == 0) rinv[row] = r;
+}
+
+// U [cols, D] -> U^T [D, cols]
+__global__ void transpose_kernel(const float* __restrict__ u, float* __restrict__ ut, int cols, int D) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) tile[i][threadIdx.x] = u[(size_t)(c0 + i) * D + d0 + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) ut[(size_t)(d0 + i) * cols + c0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+__global__ void cexp_kernel(const float* __restrict__ lse, float* __restrict__ cexp, int cols, float inv_T) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < cols) cexp[j] = expf(inv_T - lse[j]);
+}
+
+// lse_i = 1/T + log(sum of split partials); pos_i = <u_i,u_p(i)>/T; loss = mean(lse - pos).  One block.
+__global__ void fwd_finalize_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ u_all, int D,
+                                    int row0, int rows, float inv_T, float* __restrict__ lse_rows,
+                                    float* __restrict__ loss) {
+  __shared__ float red[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int half = rows >> 1;
+  float acc = 0.f;
+  for (int i = warp; i < rows; i += nwarp) {
+    float s = 0.f;
+    for (int k = 0; k < nsplit; ++k) s += partial[(size_t)k * rows + i];
+    const float lse = inv_T + logf(s);
+    const float* ui = u_all + (size_t)(row0 + i) * D;
+    const float* up = u_all + (size_t)(row0 + (i + half) % rows) * D;
+    float dot = 0.f;
+    for (int d = lane; d < D; d += 32) dot = fmaf(ui[d], up[d], dot);
+    dot = warp_sum(dot);
+    if (lane == 0) {
+      lse_rows[i] = lse;
+      acc += lse - dot * inv_T;
+    }
+  }
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < nwarp; ++w) tot += red[w];
+    loss[0] = tot / (float)rows;
+  }
+}
+
+// dz_i = (dU_i - u_i <u_i,dU_i>) * rinv_i with dU_i = scale * sum_splits partial (the -2 u_p(i) one-hot term is
+// already inside W); one warp per row
+template <typename T>
+__global__ void bwd_finalize_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ u_all,
+                                    const T* __restrict__ z_rows, const float* __restrict__ rinv, int D, int row0,
+                                    int rows, float scale, const float* __restrict__ grad_out, T* __restrict__ dz) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= rows) return;
+  const int half = rows >> 1;
+  const float g = scale * (grad_out ? grad_out[0] : 1.f);
+  const float r = rinv[i];
+  float du[8], uu[8];   // D <= 256
+  float dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int d = lane + 32 * k;
+    du[k] = 0.f;
+    uu[k] = 0.f;
+    if (d < D) {
+      float s = 0.f;
+      for (int sp = 0; sp < nsplit; ++sp) s += partial[((size_t)sp * rows + i) * D + d];
+      du[k] = g * s;
+      uu[k] = load_as_f32(z_rows, (size_t)i * D + d) * r;
+      dot = fmaf(uu[k], du[k], dot);
+    }
+  }
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int d = lane + 32 * k;
+    if (d < D) {
+      const float v = (du[k] - uu[k] * dot) * r;
+      if constexpr (sizeof(T) == 4) dz[(size_t)i * D + d] = v;
+      else dz[(size_t)i * D + d] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// BYOL: loss = 2 - 2 mean cos(p_i,t_i); dp_i = -(2/n) (t^_i - cos_i p^_i)/|p_i|.  One warp per row.
+__global__ void byol_rows_kernel(const float* __restrict__ p, const float* __restrict__ t, int rows, int D,
+                                 float* __restrict__ cos_rows, float* __restrict__ dp) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= rows) return;
+  float pp = 0.f, tt = 0.f, pt = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float a = p[(size_t)i * D + d], b = t[(size_t)i * D + d];
+    pp = fmaf(a, a, pp);
+    tt = fmaf(b, b, tt);
+    pt = fmaf(a, b, pt);
+  }
+  pp = warp_sum(pp);
+  tt = warp_sum(tt);
+  pt = warp_sum(pt);
+  const float np = fmaxf(sqrtf(pp), 1e-12f), nt = fmaxf(sqrtf(tt), 1e-12f);
+  const float c = pt / (np * nt);
+  if (lane == 0) cos_rows[i] = c;
+  if (dp) {
+    const float k = -2.f / (float)rows;
+    for (int d = lane; d < D; d += 32) {
+      const float ph = p[(size_t)i * D + d] / np, th = t[(size_t)i * D + d] / nt;
+      dp[(size_t)i * D + d] = k * (th - c * ph) / np;
+    }
+  }
+}
+__global__ void byol_reduce_kernel(const float* __restrict__ cos_rows, int rows, float* __restrict__ loss) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) acc += cos_rows[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    loss[0] = 2.f - 2.f * tot / (float)rows;
+  }
+}
+
+// ---- host helpers -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// fp32 row-major [outer, inner] matrix, box [box_outer x 32 floats], 128-byte swizzle
+static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  MIS_REQUIRE(fn, MIS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {inner * sizeof(float)};
+  const cuuint32_t box[2] = {kKBlock, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MIS_REQUIRE(r == CUDA_SUCCESS, MIS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return MIS_OK;
+}
+
+struct Plan {
+  int row_tiles, col_tiles, tiles_per_split, nsplit;
+};
+static Plan make_plan(int rows, int cols) {
+  Plan p;
+  p.row_tiles = rows / kTile;
+  p.col_tiles = cols / kTile;
+  int target = 148 / p.row_tiles;
+  if (target < 1) target = 1;
+  if (target > p.col_tiles) target = p.col_tiles;
+  p.tiles_per_split = (p.col_tiles + target - 1) / target;
+  p.nsplit = (p.col_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  return p;
+}
+static inline size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
+
+static int check_shapes(const char* who, int rows, int cols, int D, int row0, float inv_T) {
+  MIS_REQUIRE(rows > 0 && cols > 0 && D > 0, MIS_ERR_INVALID_ARG, "%s: sizes must be positive", who);
+  MIS_REQUIRE(rows % kTile == 0 && cols % kTile == 0 && row0 % kTile == 0, MIS_ERR_UNSUPPORTED,
+              "%s: rows (%d), cols (%d) and row0 (%d) must be multiples of %d", who, rows, cols, row0, kTile);
+  MIS_REQUIRE(D % kKBlock == 0 && D <= 256, MIS_ERR_UNSUPPORTED, "%s: D=%d must be a multiple of 32 and <= 256", who, D);
+  MIS_REQUIRE(row0 >= 0 && row0 + rows <= cols, MIS_ERR_INVALID_ARG, "%s: rows [%d,%d) outside [0,%d)", who, row0,
+              row0 + rows, cols);
+  MIS_REQUIRE(inv_T > 0.f && inv_T <= 40.f, MIS_ERR_UNSUPPORTED,
+              "%s: temperature %g outside (0.025, inf): the fixed-max log-sum-exp needs exp(-2/T) to stay normal", who,
+              1.0 / inv_T);
+  return MIS_OK;
+}
+
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + sizeof(Bars) + 1024;
+
+}  // namespace ntx
+}  // namespace mis
+
 using namespace mis;
-extern "C" int64_t mis_ntxent_scratch_bytes(int, int, int) { return 0; }
-extern "C" int mis_ntxent_prep(const void*, int, int, int, float, float*, float*, float*, void*) {
-  return set_error(MIS_ERR_UNSUPPORTED, "not built yet");
+using namespace mis::ntx;
+
+extern "C" int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D) {
+  if (rows <= 0 || cols <= 0 || D <= 0) return -1;
+  const Plan p = make_plan(rows < kTile ? kTile : rows, cols < kTile ? kTile : cols);
+  size_t b = 0;
+  b += al256((size_t)cols * 4);                       // cexp
+  b += al256((size_t)D * cols * 4);                   // U^T
+  b += al256((size_t)p.nsplit * rows * D * 4);        // dU partials (also covers the forward's row-sum partials)
+  return (int64_t)b;
 }
-extern "C" int mis_ntxent_fwd(const float*, int, int, int, int, float, const float*, float*, float*, void*, int64_t, void*) {
-  return set_error(MIS_ERR_UNSUPPORTED, "not built yet");
+
+extern "C" int mis_ntxent_prep(const void* z, int z_dtype, int rows, int D, float* u, float* rinv, void* stream) {
+  MIS_REQUIRE(z && u && rinv, MIS_ERR_INVALID_ARG, "mis_ntxent_prep: null pointer");
+  MIS_REQUIRE(rows > 0 && D > 0, MIS_ERR_INVALID_ARG, "mis_ntxent_prep: sizes must be positive");
+  MIS_REQUIRE(z_dtype == MIS_DTYPE_F32 || z_dtype == MIS_DTYPE_BF16, MIS_ERR_INVALID_ARG, "mis_ntxent_prep: dtype %d", z_dtype);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int wpb = 8;
+  const dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
+  if (z_dtype == MIS_DTYPE_F32)
+    prep_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(z), rows, D, u, rinv);
+  else
+    prep_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(z), rows, D, u, rinv);
+  MIS_CUDA_TRY(cudaGetLastError());
+  return MIS_OK;
 }
-extern "C" int mis_ntxent_bwd(const float*, const float*, const float*, int, int, int, int, float, float, const float*, void*,
-                              int, void*, int64_t, void*) {
-  return set_error(MIS_ERR_UNSUPPORTED, "not built yet");
+
+extern "C" int mis_ntxent_fwd(const float* u_all, int cols, int D, int row0, int rows, float inv_T, float* lse_rows,
+                              float* loss, void* scratch, int64_t scratch_bytes, void* stream) {
+  MIS_REQUIRE(u_all && lse_rows && loss && scratch, MIS_ERR_INVALID_ARG, "mis_ntxent_fwd: null pointer");
+  if (int rc = check_shapes("mis_ntxent_fwd", rows, cols, D, row0, inv_T)) return rc;
+  MIS_REQUIRE(scratch_bytes >= mis_ntxent_scratch_bytes(rows, cols, D), MIS_ERR_INVALID_ARG,
+              "mis_ntxent_fwd: scratch too small (%lld < %lld)", (long long)scratch_bytes,
+              (long long)mis_ntxent_scratch_bytes(rows, cols, D));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const Plan p = make_plan(rows, cols);
+  uint8_t* sc = static_cast<uint8_t*>(scratch);
+  float* partial = reinterpret_cast<float*>(sc + al256((size_t)cols * 4) + al256((size_t)D * cols * 4));
+
+  CUtensorMap map_u;
+  if (int rc = make_map(&map_u, u_all, (uint64_t)D, (uint64_t)cols, kTile)) return rc;
+  TileArgs a = {};
+  a.rows = rows; a.cols = cols; a.D = D; a.row0 = row0;
+  a.col_tiles = p.col_tiles; a.tiles_per_split = p.tiles_per_split;
+  a.k1 = kLog2e * inv_T;
+  a.cexp = nullptr;
+  a.partial = partial;
+  auto* fn = &ntxent_tile_kernel<false>;
+  MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map_u, map_u, a);
+  MIS_CUDA_TRY(cudaGetLastError());
+  fwd_finalize_kernel<<<1, 1024, 0, st>>>(partial, p.nsplit, u_all, D, row0, rows, inv_T, lse_rows, loss);
+  MIS_CUDA_TRY(cudaGetLastError());
+  return MIS_OK;
 }
-extern "C" int mis_byol_loss_fwd_bwd(const float*, const float*, int, int, float*, float*, void*) {
-  return set_error(MIS_ERR_UNSUPPORTED, "not built yet");
+
+extern "C" int mis_ntxent_bwd(const float* u_all, const float* lse_all, const void* z_rows, int z_dtype,
+                              const float* rinv_rows, int cols, int D, int row0, int rows, float inv_T, float grad_scale,
+                              const float* grad_out, void* dz, void* scratch, int64_t scratch_bytes, void* stream) {
+  MIS_REQUIRE(u_all && lse_all && z_rows && rinv_rows && dz && scratch, MIS_ERR_INVALID_ARG, "mis_ntxent_bwd: null pointer");
+  MIS_REQUIRE(z_dtype == MIS_DTYPE_F32 || z_dtype == MIS_DTYPE_BF16, MIS_ERR_INVALID_ARG, "mis_ntxent_bwd: dtype %d", z_dtype);
+  if (int rc = check_shapes("mis_ntxent_bwd", rows, cols, D, row0, inv_T)) return rc;
+  MIS_REQUIRE(scratch_bytes >= mis_ntxent_scratch_bytes(rows, cols, D), MIS_ERR_INVALID_ARG,
+              "mis_ntxent_bwd: scratch too small (%lld < %lld)", (long long)scratch_bytes,
+              (long long)mis_ntxent_scratch_bytes(rows, cols, D));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const Plan p = make_plan(rows, cols);
+  uint8_t* sc = static_cast<uint8_t*>(scratch);
+  float* cexp = reinterpret_cast<float*>(sc);
+  float* ut = reinterpret_cast<float*>(sc + al256((size_t)cols * 4));
+  float* partial = reinterpret_cast<float*>(sc + al256((size_t)cols * 4) + al256((size_t)D * cols * 4));
+
+  cexp_kernel<<<(cols + 255) / 256, 256, 0, st>>>(lse_all, cexp, cols, inv_T);
+  MIS_CUDA_TRY(cudaGetLastError());
+  transpose_kernel<<<dim3(cols / 32, D / 32), dim3(32, 8), 0, st>>>(u_all, ut, cols, D);
+  MIS_CUDA_TRY(cudaGetLastError());
+
+  CUtensorMap map_u, map_ut;
+  if (int rc = make_map(&map_u, u_all, (uint64_t)D, (uint64_t)cols, kTile)) return rc;
+  if (int rc = make_map(&map_ut, ut, (uint64_t)cols, (uint64_t)D, (uint32_t)D)) return rc;
+  TileArgs a = {};
+  a.rows = rows; a.cols = cols; a.D = D; a.row0 = row0;
+  a.col_tiles = p.col_tiles; a.tiles_per_split = p.tiles_per_split;
+  a.k1 = kLog2e * inv_T;
+  a.cexp = cexp;
+  a.partial = partial;
+  auto* fn = &ntxent_tile_kernel<true>;
+  MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map_u, map_ut, a);
+  MIS_CUDA_TRY(cudaGetLastError());
+
+  const float scale = grad_scale * inv_T / (float)rows;
+  const int wpb = 8;
+  const dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
+  if (z_dtype == MIS_DTYPE_F32)
+    bwd_finalize_kernel<float><<<grid, block, 0, st>>>(partial, p.nsplit, u_all, static_cast<const float*>(z_rows),
+                                                        rinv_rows, D, row0, rows, scale, grad_out, static_cast<float*>(dz));
+  else
+    bwd_finalize_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(partial, p.nsplit, u_all,
+                                                                static_cast<const __nv_bfloat16*>(z_rows), rinv_rows, D,
+                                                                row0, rows, scale, grad_out,
+                                                                static_cast<__nv_bfloat16*>(dz));
+  MIS_CUDA_TRY(cudaGetLastError());
+  return MIS_OK;
+}
+
+extern "C" int mis_byol_loss_fwd_bwd(const float* preds, const float* targets, int rows, int D, float* loss,
+                                     float* dpreds, float* scratch_rows, void* stream) {
+  MIS_REQUIRE(preds && targets && loss && scratch_rows, MIS_ERR_INVALID_ARG, "mis_byol_loss_fwd_bwd: null pointer");
+  MIS_REQUIRE(rows > 0 && D > 0, MIS_ERR_INVALID_ARG, "mis_byol_loss_fwd_bwd: sizes must be positive");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int wpb = 8;
+  byol_rows_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(preds, targets, rows, D, scratch_rows, dpreds);
+  MIS_CUDA_TRY(cudaGetLastError());
+  byol_reduce_kernel<<<1, 1024, 0, st>>>(scratch_rows, rows, loss);
+  MIS_CUDA_TRY(cudaGetLastError());
+  return MIS_OK;
 }

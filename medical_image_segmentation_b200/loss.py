@@ -1,0 +1,173 @@
+"""Contrastive objectives behind the reference's loss call surface.
+
+The reference calls ``self.cosine_similarity_loss(preds, targets)`` from ``BYOL.training_step``
+(train/model/byol_pytorch.py:181-198, called at :217).  This module provides, with the same
+``(a, b) -> scalar`` shape,
+
+* ``nt_xent_loss(z_a, z_b, temperature=0.1, group=None)`` -- SimCLR NT-Xent over the embeddings of
+  ALL ranks of ``group``.  The reference itself has no NT-Xent; this is
+  the objective the north star specifies for that slot.
+* ``byol_cosine_loss(preds, targets)`` -- the loss the reference actually trains with, fused fwd+bwd.
+
+Both run only on CUDA through libmis_b200.so (tcgen05 kernels, csrc/ntxent.cu); there is no CPU or
+PyTorch fallback.  The multi-GPU exchange is one all-gather of the normalised rows in the forward
+and one all-gather of 2N log-sum-exp scalars in the backward (option L): no D-wide gradient
+reduce-scatter is needed because every rank can form both P_ij and P_ji for its own rows.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import MIS_DTYPE_BF16, MIS_DTYPE_F32
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return MIS_DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return MIS_DTYPE_BF16
+    raise TypeError(f"embeddings must be float32 or bfloat16, got {t.dtype}")
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+class CudaKernels:
+    """The three device steps of NT-Xent, bound to the C ABI (include/mis_b200.h)."""
+
+    launches = 0   # kernels launched through this class (bench.py's gpu_launches claim)
+
+    @staticmethod
+    def prep(z: torch.Tensor):
+        if not z.is_cuda:
+            raise RuntimeError("nt_xent_loss has no CPU path: embeddings must be CUDA tensors")
+        z = z.contiguous()
+        rows, D = z.shape
+        u = torch.empty((rows, D), dtype=torch.float32, device=z.device)
+        rinv = torch.empty((rows,), dtype=torch.float32, device=z.device)
+        with torch.cuda.device(z.device):
+            rc = _lib.lib.mis_ntxent_prep(z.data_ptr(), _dt(z), rows, D, u.data_ptr(), rinv.data_ptr(), _stream(z))
+        _lib.check(rc, "mis_ntxent_prep")
+        CudaKernels.launches += 1
+        return z, u, rinv
+
+    @staticmethod
+    def scratch(rows: int, cols: int, D: int, device) -> torch.Tensor:
+        n = int(_lib.lib.mis_ntxent_scratch_bytes(rows, cols, D))
+        return torch.empty((n,), dtype=torch.uint8, device=device)
+
+    @staticmethod
+    def fwd(u_all: torch.Tensor, row0: int, rows: int, inv_T: float, scratch: torch.Tensor):
+        cols, D = u_all.shape
+        lse = torch.empty((rows,), dtype=torch.float32, device=u_all.device)
+        loss = torch.empty((1,), dtype=torch.float32, device=u_all.device)
+        with torch.cuda.device(u_all.device):
+            rc = _lib.lib.mis_ntxent_fwd(u_all.data_ptr(), cols, D, row0, rows, inv_T, lse.data_ptr(), loss.data_ptr(),
+                                         scratch.data_ptr(), scratch.numel(), _stream(u_all))
+        _lib.check(rc, "mis_ntxent_fwd")
+        CudaKernels.launches += 2
+        return lse, loss
+
+    @staticmethod
+    def bwd(u_all, lse_all, z, rinv, row0: int, inv_T: float, grad_out: torch.Tensor, scratch: torch.Tensor):
+        cols, D = u_all.shape
+        rows = z.shape[0]
+        dz = torch.empty_like(z)
+        g = grad_out.to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(z.device):
+            rc = _lib.lib.mis_ntxent_bwd(u_all.data_ptr(), lse_all.data_ptr(), z.data_ptr(), _dt(z), rinv.data_ptr(),
+                                         cols, D, row0, rows, inv_T, 1.0, g.data_ptr(), dz.data_ptr(),
+                                         scratch.data_ptr(), scratch.numel(), _stream(z))
+        _lib.check(rc, "mis_ntxent_bwd")
+        CudaKernels.launches += 4
+        return dz
+
+
+def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
+    """Rank-major concatenation along dim 0 (the layout of concat_all_gather, train/callback/knn.py:143-144)."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+class _NTXent(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, temperature: float, group, kernels):
+        if z.dim() != 2 or z.shape[0] % 2:
+            raise ValueError(f"expected [2*B_local, D] rows laid out [view1; view2], got {tuple(z.shape)}")
+        distributed = group is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        world = dist.get_world_size(group) if distributed else 1
+        rank = dist.get_rank(group) if distributed else 0
+        rows = z.shape[0]
+        inv_T = 1.0 / float(temperature)
+        z, u, rinv = kernels.prep(z)
+        u_all = _all_gather_rows(u, group) if distributed else u
+        scratch = kernels.scratch(rows, u_all.shape[0], u_all.shape[1], z.device)
+        lse, loss = kernels.fwd(u_all, rank * rows, rows, inv_T, scratch)
+        ctx.save_for_backward(z, u_all, rinv, lse)
+        ctx.meta = (inv_T, group, distributed, rank, kernels, scratch)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        z, u_all, rinv, lse = ctx.saved_tensors
+        inv_T, group, distributed, rank, kernels, scratch = ctx.meta
+        lse_all = _all_gather_rows(lse, group) if distributed else lse
+        dz = kernels.bwd(u_all, lse_all, z, rinv, rank * z.shape[0], inv_T, grad_out, scratch)
+        return dz, None, None, None
+
+
+def nt_xent_rows(z: torch.Tensor, temperature: float = 0.1, group=None, _kernels=CudaKernels) -> torch.Tensor:
+    """NT-Xent for rows already laid out ``[view1_local; view2_local]`` (the output of the encoder on
+    ``cat([view1, view2])``, byol_pytorch.py:207-208).  Returns this rank's loss L_r; its
+    backward yields sum_r' dL_r'/dz_local so that DDP's 1/W gradient averaging is exact."""
+    return _NTXent.apply(z, float(temperature), group, _kernels)
+
+
+def nt_xent_loss(z_a: torch.Tensor, z_b: torch.Tensor, temperature: float = 0.1, group=None) -> torch.Tensor:
+    """Drop-in for the ``loss = self.cosine_similarity_loss(preds, targets)`` slot (byol_pytorch.py:217):
+    z_a[i] and z_b[i] are the two views of image i."""
+    if z_a.shape != z_b.shape:
+        raise ValueError(f"shape mismatch {tuple(z_a.shape)} vs {tuple(z_b.shape)}")
+    if group is None and dist.is_available() and dist.is_initialized():
+        group = dist.group.WORLD
+    return nt_xent_rows(torch.cat([z_a, z_b], dim=0), temperature, group)
+
+
+class _BYOLCosine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, preds, targets):
+        if not preds.is_cuda:
+            raise RuntimeError("byol_cosine_loss has no CPU path: inputs must be CUDA tensors")
+        if preds.shape != targets.shape or preds.dim() != 2:
+            raise ValueError(f"expected two [rows, D] tensors, got {tuple(preds.shape)} and {tuple(targets.shape)}")
+        p = preds.detach().to(torch.float32).contiguous()
+        t = targets.detach().to(torch.float32).contiguous()
+        rows, D = p.shape
+        loss = torch.empty((1,), dtype=torch.float32, device=p.device)
+        dp = torch.empty_like(p)
+        scratch = torch.empty((rows,), dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            rc = _lib.lib.mis_byol_loss_fwd_bwd(p.data_ptr(), t.data_ptr(), rows, D, loss.data_ptr(), dp.data_ptr(),
+                                                scratch.data_ptr(), _stream(p))
+        _lib.check(rc, "mis_byol_loss_fwd_bwd")
+        ctx.save_for_backward(dp)
+        ctx.in_dtype = preds.dtype
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dp,) = ctx.saved_tensors
+        return (dp * grad_out).to(ctx.in_dtype), None
+
+
+def byol_cosine_loss(preds: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    """``BYOL.cosine_similarity_loss`` (byol_pytorch.py:181-198): 2 - 2*mean cos(preds_i, targets_i).
+    Gradient flows to ``preds`` only (the reference computes targets under no_grad, :212-214)."""
+    return _BYOLCosine.apply(preds, targets)
