@@ -66,6 +66,8 @@ class FusedTwoViewTransforms:
         self.views_buffer: torch.Tensor | None = None
         self.last_params: np.ndarray | None = None
         self.launches = 0
+        self._staging = []        # ring of (pinned host table, device table, event): params stay alive while in flight
+        self._staging_idx = 0
 
     # -- parameters ---------------------------------------------------------------------------
     def draw_params(self, B: int, H: int, W: int) -> np.ndarray:
@@ -101,8 +103,7 @@ class FusedTwoViewTransforms:
         else:
             assert out.is_cuda and out.is_contiguous() and out.dtype == self.out_dtype
             assert tuple(out.shape) == (n_views, Cc, s, s)
-        host = torch.from_numpy(params_view_major.view(np.uint8).reshape(-1)).pin_memory()
-        dev = host.to(x.device, non_blocking=True)
+        dev = self._stage_params(params_view_major, x.device)
         mean_c = (C.c_float * Cc)(*mean)
         std_c = (C.c_float * Cc)(*std)
         with torch.cuda.device(x.device):
@@ -114,8 +115,27 @@ class FusedTwoViewTransforms:
                 1 if self.use_tma else 0, C.c_void_p(stream))
         _lib.check(rc, "mis_aug_two_view")
         self.launches += 1
-        self._keepalive = (dev, host)     # until the next call: the kernel reads `dev` asynchronously
         return out
+
+    def _stage_params(self, params: np.ndarray, device) -> torch.Tensor:
+        """Copy the table through one of three persistent pinned buffers (no per-call cudaHostAlloc)."""
+        nbytes = params.nbytes
+        if len(self._staging) < 3:
+            host = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
+            self._staging.append([host, torch.empty_like(host, device=device), torch.cuda.Event()])
+            slot = self._staging[-1]
+        else:
+            slot = self._staging[self._staging_idx % 3]
+            self._staging_idx += 1
+            slot[2].synchronize()                     # the copy that last used this buffer has finished
+            if slot[0].numel() < nbytes or slot[1].device != torch.device(device):
+                slot[0] = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+                slot[1] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        host, dev, ev = slot
+        host[:nbytes].numpy()[:] = params.view(np.uint8).reshape(-1)
+        dev[:nbytes].copy_(host[:nbytes], non_blocking=True)
+        ev.record(torch.cuda.current_stream(device))
+        return dev
 
     def __call__(self, x) -> list[torch.Tensor]:
         if isinstance(x, np.ndarray):

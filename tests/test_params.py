@@ -1,0 +1,74 @@
+"""Host RNG replay (csrc/rng_replay.cu) is bit-exact with the reference's parameter stream.
+
+Golden: tests/golden/params_stream.npz, recorded from the reference's own transform objects
+(torchvision RandomResizedCrop / RandomHorizontalFlip / ColorJitter hooked by oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from medical_image_segmentation_b200 import params as P
+from medical_image_segmentation_b200._lib import VIEW_PARAMS_DTYPE
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("tag", ["512x512", "256x768", "448x448"])
+def test_native_replay_matches_reference_stream(tag):
+    g = np.load(os.path.join(GOLD, "params_stream.npz"))
+    H, W = (int(v) for v in tag.split("x"))
+    torch.manual_seed(int(g["seed"]))
+    p = P.draw_two_view_params(400, H, W)
+    ints = g[f"ints_{tag}"]
+    assert np.array_equal(np.stack([p["top"], p["left"], p["h"], p["w"]], 1), ints[:, :4])
+    assert np.array_equal(p["flags"] & 1, ints[:, 4])
+    assert np.array_equal((p["flags"] >> 1) & 1, ints[:, 5])
+    jit = ints[:, 5] == 1
+    assert np.array_equal(p["order"][jit], g[f"order_{tag}"][jit].astype(np.uint8))
+    fac = g[f"fac_{tag}"]
+    for k, name in enumerate(("brightness", "contrast", "saturation", "hue")):
+        assert np.array_equal(p[name][jit].astype(np.float64), fac[jit, k])      # same float32 draws
+    assert np.array_equal(p["img"], np.repeat(np.arange(400), 2))
+    assert np.array_equal(torch.rand(4).numpy(), g[f"next_rand_{tag}"])          # generator left where torch leaves it
+
+
+@pytest.mark.parametrize("shape", [(512, 512), (64, 700), (1000, 90), (33, 33)])
+def test_native_replay_equals_torch_replay(shape):
+    H, W = shape
+    torch.manual_seed(99)
+    a = P.draw_two_view_params_torch(300, H, W)
+    nxt = torch.rand(2)
+    torch.manual_seed(99)
+    b = P.draw_two_view_params(300, H, W)
+    for name in VIEW_PARAMS_DTYPE.names:
+        assert np.array_equal(a[name], b[name]), name
+    assert torch.equal(nxt, torch.rand(2))
+
+
+def test_blur_probability_consumes_sigma_draw():
+    torch.manual_seed(5)
+    a = P.draw_two_view_params_torch(50, 128, 128, blur_prob=(1.0, 0.1))
+    torch.manual_seed(5)
+    b = P.draw_two_view_params(50, 128, 128, blur_prob=(1.0, 0.1))
+    for name in VIEW_PARAMS_DTYPE.names:
+        assert np.array_equal(a[name], b[name]), name
+
+
+def test_generator_state_crosses_mt_block_boundary():
+    """> 624 words per call forces mt19937 state regeneration inside the native code."""
+    torch.manual_seed(1)
+    a = P.draw_two_view_params(2000, 512, 512)
+    torch.manual_seed(1)
+    b = np.concatenate([P.draw_two_view_params(n, 512, 512) for n in (1, 7, 992, 1000)])
+    b["img"] = np.repeat(np.arange(2000), 2)
+    for name in VIEW_PARAMS_DTYPE.names:
+        assert np.array_equal(a[name], b[name]), name
+
+
+def test_view_major_reorder():
+    from medical_image_segmentation_b200 import FusedTwoViewTransforms
+    p = np.zeros(6, VIEW_PARAMS_DTYPE)
+    p["top"] = np.arange(6)
+    q = FusedTwoViewTransforms.to_view_major(p)
+    assert list(q["top"]) == [0, 2, 4, 1, 3, 5]
