@@ -32,7 +32,7 @@ constexpr int kBandRows = 32;
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;  // + producer warp
-constexpr int kChunkRows = 8;
+constexpr int kChunkRows = 4;
 constexpr int kMaxChunks = 16;
 constexpr int kMaxBands = 8;
 constexpr int kSeg = 32;  // output columns per H-pass warp
@@ -53,8 +53,9 @@ struct Args {
   int nch_log2;
   int pitch;        // ring row pitch in bytes (multiple of 16)
   int pstr;         // tmp row stride in words (odd)
+  int rmax;         // capacity of the input-stationary schedule (source rows per band)
   // shared-memory byte offsets
-  int off_vw, off_hw, off_tmp, off_ring;
+  int off_vw, off_hw, off_tmp, off_ring, off_sched;
 };
 
 struct SmemHeader {
@@ -65,6 +66,7 @@ struct SmemHeader {
   int4 v_info[kBandRows];     // {first source row, taps, chunks that must have landed, first chunk still needed}
   int h_min[256];
   int kv_max, kh_max;         // largest tap count of this band / this view
+  int m_max;                  // most output rows any single source row of this band feeds
 };
 
 // ---- packed fp32 pairs (Blackwell FFMA2 / FADD2) ---------------------------------------------
@@ -197,6 +199,112 @@ __device__ __forceinline__ void v_pass(const Ctx& c) {
   }
 }
 
+
+// Input-stationary schedule: source row rr of the band feeds output rows first .. first+2 of the band with the
+// (duplicated, FFMA2-ready) weights w[0..2]; rows before `first` are complete when rr is reached.
+struct __align__(16) SchedRow {
+  float w[3][2];
+  int first;
+  int pad;
+};
+
+// ---- V pass, input-stationary: every source pixel is loaded and converted ONCE ------------------------
+// Thread = one source column pair, streaming down the band's source rows in ring order with three running
+// accumulators (the output rows whose vertical window contains the current source row).
+template <bool kBulk, bool kWindow>
+__device__ __forceinline__ void v_pass_is(const Ctx& c, const SchedRow* __restrict__ sched, int nsrc) {
+  const Args& a = *c.a;
+  SmemHeader& sh = *c.sh;
+  const int q = c.tid;
+  const int npad = min(c.npairs + a.kstride / 2 + 1, a.pstr / 2);
+  const bool active = q < c.npairs;
+  const bool warp_idle = (c.warp * 32) >= c.npairs;      // no column pair of this warp lies inside the crop
+  const int pitch = a.pitch;
+  const int pstr = a.pstr;
+  const int wq = a.W >> 1;
+  // zero the few columns right of the crop that the unrolled H-pass taps may touch (weights there are 0)
+  for (int i = c.tid; i < c.nrows * 2 * (npad - c.npairs); i += kConsumerThreads) {
+    const int per = 2 * (npad - c.npairs);
+    c.tmp[(i / per) * pstr + 2 * c.npairs + (i % per)] = 0.f;
+  }
+  const uint64_t wsc = pack2(a.win_scale, a.win_scale);
+  const uint64_t wof = pack2(-a.win_lo * a.win_scale, -a.win_lo * a.win_scale);
+  const int qa = active ? q : 0;                         // inactive lanes compute on a valid address, never store
+  const uint8_t* rbase = c.ring + c.ring_byte0 + 4 * qa;
+  const uint32_t* gp = reinterpret_cast<const uint32_t*>(c.gplane + (int64_t)c.r_lo * a.W) + qa;
+  float* tp = c.tmp + 2 * qa;                            // next output row of this column pair
+  uint64_t acc0 = 0ull, acc1 = 0ull, acc2 = 0ull;
+  int ycur = 0;
+  const int ring_rows = a.nch * kChunkRows;
+  const int nchunks = (nsrc + kChunkRows - 1) / kChunkRows;
+  const SchedRow* sp = sched;
+
+  auto flush = [&](int target) {                           // uniform: output rows [ycur, target) are complete
+#pragma unroll 1
+    for (; ycur < target; ++ycur) {
+      if (active) {
+        float v0, v1;
+        unpack2(acc0, v0, v1);
+        tp[0] = v0;
+        tp[1] = v1;
+      }
+      tp += pstr;
+      acc0 = acc1;
+      acc1 = acc2;
+      acc2 = 0ull;
+    }
+  };
+  auto row = [&](uint32_t p, const float4& s0, const float4& s1) {
+    flush(__float_as_int(s1.z));
+    uint64_t f = u16x2_to_f32x2(p);
+    if (kWindow) {
+      f = ffma2(f, wsc, wof);
+      float f0, f1;
+      unpack2(f, f0, f1);
+      f = pack2(fminf(fmaxf(f0, 0.f), 1.f), fminf(fmaxf(f1, 0.f), 1.f));
+    }
+    acc0 = ffma2(f, pack2(s0.x, s0.y), acc0);
+    acc1 = ffma2(f, pack2(s0.z, s0.w), acc1);
+    acc2 = ffma2(f, pack2(s1.x, s1.y), acc2);
+  };
+
+#pragma unroll 1
+  for (int ci = 0; ci < nchunks; ++ci) {
+    if (kBulk) mbar_wait(&sh.full[ci & (a.nch - 1)], (ci >> a.nch_log2) & 1);
+    if (!warp_idle) {
+      const int rr0 = ci * kChunkRows;
+      const uint8_t* rp = rbase + (size_t)(rr0 & (ring_rows - 1)) * pitch;
+      if (rr0 + kChunkRows <= nsrc) {                      // full chunk: loads hoisted, no loop overhead
+        uint32_t p[kChunkRows];
+        float4 s0[kChunkRows], s1[kChunkRows];
+#pragma unroll
+        for (int k = 0; k < kChunkRows; ++k) {
+          if (kBulk) p[k] = *reinterpret_cast<const uint32_t*>(rp + k * pitch);
+          else p[k] = __ldg(gp + k * wq);
+          s0[k] = *reinterpret_cast<const float4*>(&sp[k].w[0][0]);
+          s1[k] = *reinterpret_cast<const float4*>(&sp[k].w[2][0]);
+        }
+#pragma unroll
+        for (int k = 0; k < kChunkRows; ++k) row(p[k], s0[k], s1[k]);
+      } else {
+        for (int k = 0; k < nsrc - rr0; ++k) {
+          uint32_t p;
+          if (kBulk) p = *reinterpret_cast<const uint32_t*>(rp + k * pitch);
+          else p = __ldg(gp + k * wq);
+          row(p, *reinterpret_cast<const float4*>(&sp[k].w[0][0]), *reinterpret_cast<const float4*>(&sp[k].w[2][0]));
+        }
+      }
+      gp += kChunkRows * wq;
+      sp += kChunkRows;
+    }
+    if (kBulk) {
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive(&sh.empty[ci & (a.nch - 1)]);
+    }
+  }
+  if (!warp_idle) flush(c.nrows);
+}
+
 // dynamic-length fallback (tap counts outside the unrolled set)
 template <bool kBulk, bool kWindow>
 __device__ __forceinline__ void v_pass_dyn(const Ctx& c) {
@@ -299,6 +407,7 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
   float* h_w = reinterpret_cast<float*>(smem + a.off_hw);
   float* tmp = reinterpret_cast<float*>(smem + a.off_tmp);
   uint8_t* ring = smem + a.off_ring;
+  SchedRow* sched = reinterpret_cast<SchedRow*>(smem + a.off_sched);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -322,6 +431,7 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
   if (tid == 0) {
     sh.kv_max = 0;
     sh.kh_max = 0;
+    sh.m_max = 0;
     if (kBulk) {
       for (int i = 0; i < a.nch; ++i) {
         mbar_init(&sh.full[i], 1);
@@ -372,7 +482,35 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
     info.z = min(last / kChunkRows + 1, total_chunks);
     sh.v_info[tid] = info;
   }
+  // input-stationary schedule: one entry per source row of the band (windows are monotone in y)
+  const int nsrc = r_hi - r_lo;
+  for (int rr = tid; rr < min(nsrc, a.rmax); rr += kThreads) {
+    const int r = r_lo + rr;
+    int first = nrows, last = -1;
+    for (int yy = 0; yy < nrows; ++yy) {
+      const int4 info = sh.v_info[yy];
+      if (info.x <= r && r < info.x + info.y) {
+        first = min(first, yy);
+        last = yy;
+      }
+    }
+    if (last < 0) first = 0;   // cannot happen (windows overlap); keeps the flush logic monotone anyway
+    SchedRow e;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float w = 0.f;
+      const int yy = first + k;
+      if (yy <= last) w = v_w[(yy * a.kstride + (r - sh.v_info[yy].x)) * 2];
+      e.w[k][0] = w;
+      e.w[k][1] = w;
+    }
+    e.first = first;
+    e.pad = 0;
+    sched[rr] = e;
+    atomicMax(&sh.m_max, last - first + 1);
+  }
   __syncthreads();
+  const bool use_is = (sh.m_max <= 3) && (nsrc <= a.rmax) && (((lp + P.w + 1) >> 1) <= kConsumerThreads);
 
   float o[kSeg];     // this thread's 32 output pixels (row y0+lane, columns 32*warp ..)
 #pragma unroll
@@ -414,7 +552,8 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
     c.h = P.h;
     c.r_lo = r_lo;
     c.ring_byte0 = 2 * ((int)(e0 & 7) - lp);
-    switch (KV) {
+    if (use_is) v_pass_is<kBulk, kWindow>(c, sched, nsrc);
+    else switch (KV) {
       case 3: v_pass<3, kBulk, kWindow>(c); break;
       case 5: v_pass<5, kBulk, kWindow>(c); break;
       case 7: v_pass<7, kBulk, kWindow>(c); break;
@@ -625,6 +764,9 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
   off += align_up(s * a.kstride * 4, 16);
   a.off_tmp = off;
   off += align_up(kBandRows * a.pstr * 4, 128);
+  a.rmax = (kBandRows * ((H + s - 1) / s)) + a.kstride + 4;
+  a.off_sched = off;
+  off += align_up(a.rmax * (int)sizeof(SchedRow), 128);
   a.off_ring = off;
   if (bulk) off += a.nch * kChunkRows * a.pitch;
   const size_t smem = (size_t)off;
