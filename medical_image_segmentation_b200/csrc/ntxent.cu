@@ -405,34 +405,38 @@ __global__ void cexp_kernel(const float* __restrict__ lse, float* __restrict__ c
   if (j < cols) cexp[j] = expf(inv_T - lse[j]);
 }
 
-// lse_i = 1/T + log(sum of split partials); pos_i = <u_i,u_p(i)>/T; loss = mean(lse - pos).  One block.
-__global__ void fwd_finalize_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ u_all, int D,
-                                    int row0, int rows, float inv_T, float* __restrict__ lse_rows,
-                                    float* __restrict__ loss) {
-  __shared__ float red[32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  const int half = rows >> 1;
-  float acc = 0.f;
-  for (int i = warp; i < rows; i += nwarp) {
-    float s = 0.f;
-    for (int k = 0; k < nsplit; ++k) s += partial[(size_t)k * rows + i];
-    const float lse = inv_T + logf(s);
-    const float* ui = u_all + (size_t)(row0 + i) * D;
-    const float* up = u_all + (size_t)(row0 + (i + half) % rows) * D;
-    float dot = 0.f;
-    for (int d = lane; d < D; d += 32) dot = fmaf(ui[d], up[d], dot);
-    dot = warp_sum(dot);
-    if (lane == 0) {
-      lse_rows[i] = lse;
-      acc += lse - dot * inv_T;
-    }
+// lse_i = 1/T + log(sum of split partials); pos_i = <u_i,u_p(i)>/T; per-row loss term lse_i - pos_i.  One warp per row.
+__global__ void fwd_rows_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ u_all, int D,
+                                int row0, int rows, float inv_T, float* __restrict__ lse_rows,
+                                float* __restrict__ row_loss) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= rows) return;
+  float s = 0.f;
+  for (int k = 0; k < nsplit; ++k) s += partial[(size_t)k * rows + i];
+  const float lse = inv_T + logf(s);
+  const float* ui = u_all + (size_t)(row0 + i) * D;
+  const float* up = u_all + (size_t)(row0 + (i + (rows >> 1)) % rows) * D;
+  float dot = 0.f;
+  for (int d = lane; d < D; d += 32) dot = fmaf(ui[d], up[d], dot);
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    lse_rows[i] = lse;
+    row_loss[i] = lse - dot * inv_T;
   }
-  if (lane == 0) red[warp] = acc;
+}
+// loss = mean(row_loss): one block, fixed summation order (deterministic)
+__global__ void mean_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += v[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     float tot = 0.f;
-    for (int w = 0; w < nwarp; ++w) tot += red[w];
-    loss[0] = tot / (float)rows;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    out[0] = tot / (float)n;
   }
 }
 
@@ -635,7 +639,10 @@ extern "C" int mis_ntxent_fwd(const float* u_all, int cols, int D, int row0, int
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map_u, map_u, a);
   MIS_CUDA_TRY(cudaGetLastError());
-  fwd_finalize_kernel<<<1, 1024, 0, st>>>(partial, p.nsplit, u_all, D, row0, rows, inv_T, lse_rows, loss);
+  float* row_loss = reinterpret_cast<float*>(sc);     // reuses the (backward-only) cexp slot
+  fwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(partial, p.nsplit, u_all, D, row0, rows, inv_T, lse_rows, row_loss);
+  MIS_CUDA_TRY(cudaGetLastError());
+  mean_kernel<<<1, 1024, 0, st>>>(row_loss, rows, loss);
   MIS_CUDA_TRY(cudaGetLastError());
   return MIS_OK;
 }

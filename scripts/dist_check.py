@@ -1,0 +1,36 @@
+"""Multi-GPU parity of the NT-Xent path (NCCL all-gather + option-L backward) against the sharded oracle.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/dist_check.py
+"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, ".")
+from oracle import loss_oracle as L
+from medical_image_segmentation_b200 import nt_xent_loss
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for (B, D, T) in ((64, 64, 0.1), (256, 128, 0.1), (128, 256, 0.2)):
+    g = torch.Generator().manual_seed(11)
+    z_locals = [torch.randn(2 * B, D, generator=g) for _ in range(world)]
+    ref_losses, ref_grads = L.ntxent_rank_sharded(z_locals, T)
+    z = z_locals[rank].cuda()
+    a = z[:B].clone().requires_grad_(True)
+    b = z[B:].clone().requires_grad_(True)
+    loss = nt_xent_loss(a, b, T)          # default group
+    loss.backward()
+    got = torch.cat([a.grad, b.grad]).cpu().double().numpy()
+    ref = ref_grads[rank].numpy()
+    fro = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    lrel = abs(loss.item() - ref_losses[rank]) / abs(ref_losses[rank])
+    good = fro <= 1e-3 and lrel <= 1e-3
+    ok &= good
+    print(f"rank {rank}/{world} B={B} D={D} T={T}: loss rel {lrel:.2e} grad fro rel {fro:.2e} {'OK' if good else 'FAIL'}", flush=True)
+flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+if rank == 0:
+    print("DIST_CHECK", "PASS" if flag.item() == 1.0 else "FAIL")
+sys.exit(0 if flag.item() == 1.0 else 1)
