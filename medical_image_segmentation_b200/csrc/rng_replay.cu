@@ -93,9 +93,17 @@ struct Box {
   bool ok;
 };
 
-static inline void box_dims(double target_area, float ar, int& w, int& h) {
-  w = (int)std::nearbyint(std::sqrt(target_area * (double)ar));
-  h = (int)std::nearbyint(std::sqrt(target_area / (double)ar));
+// w = round(sqrt(area*ar)), h = round(sqrt(area/ar)) as Python computes them (double sqrt, round-half-even).
+// `safe` is false when either value is so close to a rounding boundary that the last bit of exp() could flip it:
+// a one-ulp change of the float32 ratio moves sqrt(...) by < 1e-7 relative, i.e. < 1e-4 px for boxes < 1000 px.
+static inline void box_dims(double target_area, float ar, int& w, int& h, bool& safe) {
+  const double ws = std::sqrt(target_area * (double)ar);
+  const double hs = std::sqrt(target_area / (double)ar);
+  w = (int)std::nearbyint(ws);
+  h = (int)std::nearbyint(hs);
+  const double fw = std::fabs(ws - std::floor(ws) - 0.5), fh = std::fabs(hs - std::floor(hs) - 0.5);
+  const double eps = 1e-6 * (ws > hs ? ws : hs) + 1e-9;
+  safe = fw > eps && fh > eps;
 }
 
 // returns false when the result depends on the last bit of exp()
@@ -107,11 +115,16 @@ static bool draw_view(Engine& e, int H, int W, float blur_p, float sol_p, MisVie
     const double target_area = area * (double)e.uniform(kScaleLo, kScaleHi);
     const float lr = e.uniform(kLogRatioLo, kLogRatioHi);
     const float ar = expf(lr);
-    box_dims(target_area, ar, w, h);
-    int w1, h1, w2, h2;
-    box_dims(target_area, std::nextafterf(ar, 0.f), w1, h1);
-    box_dims(target_area, std::nextafterf(ar, 4.f), w2, h2);
-    if (w1 != w || w2 != w || h1 != h || h2 != h) return false;
+    bool safe;
+    box_dims(target_area, ar, w, h, safe);
+    if (!safe) {   // rare: decide with the neighbouring float32 ratios; if they disagree, hand the image back
+      int w1, h1, w2, h2;
+      bool s1, s2;
+      // libm expf and SLEEF's vector expf are each within 1 ulp of exp(): they differ by at most 2 ulp
+      box_dims(target_area, std::nextafterf(std::nextafterf(ar, 0.f), 0.f), w1, h1, s1);
+      box_dims(target_area, std::nextafterf(std::nextafterf(ar, 4.f), 4.f), w2, h2, s2);
+      if (w1 != w || w2 != w || h1 != h || h2 != h) return false;
+    }
     if (0 < w && w <= W && 0 < h && h <= H) {
       top = (int)(e.random() % (uint32_t)(H - h + 1));
       left = (int)(e.random() % (uint32_t)(W - w + 1));

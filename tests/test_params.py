@@ -72,3 +72,25 @@ def test_view_major_reorder():
     p["top"] = np.arange(6)
     q = FusedTwoViewTransforms.to_view_major(p)
     assert list(q["top"]) == [0, 2, 4, 1, 3, 5]
+
+
+def test_handback_images_are_drawn_by_torch_and_stay_bit_exact(monkeypatch):
+    """~2.6e-4 of the images have a crop box within rounding distance of a .5 boundary; the native code hands
+    them back and torch draws them.  Check the path fires and that the stream stays aligned afterwards."""
+    calls = []
+    orig = P.draw_two_view_params_torch
+
+    def counting(*a, **k):
+        calls.append(k.get("img0"))
+        return orig(*a, **k)
+
+    monkeypatch.setattr(P, "draw_two_view_params_torch", counting)
+    torch.manual_seed(123)
+    p = P.draw_two_view_params(30000, 512, 512)
+    assert len(calls) >= 1
+    i = calls[0]
+    torch.manual_seed(123)
+    P.draw_two_view_params(i, 512, 512)          # no hand-back before image i by construction
+    ref = orig(3, 512, 512, img0=i)              # pure torch replay of image i and its two successors
+    for name in VIEW_PARAMS_DTYPE.names:
+        assert np.array_equal(ref[name], p[name][2 * i:2 * i + 6]), name
