@@ -2,26 +2,35 @@
 //
 // One thread-block CLUSTER per output view plane, one CTA per band of 32 output rows:
 //
-//   producer warp : streams the crop-window rows the band needs from HBM into a shared-memory
-//                   ring with 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP), one mbarrier
-//                   per 8-row chunk, released by the consumers chunk by chunk;
-//   V pass        : 8 consumer warps, lanes over source columns (u16x2 per lane, conflict-free),
-//                   vertical antialias taps with warp-uniform weights -> fp32 tile in smem;
-//   H pass        : lanes over the band's 32 output rows (conflict-free, odd row stride), each
-//                   warp owns 32 consecutive output columns -> 32 results stay in registers;
-//   colour        : brightness / contrast in the per-view fn_idx order; the contrast mean over the
-//                   whole view is reduced warp -> CTA -> cluster through distributed shared
-//                   memory (st.shared::cluster + barrier.cluster), so the view is written once;
+//   staging       : (use_tma=1) a producer warp streams the band's crop rows into a shared-memory ring with 2-D TMA
+//                   tensor-map boxes (cp.async.bulk.tensor.2d -> SASS UTMALDG; 8 rows x <=256 columns, inner start
+//                   coordinate 16-byte aligned), one full/empty mbarrier pair per slot, started at kernel entry so it
+//                   overlaps the table prologue; (use_tma=0) every consumer thread fetches its own four columns with
+//                   8-byte cp.async into a private 8-deep ring after an early L2 prefetch of the band, two 16-row
+//                   streams per band, no producer and no barriers;
+//   V pass        : input-stationary: thread = 4 adjacent source columns, every source pixel is loaded and converted
+//                   once (exact magic-number u16->f32, no I2F) and scattered into the <=3 output rows whose window
+//                   contains it with packed fma.rn.f32x2 (FFMA2); output-stationary unrolled taps as fallback
+//                   (upscaling / very wide images);
+//   H pass        : lanes over the band's 32 output rows (conflict-free, odd row stride), each warp owns 32 consecutive
+//                   output columns, per-view tap count unrolled -> 32 results stay in registers;
+//   colour        : brightness / contrast in the per-view fn_idx order; the contrast mean over the whole view is
+//                   reduced warp -> CTA -> cluster through distributed shared memory (st.shared::cluster +
+//                   barrier.cluster), so the view is written once;
 //   store         : normalise, flip, convert to bf16 (or fp32) and write NCHW with 16-byte stores.
 //
-// HBM traffic per view = crop window (u16) once + output once: the resampled tile, the tap
-// tables and the mean never leave the SM / cluster.
+// HBM traffic per view = crop window (u16) once + output once: the resampled tile, the tap tables and the mean never
+// leave the SM / cluster.
 //
 // Arithmetic restated from torchvision 0.26 / ATen (see oracle/aug_oracle.py):
 //   taps   : _upsample_bilinear2d_aa (triangle filter, support = max(scale,1), weights normalised)
 //   colour : functional/_color.py:114-125 (brightness), :190-205 + _blend :92-97 (contrast)
 //   output : (x - mean) / std, functional/_misc.py:37-67
+#include <cuda.h>
 #include <cuda_bf16.h>
+
+#include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -32,7 +41,10 @@ constexpr int kBandRows = 32;
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;  // + producer warp
-constexpr int kChunkRows = 4;
+constexpr int kChunkRows = 8;     // rows per TMA box: one thread issues ~1 box per 455 clk whatever its size (measured)
+constexpr int kRowUnroll = 4;     // rows whose loads are hoisted together in the V pass
+constexpr int kBoxCols = 256;                           // widest TMA box (tensor-map limit)
+constexpr int kBoxBytes = kBoxCols * 2 * kChunkRows;      // bytes one box occupies in a ring slot
 constexpr int kMaxChunks = 16;
 constexpr int kMaxBands = 8;
 constexpr int kSeg = 32;  // output columns per H-pass warp
@@ -51,11 +63,13 @@ struct Args {
   int kstride;      // tap-table stride in floats (multiple of 4, >= unrolled tap count)
   int nch;          // ring depth in chunks (power of two)
   int nch_log2;
-  int pitch;        // ring row pitch in bytes (multiple of 16)
+  int slot_bytes;   // bytes of one ring slot (= boxes per row * kBoxBytes)
+  int64_t plane_rows;  // H (rows per plane in the [planes*H, W] tensor-map view)
   int pstr;         // tmp row stride in words (odd)
   int rmax;         // capacity of the input-stationary schedule (source rows per band)
   // shared-memory byte offsets
   int off_vw, off_hw, off_tmp, off_ring, off_sched;
+  long long* dbg;   // optional [grid][8] clock stamps of thread 0 (debug / profiling aid), may be null
 };
 
 struct SmemHeader {
@@ -97,15 +111,54 @@ __device__ __forceinline__ uint64_t u16x2_to_f32x2(uint32_t p) {
   return fadd2(pack2(__uint_as_float(lo), __uint_as_float(hi)), pack2(-8388608.f, -8388608.f));
 }
 
+
+// ---- TMA-staged ring --------------------------------------------------------------------------
+// A ring slot holds kChunkRows source rows of the crop.  The crop's columns are fetched as 2-D TMA boxes of
+// up to 256 columns (box b covers crop columns [256b, 256b + wb)), wb rounded up to 64 so that one of four
+// tensor maps (box widths 64/128/192/256) fits; box b lives at byte b*kBoxBytes of the slot, row pitch 2*wb.
+// Tiled TMA needs a 16-byte aligned inner start coordinate (measured: an unaligned one raises 'illegal
+// instruction' on sm_100a), so boxes start at column left & ~7 and crop column 0 sits at slot column left & 7.
+// `w` in the helpers below is that total width (left & 7) + crop width.
+__device__ __forceinline__ int box_width(int w, int b) {
+  const int rem = w - b * kBoxCols;
+  return rem >= kBoxCols ? kBoxCols : ((rem + 63) & ~63);
+}
+struct ColAddr {
+  int off;     // byte offset of this thread's first column inside a slot
+  int pitch;   // row pitch of the box holding it
+};
+__device__ __forceinline__ ColAddr col_addr(int col, int w) {
+  const int b = col / kBoxCols;
+  ColAddr ca;
+  ca.off = b * kBoxBytes + (col - b * kBoxCols) * 2;
+  ca.pitch = box_width(w, b) * 2;
+  return ca;
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_box_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // Tap table of one output index.  n = input size, scale = n/m in fp32.
 // Writes kstride weights (zero padded) with element stride `wstep` (2 = duplicated pairs).
+__device__ __forceinline__ void aa_window(int i, int n, float scale, float support, int& lo, int& hi, float& center) {
+  center = (float)((double)scale * ((double)i + 0.5));
+  lo = (int)((double)center - (double)support + 0.5);
+  lo = lo < 0 ? 0 : lo;
+  hi = (int)((double)center + (double)support + 0.5);
+  hi = hi > n ? n : hi;
+}
+
 __device__ __forceinline__ void aa_taps(int i, int n, float scale, float support, float invscale, int kstride,
                                         int wstep, int& lo_out, int& size_out, float* w) {
-  const float center = (float)((double)scale * ((double)i + 0.5));
-  int lo = (int)((double)center - (double)support + 0.5);
-  lo = lo < 0 ? 0 : lo;
-  int hi = (int)((double)center + (double)support + 0.5);
-  hi = hi > n ? n : hi;
+  float center;
+  int lo, hi;
+  aa_window(i, n, scale, support, lo, hi, center);
   int size = hi - lo;
   size = size < 0 ? 0 : (size > kstride ? kstride : size);
   float total = 0.f;
@@ -134,7 +187,8 @@ struct Ctx {
   const uint16_t* gplane;   // crop (0, -lp) in global memory
   int tid, lane, warp;
   int nrows, npairs, lp, w, h, r_lo;
-  int ring_byte0;       // byte offset of pair 0 inside a ring row
+  int coff;             // tmp column of crop column 0 (left&1 for the pair paths, left&3 for the quad path)
+  int ring_byte0;       // unused by the TMA ring (boxes start at the crop's first column)
 };
 
 // ---- V pass: lanes over source column pairs, K taps unrolled, packed FMAs -----------------------
@@ -167,11 +221,14 @@ __device__ __forceinline__ void v_pass(const Ctx& c) {
       if (q < c.npairs) {
         uint32_t p[K];
         if (kBulk) {
-          const uint8_t* base = c.ring + c.ring_byte0 + 4 * q;
+          const ColAddr ca = col_addr(2 * q, c.coff + c.w);
           const int sr0 = info.x - c.r_lo;
 #pragma unroll
-          for (int j = 0; j < K; ++j)
-            p[j] = *reinterpret_cast<const uint32_t*>(base + (size_t)((sr0 + j) & ring_mask) * a.pitch);
+          for (int j = 0; j < K; ++j) {
+            const int sr = (sr0 + j) & ring_mask;
+            p[j] = *reinterpret_cast<const uint32_t*>(c.ring + (sr / kChunkRows) * a.slot_bytes + ca.off +
+                                                      (sr % kChunkRows) * ca.pitch);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < K; ++j) {
@@ -215,27 +272,29 @@ template <bool kBulk, bool kWindow>
 __device__ __forceinline__ void v_pass_is(const Ctx& c, const SchedRow* __restrict__ sched, int nsrc) {
   const Args& a = *c.a;
   SmemHeader& sh = *c.sh;
+  // thread = FOUR adjacent source columns (one 8-byte load per source row); column group 0 starts at the crop's
+  // first column rounded down to a multiple of 4 (c.coff = left & 3 columns of slack on the left)
+  const int ngroups = (c.coff + c.w + 3) >> 2;
   const int q = c.tid;
-  const int npad = min(c.npairs + a.kstride / 2 + 1, a.pstr / 2);
-  const bool active = q < c.npairs;
-  const bool warp_idle = (c.warp * 32) >= c.npairs;      // no column pair of this warp lies inside the crop
-  const int pitch = a.pitch;
+  const bool active = q < ngroups;
+  const bool warp_idle = (c.warp * 32) >= ngroups;
   const int pstr = a.pstr;
-  const int wq = a.W >> 1;
+  const int wq = a.W >> 2;
   // zero the few columns right of the crop that the unrolled H-pass taps may touch (weights there are 0)
-  for (int i = c.tid; i < c.nrows * 2 * (npad - c.npairs); i += kConsumerThreads) {
-    const int per = 2 * (npad - c.npairs);
-    c.tmp[(i / per) * pstr + 2 * c.npairs + (i % per)] = 0.f;
+  {
+    const int c0 = 4 * ngroups, per = min(a.kstride + 2, pstr - c0);
+    for (int i = c.tid; i < c.nrows * per; i += kConsumerThreads) c.tmp[(i / per) * pstr + c0 + (i % per)] = 0.f;
   }
   const uint64_t wsc = pack2(a.win_scale, a.win_scale);
   const uint64_t wof = pack2(-a.win_lo * a.win_scale, -a.win_lo * a.win_scale);
   const int qa = active ? q : 0;                         // inactive lanes compute on a valid address, never store
-  const uint8_t* rbase = c.ring + c.ring_byte0 + 4 * qa;
-  const uint32_t* gp = reinterpret_cast<const uint32_t*>(c.gplane + (int64_t)c.r_lo * a.W) + qa;
-  float* tp = c.tmp + 2 * qa;                            // next output row of this column pair
-  uint64_t acc0 = 0ull, acc1 = 0ull, acc2 = 0ull;
+  const ColAddr ca = col_addr(4 * qa, c.coff + c.w);
+  const int pitch = ca.pitch;
+  const uint8_t* rbase = c.ring + ca.off;
+  const uint2* gp = reinterpret_cast<const uint2*>(c.gplane + (int64_t)c.r_lo * a.W) + qa;
+  float* tp = c.tmp + 4 * qa;                            // next output row of this column group
+  uint64_t a0 = 0ull, a1 = 0ull, b0 = 0ull, b1 = 0ull, c0 = 0ull, c1 = 0ull;   // 3 open output rows x 4 columns
   int ycur = 0;
-  const int ring_rows = a.nch * kChunkRows;
   const int nchunks = (nsrc + kChunkRows - 1) / kChunkRows;
   const SchedRow* sp = sched;
 
@@ -243,19 +302,21 @@ __device__ __forceinline__ void v_pass_is(const Ctx& c, const SchedRow* __restri
 #pragma unroll 1
     for (; ycur < target; ++ycur) {
       if (active) {
-        float v0, v1;
-        unpack2(acc0, v0, v1);
+        float v0, v1, v2, v3;
+        unpack2(a0, v0, v1);
+        unpack2(a1, v2, v3);
         tp[0] = v0;
         tp[1] = v1;
+        tp[2] = v2;
+        tp[3] = v3;
       }
       tp += pstr;
-      acc0 = acc1;
-      acc1 = acc2;
-      acc2 = 0ull;
+      a0 = b0; a1 = b1;
+      b0 = c0; b1 = c1;
+      c0 = 0ull; c1 = 0ull;
     }
   };
-  auto row = [&](uint32_t p, const float4& s0, const float4& s1) {
-    flush(__float_as_int(s1.z));
+  auto conv = [&](uint32_t p) {
     uint64_t f = u16x2_to_f32x2(p);
     if (kWindow) {
       f = ffma2(f, wsc, wof);
@@ -263,9 +324,18 @@ __device__ __forceinline__ void v_pass_is(const Ctx& c, const SchedRow* __restri
       unpack2(f, f0, f1);
       f = pack2(fminf(fmaxf(f0, 0.f), 1.f), fminf(fmaxf(f1, 0.f), 1.f));
     }
-    acc0 = ffma2(f, pack2(s0.x, s0.y), acc0);
-    acc1 = ffma2(f, pack2(s0.z, s0.w), acc1);
-    acc2 = ffma2(f, pack2(s1.x, s1.y), acc2);
+    return f;
+  };
+  auto row = [&](uint2 p, const float4& s0, const float4& s1) {
+    flush(__float_as_int(s1.z));
+    const uint64_t f0 = conv(p.x), f1 = conv(p.y);
+    const uint64_t w0 = pack2(s0.x, s0.y), w1 = pack2(s0.z, s0.w), w2 = pack2(s1.x, s1.y);
+    a0 = ffma2(f0, w0, a0);
+    a1 = ffma2(f1, w0, a1);
+    b0 = ffma2(f0, w1, b0);
+    b1 = ffma2(f1, w1, b1);
+    c0 = ffma2(f0, w2, c0);
+    c1 = ffma2(f1, w2, c1);
   };
 
 #pragma unroll 1
@@ -273,26 +343,27 @@ __device__ __forceinline__ void v_pass_is(const Ctx& c, const SchedRow* __restri
     if (kBulk) mbar_wait(&sh.full[ci & (a.nch - 1)], (ci >> a.nch_log2) & 1);
     if (!warp_idle) {
       const int rr0 = ci * kChunkRows;
-      const uint8_t* rp = rbase + (size_t)(rr0 & (ring_rows - 1)) * pitch;
-      if (rr0 + kChunkRows <= nsrc) {                      // full chunk: loads hoisted, no loop overhead
-        uint32_t p[kChunkRows];
-        float4 s0[kChunkRows], s1[kChunkRows];
+      const uint8_t* rp = rbase + (size_t)(ci & (a.nch - 1)) * a.slot_bytes;
+      const int nrow = min(kChunkRows, nsrc - rr0);
+      int k0 = 0;
+      for (; k0 + kRowUnroll <= nrow; k0 += kRowUnroll) {  // groups of 4 rows: loads hoisted, no per-row loop overhead
+        uint2 p[kRowUnroll];
+        float4 s0[kRowUnroll], s1[kRowUnroll];
 #pragma unroll
-        for (int k = 0; k < kChunkRows; ++k) {
-          if (kBulk) p[k] = *reinterpret_cast<const uint32_t*>(rp + k * pitch);
-          else p[k] = __ldg(gp + k * wq);
-          s0[k] = *reinterpret_cast<const float4*>(&sp[k].w[0][0]);
-          s1[k] = *reinterpret_cast<const float4*>(&sp[k].w[2][0]);
+        for (int k = 0; k < kRowUnroll; ++k) {
+          if (kBulk) p[k] = *reinterpret_cast<const uint2*>(rp + (k0 + k) * pitch);
+          else p[k] = __ldg(gp + (k0 + k) * wq);
+          s0[k] = *reinterpret_cast<const float4*>(&sp[k0 + k].w[0][0]);
+          s1[k] = *reinterpret_cast<const float4*>(&sp[k0 + k].w[2][0]);
         }
 #pragma unroll
-        for (int k = 0; k < kChunkRows; ++k) row(p[k], s0[k], s1[k]);
-      } else {
-        for (int k = 0; k < nsrc - rr0; ++k) {
-          uint32_t p;
-          if (kBulk) p = *reinterpret_cast<const uint32_t*>(rp + k * pitch);
-          else p = __ldg(gp + k * wq);
-          row(p, *reinterpret_cast<const float4*>(&sp[k].w[0][0]), *reinterpret_cast<const float4*>(&sp[k].w[2][0]));
-        }
+        for (int k = 0; k < kRowUnroll; ++k) row(p[k], s0[k], s1[k]);
+      }
+      for (; k0 < nrow; ++k0) {
+        uint2 p;
+        if (kBulk) p = *reinterpret_cast<const uint2*>(rp + k0 * pitch);
+        else p = __ldg(gp + k0 * wq);
+        row(p, *reinterpret_cast<const float4*>(&sp[k0].w[0][0]), *reinterpret_cast<const float4*>(&sp[k0].w[2][0]));
       }
       gp += kChunkRows * wq;
       sp += kChunkRows;
@@ -303,6 +374,101 @@ __device__ __forceinline__ void v_pass_is(const Ctx& c, const SchedRow* __restri
     }
   }
   if (!warp_idle) flush(c.nrows);
+}
+
+
+// ---- V pass without TMA: per-thread cp.async ring, two independent row streams -----------------------------
+// Measured on B200: one thread issues at most ~1 TMA box per 455 clk, so a producer-fed ring delivers only
+// ~4.5-9 B/clk per CTA with the 2-4 KB boxes that fit next to the 68 KB transposition tile.  Here every
+// consumer thread instead fetches ITS OWN four columns with 8-byte cp.async (LDGSTS) into a private 8-deep
+// ring: no producer, no mbarriers, no cross-thread hazards (a thread only reads what it copied itself).
+// The band's 32 output rows are split in two streams of 16 rows (warps 0-3 / 4-7), each walking its own source
+// row range, which halves the serial dependency chain per warp.
+constexpr int kCpDepth = 8;
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool kWindow>
+__device__ __forceinline__ void v_pass_cp(const Ctx& c, const SchedRow* __restrict__ sched, int nsrc, int r_first,
+                                          int ya, int yb, uint2* __restrict__ ring) {
+  const Args& a = *c.a;
+  const int q = c.tid & 127;                                   // column group inside the stream
+  const int ngroups = (c.coff + c.w + 3) >> 2;
+  const bool active = q < ngroups;
+  const int qa = active ? q : 0;
+  const int pstr = a.pstr;
+  const int wq = a.W >> 2;
+  const uint64_t wsc = pack2(a.win_scale, a.win_scale);
+  const uint64_t wof = pack2(-a.win_lo * a.win_scale, -a.win_lo * a.win_scale);
+  const uint2* gp = reinterpret_cast<const uint2*>(c.gplane + (int64_t)r_first * a.W) + qa;
+  uint2* myr = ring + c.tid;                                   // slot k of this thread: myr[k * 256]
+  float* tp = c.tmp + ya * pstr + 4 * qa;
+  uint64_t a0 = 0ull, a1 = 0ull, b0 = 0ull, b1 = 0ull, c0 = 0ull, c1 = 0ull;
+  int ycur = ya;
+
+  auto flush = [&](int target) {
+#pragma unroll 1
+    for (; ycur < target; ++ycur) {
+      if (active) {
+        float v0, v1, v2, v3;
+        unpack2(a0, v0, v1);
+        unpack2(a1, v2, v3);
+        tp[0] = v0;
+        tp[1] = v1;
+        tp[2] = v2;
+        tp[3] = v3;
+      }
+      tp += pstr;
+      a0 = b0; a1 = b1;
+      b0 = c0; b1 = c1;
+      c0 = 0ull; c1 = 0ull;
+    }
+  };
+  auto conv = [&](uint32_t p) {
+    uint64_t f = u16x2_to_f32x2(p);
+    if (kWindow) {
+      f = ffma2(f, wsc, wof);
+      float f0, f1;
+      unpack2(f, f0, f1);
+      f = pack2(fminf(fmaxf(f0, 0.f), 1.f), fminf(fmaxf(f1, 0.f), 1.f));
+    }
+    return f;
+  };
+
+#pragma unroll
+  for (int k = 0; k < kCpDepth; ++k) {
+    if (k < nsrc) cp_async8(myr + k * kConsumerThreads, gp + (size_t)k * wq);
+    cp_async_commit();
+  }
+#pragma unroll 1
+  for (int rr0 = 0; rr0 < nsrc; rr0 += kCpDepth) {
+#pragma unroll
+    for (int k = 0; k < kCpDepth; ++k) {
+      const int rr = rr0 + k;
+      if (rr < nsrc) {                                          // uniform
+        cp_async_wait<kCpDepth - 1>();                          // the copy of row rr has landed
+        const uint2 p = myr[k * kConsumerThreads];
+        const float4 s0 = *reinterpret_cast<const float4*>(&sched[rr].w[0][0]);
+        const float4 s1 = *reinterpret_cast<const float4*>(&sched[rr].w[2][0]);
+        if (rr + kCpDepth < nsrc) cp_async8(myr + k * kConsumerThreads, gp + (size_t)(rr + kCpDepth) * wq);
+        cp_async_commit();
+        flush(__float_as_int(s1.z));
+        const uint64_t f0 = conv(p.x), f1 = conv(p.y);
+        const uint64_t w0 = pack2(s0.x, s0.y), w1 = pack2(s0.z, s0.w), w2 = pack2(s1.x, s1.y);
+        a0 = ffma2(f0, w0, a0);
+        a1 = ffma2(f1, w0, a1);
+        b0 = ffma2(f0, w1, b0);
+        b1 = ffma2(f1, w1, b1);
+        c0 = ffma2(f0, w2, c0);
+        c1 = ffma2(f1, w2, c1);
+      }
+    }
+  }
+  flush(yb);
 }
 
 // dynamic-length fallback (tap counts outside the unrolled set)
@@ -334,8 +500,12 @@ __device__ __forceinline__ void v_pass_dyn(const Ctx& c) {
         for (int j = 0; j < info.y; ++j) {
           uint32_t p;
           if (kBulk)
-            p = *reinterpret_cast<const uint32_t*>(c.ring + c.ring_byte0 + 4 * q +
-                                                   (size_t)((info.x - c.r_lo + j) & ring_mask) * a.pitch);
+          {
+            const ColAddr ca = col_addr(2 * q, c.coff + c.w);
+            const int sr = (info.x - c.r_lo + j) & ring_mask;
+            p = *reinterpret_cast<const uint32_t*>(c.ring + (sr / kChunkRows) * a.slot_bytes + ca.off +
+                                                   (sr % kChunkRows) * ca.pitch);
+          }
           else
             p = __ldg(reinterpret_cast<const uint32_t*>(c.gplane + (int64_t)(info.x + j) * a.W) + q);
           float f0, f1;
@@ -360,7 +530,7 @@ template <int K>
 __device__ __forceinline__ void h_pass(const Ctx& c, float (&o)[kSeg], float post) {
   const Args& a = *c.a;
   const int x0 = c.warp * kSeg;
-  const float* trow = c.tmp + c.lane * a.pstr + c.lp;
+  const float* trow = c.tmp + c.lane * a.pstr + c.coff;
   constexpr int K4 = (K + 3) / 4;
 #pragma unroll
   for (int i = 0; i < kSeg; ++i) {
@@ -385,7 +555,7 @@ __device__ __forceinline__ void h_pass(const Ctx& c, float (&o)[kSeg], float pos
 __device__ __forceinline__ void h_pass_dyn(const Ctx& c, float (&o)[kSeg], float post) {
   const Args& a = *c.a;
   const int x0 = c.warp * kSeg;
-  const float* trow = c.tmp + c.lane * a.pstr + c.lp;
+  const float* trow = c.tmp + c.lane * a.pstr + c.coff;
 #pragma unroll
   for (int i = 0; i < kSeg; ++i) {
     const int x = x0 + i;
@@ -400,7 +570,9 @@ __device__ __forceinline__ void h_pass_dyn(const Ctx& c, float (&o)[kSeg], float
 }
 
 template <bool kBulk, bool kWindow>
-__global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
+__global__ void __launch_bounds__(kThreads, 2)
+aug_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CUtensorMap map128,
+           const __grid_constant__ CUtensorMap map192, const __grid_constant__ CUtensorMap map256, const Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
   SmemHeader& sh = *reinterpret_cast<SmemHeader*>(smem);
   float* v_w = reinterpret_cast<float*>(smem + a.off_vw);
@@ -419,6 +591,8 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
   const int s = a.s;
 
   cluster_arrive_relaxed();   // phase 1: "every CTA of the cluster is running" (waited before DSMEM use)
+#define MIS_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[(size_t)blockIdx.x * 8 + (i)] = clock64(); } while (0)
+  MIS_STAMP(0);
 
   const MisViewParams P = a.params[view];
   const int y0 = band * kBandRows;
@@ -427,26 +601,86 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
   const int64_t plane_base = (int64_t)P.img * a.img_stride + (int64_t)chan * a.H * a.W;
   const int64_t e0 = plane_base + (int64_t)P.top * a.W + P.left;   // element index of crop (0,0)
 
-  // ---- tap tables + barriers ------------------------------------------------------------
+  // ---- producer head start + tap tables ------------------------------------------------------
+  // The producer lane derives the band's source-row range on its own (two window evaluations), prefetches the
+  // whole range into L2 and fills the ring, all while the 8 consumer warps build the tap tables.
+  const float vscale = (float)P.h / (float)s;
+  const float hscale = (float)P.w / (float)s;
+  const float vsup = vscale >= 1.f ? vscale : 1.f, vinv = vscale >= 1.f ? 1.f / vscale : 1.f;
+  const float hsup = hscale >= 1.f ? hscale : 1.f, hinv = hscale >= 1.f ? 1.f / hscale : 1.f;
+  // one chunk = kChunkRows rows x the crop's columns, fetched as ceil(w/256) TMA boxes into ring slot `slot`
+  const int wtot = (P.left & 7) + P.w;                            // slot columns: aligned box start .. crop end
+  const int nbox = (wtot + kBoxCols - 1) / kBoxCols;
+  uint32_t chunk_bytes = 0;
+  for (int b = 0; b < nbox; ++b) chunk_bytes += (uint32_t)box_width(wtot, b) * 2 * kChunkRows;
+  const int row_base = (P.img * a.C + chan) * (int)a.plane_rows + P.top;    // tensor-map row of crop row 0
+  // (macro, not a lambda: the tensor maps must be addressed in param space, a closure would copy them to local memory)
+#define MIS_ISSUE_CHUNK(slot_, r_)                                                                                  \
+  do {                                                                                                              \
+    mbar_arrive_expect_tx(&sh.full[slot_], chunk_bytes);                                                            \
+    for (int b_ = 0; b_ < nbox; ++b_) {                                                                             \
+      const int wb_ = box_width(wtot, b_);                                                                           \
+      void* dst_ = ring + (size_t)(slot_) * a.slot_bytes + b_ * kBoxBytes;                                          \
+      const int c0_ = (P.left & ~7) + b_ * kBoxCols, c1_ = row_base + (r_);                                                \
+      if (wb_ == 64) tma_box_2d(dst_, &map64, c0_, c1_, &sh.full[slot_]);                                           \
+      else if (wb_ == 128) tma_box_2d(dst_, &map128, c0_, c1_, &sh.full[slot_]);                                    \
+      else if (wb_ == 192) tma_box_2d(dst_, &map192, c0_, c1_, &sh.full[slot_]);                                    \
+      else tma_box_2d(dst_, &map256, c0_, c1_, &sh.full[slot_]);                                                    \
+    }                                                                                                               \
+  } while (0)
+#define MIS_PREFETCH_CHUNK(r_)                                                                                      \
+  do {                                                                                                              \
+    for (int b_ = 0; b_ < nbox; ++b_) {                                                                             \
+      const int wb_ = box_width(wtot, b_);                                                                          \
+      const int c0_ = (P.left & ~7) + b_ * kBoxCols, c1_ = row_base + (r_);                                         \
+      if (wb_ == 64) tma_prefetch_2d(&map64, c0_, c1_);                                                             \
+      else if (wb_ == 128) tma_prefetch_2d(&map128, c0_, c1_);                                                      \
+      else if (wb_ == 192) tma_prefetch_2d(&map192, c0_, c1_);                                                      \
+      else tma_prefetch_2d(&map256, c0_, c1_);                                                                      \
+    }                                                                                                               \
+  } while (0)
+  int issued = 0;                                                // chunks already issued by the head start
+  if (!kBulk) {
+    // non-TMA path: pull the band's crop rows into L2 right away (every thread derives the row range itself and
+    // prefetches a few 128-byte lines), so the cp.async stream of the V pass, which starts ~3 us later, hits L2
+    int lo0, hi0, lo1, hi1;
+    float ctr;
+    aa_window(y0, P.h, vscale, vsup, lo0, hi0, ctr);
+    aa_window(y0 + nrows - 1, P.h, vscale, vsup, lo1, hi1, ctr);
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(a.src + e0);
+    const int head = (int)(reinterpret_cast<uintptr_t>(base) & 127);
+    const int lines = (head + 2 * P.w + 127) >> 7;               // 128-byte lines per crop row
+    const int total = (hi1 - lo0) * lines;
+    for (int i = tid; i < total; i += kThreads) {
+      const int r = lo0 + i / lines, l = i - (i / lines) * lines;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)r * a.W * 2 - head + l * 128));
+    }
+  }
   if (tid == 0) {
     sh.kv_max = 0;
     sh.kh_max = 0;
     sh.m_max = 0;
-    if (kBulk) {
+  }
+  if (kBulk && warp == kConsumerWarps) {
+    if (lane == 0) {
       for (int i = 0; i < a.nch; ++i) {
         mbar_init(&sh.full[i], 1);
         mbar_init(&sh.empty[i], kConsumerWarps);
       }
       mbar_fence_init();
+      int lo0, hi0, lo1, hi1;
+      float ctr;
+      aa_window(y0, P.h, vscale, vsup, lo0, hi0, ctr);
+      aa_window(y0 + nrows - 1, P.h, vscale, vsup, lo1, hi1, ctr);
+      const int total = (hi1 - lo0 + kChunkRows - 1) / kChunkRows;
+      issued = min(a.nch, total);
+      for (int ci = 0; ci < issued; ++ci) MIS_ISSUE_CHUNK(ci, lo0 + ci * kChunkRows);
     }
+    __syncwarp();
   }
   __syncthreads();
-  {
-    const float vscale = (float)P.h / (float)s;
-    const float hscale = (float)P.w / (float)s;
-    const float vsup = vscale >= 1.f ? vscale : 1.f, vinv = vscale >= 1.f ? 1.f / vscale : 1.f;
-    const float hsup = hscale >= 1.f ? hscale : 1.f, hinv = hscale >= 1.f ? 1.f / hscale : 1.f;
-    for (int idx = tid; idx < nrows + s; idx += kThreads) {
+  if (warp < kConsumerWarps) {
+    for (int idx = tid; idx < nrows + s; idx += kConsumerThreads) {
       int lo, size;
       if (idx < nrows) {
         aa_taps(y0 + idx, P.h, vscale, vsup, vinv, a.kstride, 2, lo, size, v_w + idx * a.kstride * 2);
@@ -482,36 +716,55 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
     info.z = min(last / kChunkRows + 1, total_chunks);
     sh.v_info[tid] = info;
   }
-  // input-stationary schedule: one entry per source row of the band (windows are monotone in y)
-  const int nsrc = r_hi - r_lo;
-  for (int rr = tid; rr < min(nsrc, a.rmax); rr += kThreads) {
-    const int r = r_lo + rr;
-    int first = nrows, last = -1;
-    for (int yy = 0; yy < nrows; ++yy) {
-      const int4 info = sh.v_info[yy];
-      if (info.x <= r && r < info.x + info.y) {
-        first = min(first, yy);
-        last = yy;
+  // input-stationary schedules (windows are monotone in y): one entry per source row feeding output rows [ya, yb)
+  auto build_sched = [&](SchedRow* out, int ya, int yb, int cap) {
+    const int rlo = sh.v_info[ya].x;
+    const int n = sh.v_info[yb - 1].x + sh.v_info[yb - 1].y - rlo;
+    for (int rr = tid; rr < min(n, cap); rr += kThreads) {
+      const int r = rlo + rr;
+      int first = yb, last = -1;
+      for (int yy = ya; yy < yb; ++yy) {
+        const int4 info = sh.v_info[yy];
+        if (info.x <= r && r < info.x + info.y) {
+          first = min(first, yy);
+          last = yy;
+        }
       }
-    }
-    if (last < 0) first = 0;   // cannot happen (windows overlap); keeps the flush logic monotone anyway
-    SchedRow e;
+      if (last < 0) first = ya;   // cannot happen (windows overlap); keeps the flush logic monotone anyway
+      SchedRow e;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      float w = 0.f;
-      const int yy = first + k;
-      if (yy <= last) w = v_w[(yy * a.kstride + (r - sh.v_info[yy].x)) * 2];
-      e.w[k][0] = w;
-      e.w[k][1] = w;
+      for (int k = 0; k < 3; ++k) {
+        float w = 0.f;
+        const int yy = first + k;
+        if (yy <= last) w = v_w[(yy * a.kstride + (r - sh.v_info[yy].x)) * 2];
+        e.w[k][0] = w;
+        e.w[k][1] = w;
+      }
+      e.first = first;
+      e.pad = 0;
+      out[rr] = e;
+      atomicMax(&sh.m_max, last - first + 1);
     }
-    e.first = first;
-    e.pad = 0;
-    sched[rr] = e;
-    atomicMax(&sh.m_max, last - first + 1);
+    return n;
+  };
+  const int nsrc = r_hi - r_lo;
+  // TMA path: one stream over the whole band.  cp.async path: two streams of 16 output rows.
+  const int ysplit = min(nrows, kBandRows / 2);
+  const int cap_s = a.rmax / 2;
+  int nsrc_s0 = 0, nsrc_s1 = 0;
+  if (kBulk) {
+    build_sched(sched, 0, nrows, a.rmax);
+  } else {
+    nsrc_s0 = build_sched(sched, 0, ysplit, cap_s);
+    if (nrows > ysplit) nsrc_s1 = build_sched(sched + cap_s, ysplit, nrows, cap_s);
   }
   __syncthreads();
-  const bool use_is = (sh.m_max <= 3) && (nsrc <= a.rmax) && (((lp + P.w + 1) >> 1) <= kConsumerThreads);
+  const bool use_is = kBulk ? ((sh.m_max <= 3) && (nsrc <= a.rmax) && ((a.W & 3) == 0) &&
+                               ((((P.left & 7) + P.w + 3) >> 2) <= kConsumerThreads))
+                            : ((sh.m_max <= 3) && (nsrc_s0 <= cap_s) && (nsrc_s1 <= cap_s) && ((a.W & 3) == 0) &&
+                               ((((P.left & 3) + P.w + 3) >> 2) <= kConsumerThreads / 2));
 
+  MIS_STAMP(1);   // tables + schedule done
   float o[kSeg];     // this thread's 32 output pixels (row y0+lane, columns 32*warp ..)
 #pragma unroll
   for (int i = 0; i < kSeg; ++i) o[i] = 0.f;
@@ -519,17 +772,10 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
   if (warp == kConsumerWarps) {
     // ================================ producer warp =======================================
     if (kBulk && lane == 0) {
-      const int ph = (int)(e0 & 7);                          // W % 8 == 0: same phase for every row
-      const uint32_t nb = (uint32_t)((ph + P.w + 7) >> 3) << 4;
-      for (int ci = 0; ci < total_chunks; ++ci) {
+      for (int ci = issued; ci < total_chunks; ++ci) {
         const int slot = ci & (a.nch - 1);
-        if (ci >= a.nch) mbar_wait(&sh.empty[slot], ((ci >> a.nch_log2) - 1) & 1);
-        const int rbeg = r_lo + ci * kChunkRows;
-        const int rend = min(rbeg + kChunkRows, r_hi);
-        mbar_arrive_expect_tx(&sh.full[slot], nb * (uint32_t)(rend - rbeg));
-        for (int r = rbeg; r < rend; ++r)
-          bulk_g2s(ring + (size_t)(slot * kChunkRows + (r - rbeg)) * a.pitch, a.src + (e0 + (int64_t)r * a.W - ph), nb,
-                   &sh.full[slot]);
+        if (ci >= a.nch) mbar_spin_wait(&sh.empty[slot], ((ci >> a.nch_log2) - 1) & 1);
+        MIS_ISSUE_CHUNK(slot, r_lo + ci * kChunkRows);
       }
     }
     __syncwarp();
@@ -546,14 +792,26 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
     c.lane = lane;
     c.warp = warp;
     c.nrows = nrows;
-    c.lp = lp;
-    c.npairs = (lp + P.w + 1) >> 1;
+    c.lp = kBulk ? (P.left & 7) : lp;
+    c.npairs = (c.lp + P.w + 1) >> 1;
     c.w = P.w;
     c.h = P.h;
     c.r_lo = r_lo;
-    c.ring_byte0 = 2 * ((int)(e0 & 7) - lp);
-    if (use_is) v_pass_is<kBulk, kWindow>(c, sched, nsrc);
-    else switch (KV) {
+    c.coff = kBulk ? (P.left & 7) : (use_is ? (P.left & 3) : lp);   // tmp/slot column of crop column 0
+    c.gplane = a.src + (e0 - c.coff);
+    c.ring_byte0 = 0;
+    if (use_is && kBulk) {
+      v_pass_is<kBulk, kWindow>(c, sched, nsrc);
+    } else if (use_is) {
+      // zero the columns right of the crop that the unrolled H-pass taps may touch (their weights are 0)
+      const int c0z = 4 * ((c.coff + c.w + 3) >> 2), per = min(a.kstride + 2, a.pstr - c0z);
+      for (int i = tid; i < nrows * per; i += kConsumerThreads) tmp[(i / per) * a.pstr + c0z + (i % per)] = 0.f;
+      uint2* cpring = reinterpret_cast<uint2*>(ring);
+      if (warp < kConsumerWarps / 2)
+        v_pass_cp<kWindow>(c, sched, nsrc_s0, sh.v_info[0].x, 0, ysplit, cpring);
+      else if (nrows > ysplit)
+        v_pass_cp<kWindow>(c, sched + cap_s, nsrc_s1, sh.v_info[ysplit].x, ysplit, nrows, cpring);
+    } else switch (KV) {
       case 3: v_pass<3, kBulk, kWindow>(c); break;
       case 5: v_pass<5, kBulk, kWindow>(c); break;
       case 7: v_pass<7, kBulk, kWindow>(c); break;
@@ -561,7 +819,9 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
       case 13: v_pass<13, kBulk, kWindow>(c); break;
       default: v_pass_dyn<kBulk, kWindow>(c); break;
     }
+    MIS_STAMP(2);   // V pass done (this warp)
     bar_sync(1, kConsumerThreads);
+    MIS_STAMP(3);   // all V warps done
     if (warp * kSeg < s) {
       const float post = kWindow ? 1.f : (1.f / 65535.f);
       switch (KH) {
@@ -575,6 +835,7 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
     }
   }
 
+  MIS_STAMP(4);   // H pass done
   // ================================ colour ops =============================================
   cluster_wait_acquire();   // phase 1 done: all CTAs of the cluster are resident
   const bool row_ok = (warp < kConsumerWarps) && (lane < nrows);
@@ -617,6 +878,7 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
     }
   }
 
+  MIS_STAMP(5);   // colour ops (incl. cluster reduction) done
   // ================================ normalise + store ======================================
   if (row_ok && x0 < s) {
     const float mean = a.mean[chan], inv_std = a.inv_std[chan];
@@ -670,12 +932,44 @@ __global__ void __launch_bounds__(kThreads, 2) aug_kernel(const Args a) {
       }
     }
   }
+  MIS_STAMP(6);
+#undef MIS_STAMP
 }
 
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+// uint16 [rows, W] row-major, box [kChunkRows x box_w], no swizzle, out-of-bounds elements read as 0
+static int make_map(CUtensorMap* map, const uint16_t* base, uint64_t W, uint64_t rows, uint32_t box_w) {
+  EncodeTiledFn fn = encode_fn();
+  MIS_REQUIRE(fn, MIS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {W, rows};
+  const cuuint64_t strides[1] = {W * sizeof(uint16_t)};
+  const cuuint32_t box[2] = {box_w, (cuuint32_t)kChunkRows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MIS_REQUIRE(r == CUDA_SUCCESS, MIS_ERR_CUDA, "cuTensorMapEncodeTiled(uint16, box %u) failed with CUresult %d", box_w, (int)r);
+  return MIS_OK;
+}
+
 template <bool kBulk, bool kWindow>
-static int launch(const Args& a, int grid, size_t smem, cudaStream_t stream) {
+static int launch(const Args& a, const CUtensorMap* maps, int grid, size_t smem, cudaStream_t stream) {
   auto* fn = &aug_kernel<kBulk, kWindow>;
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
@@ -690,7 +984,7 @@ static int launch(const Args& a, int grid, size_t smem, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MIS_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, a));
+  MIS_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, maps[0], maps[1], maps[2], maps[3], a));
   return MIS_OK;
 }
 
@@ -698,6 +992,10 @@ static int launch(const Args& a, int grid, size_t smem, cudaStream_t stream) {
 }  // namespace mis
 
 using namespace mis;
+
+static long long* g_dbg = nullptr;
+// profiling aid (not part of the public ABI contract): device buffer of [grid][8] int64 clock stamps, or NULL
+extern "C" void mis_debug_set_stamp_buffer(void* p) { g_dbg = static_cast<long long*>(p); }
 
 extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H, int W, int64_t img_stride,
                                 const MisViewParams* params, int n_views, float win_lo, float win_hi,
@@ -746,6 +1044,8 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
   const int kunroll = kbound <= 3 ? 3 : kbound <= 5 ? 5 : kbound <= 7 ? 7 : kbound <= 9 ? 9 : kbound <= 13 ? 13 : kbound;
   a.kstride = align_up(kunroll, 4);
   // ring: the widest read window (kunroll rows) plus the chunk being filled; power of two for cheap wrap
+  // ring: 4 slots of 8 rows (32 rows in flight); the unrolled fallback's read window must fit next to the slot
+  // being filled
   int nch = 4;
   while (nch * kChunkRows < kunroll + 2 * kChunkRows) nch *= 2;
   a.nch = nch;
@@ -754,9 +1054,11 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
   MIS_REQUIRE(a.nch <= kMaxChunks, MIS_ERR_UNSUPPORTED,
               "mis_aug_two_view: H/s = %d/%d needs a %d-chunk ring (max %d)", H, s, a.nch, kMaxChunks);
   // TMA staging needs one 16-byte phase for all rows of a crop (W % 8 == 0); otherwise plain loads
-  const bool bulk = use_tma && (W % 8 == 0) && (img_stride % 8 == 0);
-  a.pitch = align_up(2 * W + 32, 16);
-  a.pstr = (W + 2 + a.kstride + 2) | 1;
+  // TMA staging views the batch as one [n_images*C*H, W] uint16 matrix: needs 16-byte row pitch and dense images
+  const bool bulk = use_tma && (W % 8 == 0) && (img_stride == (int64_t)C * H * W);
+  a.plane_rows = H;
+  a.slot_bytes = ((W + kBoxCols - 1) / kBoxCols) * kBoxBytes;
+  a.pstr = (W + 6 + a.kstride + 2) | 1;
   int off = align_up((int)sizeof(SmemHeader), 16);
   a.off_vw = off;
   off += align_up(kBandRows * a.kstride * 2 * 4, 16);
@@ -764,20 +1066,28 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
   off += align_up(s * a.kstride * 4, 16);
   a.off_tmp = off;
   off += align_up(kBandRows * a.pstr * 4, 128);
-  a.rmax = (kBandRows * ((H + s - 1) / s)) + a.kstride + 4;
+  a.rmax = (kBandRows * ((H + s - 1) / s)) + 2 * (a.kstride + 4);   // one band-long or two half-band schedules
   a.off_sched = off;
   off += align_up(a.rmax * (int)sizeof(SchedRow), 128);
+  off = align_up(off, 128);
   a.off_ring = off;
-  if (bulk) off += a.nch * kChunkRows * a.pitch;
+  if (bulk) off += a.nch * a.slot_bytes;
+  else off += kCpDepth * kConsumerThreads * 8;     // per-thread cp.async ring of the non-TMA path
   const size_t smem = (size_t)off;
   MIS_REQUIRE(smem <= 227 * 1024, MIS_ERR_UNSUPPORTED,
               "mis_aug_two_view: needs %zu B of shared memory per CTA (H=%d W=%d s=%d)", smem, H, W, s);
 
+  a.dbg = g_dbg;
   const bool window = !(win_lo == 0.f && win_hi == 65535.f);
   const int grid = a.nbands * n_views * C;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (bulk) return window ? launch<true, true>(a, grid, smem, st) : launch<true, false>(a, grid, smem, st);
-  return window ? launch<false, true>(a, grid, smem, st) : launch<false, false>(a, grid, smem, st);
+  CUtensorMap maps[4] = {};
+  if (bulk) {
+    for (int i = 0; i < 4; ++i)
+      if (int rc = make_map(&maps[i], src, (uint64_t)W, (uint64_t)n_images * C * H, 64u * (i + 1))) return rc;
+    return window ? launch<true, true>(a, maps, grid, smem, st) : launch<true, false>(a, maps, grid, smem, st);
+  }
+  return window ? launch<false, true>(a, maps, grid, smem, st) : launch<false, false>(a, maps, grid, smem, st);
 }
 
 extern "C" int64_t mis_aug_algorithmic_bytes(const MisViewParams* p, int n_views, int C, int s, int out_dtype) {

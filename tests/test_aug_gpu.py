@@ -101,6 +101,27 @@ def test_batch_matches_oracle(shape, crop):
             _check(out[v * B + i, 0], ref, f"{shape} crop {crop} img {i} view {v}")
 
 
+@pytest.mark.parametrize("shape,crop", [((512, 512), 224), ((512, 512), 96), ((300, 500), 64)])
+def test_cp_async_path_matches_tma_path_and_oracle(shape, crop):
+    """use_tma=False (per-thread cp.async ring, two 16-row streams) against use_tma=True and the oracle."""
+    H, W = shape
+    imgs = synth.batch_512(4, seed=13, H=H, W=W)
+    x = torch.from_numpy(imgs).cuda()
+    ta = _mk(crop, out_dtype=torch.float32, use_tma=True)
+    tb = _mk(crop, out_dtype=torch.float32, use_tma=False)
+    torch.manual_seed(77)
+    ta(x)
+    torch.manual_seed(77)
+    tb(x)
+    a, b = ta.views_buffer.cpu().numpy(), tb.views_buffer.cpu().numpy()
+    assert np.abs(a - b).max() <= 2e-6
+    p = tb.last_params
+    for i in range(4):
+        for v in range(2):
+            ref = A.apply_view(imgs[i], _oracle_params(p[2 * i + v]), crop, MEAN, STD)
+            _check(b[v * 4 + i, 0], ref, f"cp path {shape} img {i} view {v}")
+
+
 def test_bf16_output_is_rounded_fp32_output():
     imgs = synth.batch_512(8, seed=5)
     x = torch.from_numpy(imgs).cuda()
