@@ -384,48 +384,59 @@ __device__ __forceinline__ void v_pass_is(const Ctx& c, const SchedRow* __restri
 // ring: no producer, no mbarriers, no cross-thread hazards (a thread only reads what it copied itself).
 // The band's 32 output rows are split in two streams of 16 rows (warps 0-3 / 4-7), each walking its own source
 // row range, which halves the serial dependency chain per warp.
-constexpr int kCpDepth = 8;
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+constexpr int kCpDepth = 6;      // rows in flight per thread (the band is L2-prefetched at kernel entry)
+constexpr int kCpSlotBytes = 16; // bytes one thread stages per source row (8 columns; the 4-column variant uses half)
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool kWindow>
+// VEC = source columns per thread (4 -> 8-byte copies, 8 -> 16-byte copies); `t` = thread index inside the stream.
+template <int VEC, bool kWindow>
 __device__ __forceinline__ void v_pass_cp(const Ctx& c, const SchedRow* __restrict__ sched, int nsrc, int r_first,
-                                          int ya, int yb, uint2* __restrict__ ring) {
+                                          int ya, int yb, uint8_t* __restrict__ ring, int t) {
+  constexpr int NP = VEC / 2;                                  // packed pairs per thread
   const Args& a = *c.a;
-  const int q = c.tid & 127;                                   // column group inside the stream
-  const int ngroups = (c.coff + c.w + 3) >> 2;
-  const bool active = q < ngroups;
-  const int qa = active ? q : 0;
+  const int ngroups = (c.coff + c.w + VEC - 1) / VEC;
+  const bool active = t < ngroups;
+  const int ta = active ? t : 0;
   const int pstr = a.pstr;
-  const int wq = a.W >> 2;
+  const size_t row_bytes = (size_t)a.W * 2;
   const uint64_t wsc = pack2(a.win_scale, a.win_scale);
   const uint64_t wof = pack2(-a.win_lo * a.win_scale, -a.win_lo * a.win_scale);
-  const uint2* gp = reinterpret_cast<const uint2*>(c.gplane + (int64_t)r_first * a.W) + qa;
-  uint2* myr = ring + c.tid;                                   // slot k of this thread: myr[k * 256]
-  float* tp = c.tmp + ya * pstr + 4 * qa;
-  uint64_t a0 = 0ull, a1 = 0ull, b0 = 0ull, b1 = 0ull, c0 = 0ull, c1 = 0ull;
+  const uint8_t* gp = reinterpret_cast<const uint8_t*>(c.gplane + (int64_t)r_first * a.W) + (size_t)ta * VEC * 2;
+  uint8_t* myr = ring + (size_t)c.tid * kCpSlotBytes;          // slot k of this thread: myr + k * 256 * kCpSlotBytes
+  constexpr int kSlotStride = kConsumerThreads * kCpSlotBytes;
+  float* tp = c.tmp + ya * pstr + VEC * ta;
+  uint64_t acc[3][NP];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int i = 0; i < NP; ++i) acc[k][i] = 0ull;
   int ycur = ya;
 
   auto flush = [&](int target) {
 #pragma unroll 1
     for (; ycur < target; ++ycur) {
       if (active) {
-        float v0, v1, v2, v3;
-        unpack2(a0, v0, v1);
-        unpack2(a1, v2, v3);
-        tp[0] = v0;
-        tp[1] = v1;
-        tp[2] = v2;
-        tp[3] = v3;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          float v0, v1;
+          unpack2(acc[0][i], v0, v1);
+          tp[2 * i] = v0;
+          tp[2 * i + 1] = v1;
+        }
       }
       tp += pstr;
-      a0 = b0; a1 = b1;
-      b0 = c0; b1 = c1;
-      c0 = 0ull; c1 = 0ull;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        acc[0][i] = acc[1][i];
+        acc[1][i] = acc[2][i];
+        acc[2][i] = 0ull;
+      }
     }
   };
   auto conv = [&](uint32_t p) {
@@ -441,7 +452,7 @@ __device__ __forceinline__ void v_pass_cp(const Ctx& c, const SchedRow* __restri
 
 #pragma unroll
   for (int k = 0; k < kCpDepth; ++k) {
-    if (k < nsrc) cp_async8(myr + k * kConsumerThreads, gp + (size_t)k * wq);
+    if (k < nsrc) cp_async<VEC * 2>(myr + k * kSlotStride, gp + k * row_bytes);
     cp_async_commit();
   }
 #pragma unroll 1
@@ -451,20 +462,28 @@ __device__ __forceinline__ void v_pass_cp(const Ctx& c, const SchedRow* __restri
       const int rr = rr0 + k;
       if (rr < nsrc) {                                          // uniform
         cp_async_wait<kCpDepth - 1>();                          // the copy of row rr has landed
-        const uint2 p = myr[k * kConsumerThreads];
+        if (a.dbg && rr == 0 && c.tid == 0) a.dbg[(size_t)blockIdx.x * 8 + 7] = clock64();
+        uint32_t p[NP];
+        if (VEC == 8) {
+          const uint4 v = *reinterpret_cast<const uint4*>(myr + k * kSlotStride);
+          p[0] = v.x; p[1] = v.y; p[NP - 2] = v.z; p[NP - 1] = v.w;
+        } else {
+          const uint2 v = *reinterpret_cast<const uint2*>(myr + k * kSlotStride);
+          p[0] = v.x; p[NP - 1] = v.y;
+        }
         const float4 s0 = *reinterpret_cast<const float4*>(&sched[rr].w[0][0]);
         const float4 s1 = *reinterpret_cast<const float4*>(&sched[rr].w[2][0]);
-        if (rr + kCpDepth < nsrc) cp_async8(myr + k * kConsumerThreads, gp + (size_t)(rr + kCpDepth) * wq);
+        if (rr + kCpDepth < nsrc) cp_async<VEC * 2>(myr + k * kSlotStride, gp + (size_t)(rr + kCpDepth) * row_bytes);
         cp_async_commit();
         flush(__float_as_int(s1.z));
-        const uint64_t f0 = conv(p.x), f1 = conv(p.y);
         const uint64_t w0 = pack2(s0.x, s0.y), w1 = pack2(s0.z, s0.w), w2 = pack2(s1.x, s1.y);
-        a0 = ffma2(f0, w0, a0);
-        a1 = ffma2(f1, w0, a1);
-        b0 = ffma2(f0, w1, b0);
-        b1 = ffma2(f1, w1, b1);
-        c0 = ffma2(f0, w2, c0);
-        c1 = ffma2(f1, w2, c1);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          const uint64_t f = conv(p[i]);
+          acc[0][i] = ffma2(f, w0, acc[0][i]);
+          acc[1][i] = ffma2(f, w1, acc[1][i]);
+          acc[2][i] = ffma2(f, w2, acc[2][i]);
+        }
       }
     }
   }
@@ -748,21 +767,29 @@ aug_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CU
     return n;
   };
   const int nsrc = r_hi - r_lo;
-  // TMA path: one stream over the whole band.  cp.async path: two streams of 16 output rows.
-  const int ysplit = min(nrows, kBandRows / 2);
-  const int cap_s = a.rmax / 2;
-  int nsrc_s0 = 0, nsrc_s1 = 0;
+  // TMA path: one stream over the whole band.  cp.async path: NS independent streams of 32/NS output rows, each
+  // owned by 256/NS threads: 4 streams x 8 columns per thread when the crop fits 64 x 8 columns and rows are
+  // 16-byte aligned (W % 8 == 0), else 2 streams x 4 columns.
+  const bool wide8 = !kBulk && ((a.W & 7) == 0) && ((a.img_stride & 7) == 0) &&
+                     ((((P.left & 7) + P.w + 7) >> 3) <= kConsumerThreads / 4);
+  const int ns = wide8 ? 4 : 2;
+  const int rows_per_stream = kBandRows / ns;
+  const int cap_s = a.rmax / 4;
+  int nsrc_s[4] = {0, 0, 0, 0};
   if (kBulk) {
     build_sched(sched, 0, nrows, a.rmax);
   } else {
-    nsrc_s0 = build_sched(sched, 0, ysplit, cap_s);
-    if (nrows > ysplit) nsrc_s1 = build_sched(sched + cap_s, ysplit, nrows, cap_s);
+    for (int st = 0; st < ns; ++st) {
+      const int ya = st * rows_per_stream, yb = min(ya + rows_per_stream, nrows);
+      if (ya < nrows) nsrc_s[st] = build_sched(sched + st * cap_s, ya, yb, cap_s);
+    }
   }
   __syncthreads();
+  const int nsrc_max = max(max(nsrc_s[0], nsrc_s[1]), max(nsrc_s[2], nsrc_s[3]));
   const bool use_is = kBulk ? ((sh.m_max <= 3) && (nsrc <= a.rmax) && ((a.W & 3) == 0) &&
                                ((((P.left & 7) + P.w + 3) >> 2) <= kConsumerThreads))
-                            : ((sh.m_max <= 3) && (nsrc_s0 <= cap_s) && (nsrc_s1 <= cap_s) && ((a.W & 3) == 0) &&
-                               ((((P.left & 3) + P.w + 3) >> 2) <= kConsumerThreads / 2));
+                            : ((sh.m_max <= 3) && (nsrc_max <= cap_s) && ((a.W & 3) == 0) && ((a.img_stride & 3) == 0) &&
+                               (wide8 || ((((P.left & 3) + P.w + 3) >> 2) <= kConsumerThreads / 2)));
 
   MIS_STAMP(1);   // tables + schedule done
   float o[kSeg];     // this thread's 32 output pixels (row y0+lane, columns 32*warp ..)
@@ -797,20 +824,23 @@ aug_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CU
     c.w = P.w;
     c.h = P.h;
     c.r_lo = r_lo;
-    c.coff = kBulk ? (P.left & 7) : (use_is ? (P.left & 3) : lp);   // tmp/slot column of crop column 0
+    c.coff = kBulk ? (P.left & 7) : (use_is ? (wide8 ? (P.left & 7) : (P.left & 3)) : lp);   // tmp column of crop column 0
     c.gplane = a.src + (e0 - c.coff);
     c.ring_byte0 = 0;
     if (use_is && kBulk) {
       v_pass_is<kBulk, kWindow>(c, sched, nsrc);
     } else if (use_is) {
       // zero the columns right of the crop that the unrolled H-pass taps may touch (their weights are 0)
-      const int c0z = 4 * ((c.coff + c.w + 3) >> 2), per = min(a.kstride + 2, a.pstr - c0z);
+      const int vec = wide8 ? 8 : 4;
+      const int c0z = vec * ((c.coff + c.w + vec - 1) / vec), per = min(a.kstride + 2, a.pstr - c0z);
       for (int i = tid; i < nrows * per; i += kConsumerThreads) tmp[(i / per) * a.pstr + c0z + (i % per)] = 0.f;
-      uint2* cpring = reinterpret_cast<uint2*>(ring);
-      if (warp < kConsumerWarps / 2)
-        v_pass_cp<kWindow>(c, sched, nsrc_s0, sh.v_info[0].x, 0, ysplit, cpring);
-      else if (nrows > ysplit)
-        v_pass_cp<kWindow>(c, sched + cap_s, nsrc_s1, sh.v_info[ysplit].x, ysplit, nrows, cpring);
+      const int tps = kConsumerThreads / ns;                   // threads per stream
+      const int st = tid / tps, t = tid - st * tps;
+      const int ya = st * rows_per_stream, yb = min(ya + rows_per_stream, nrows);
+      if (ya < nrows) {
+        if (wide8) v_pass_cp<8, kWindow>(c, sched + st * cap_s, nsrc_s[st], sh.v_info[ya].x, ya, yb, ring, t);
+        else v_pass_cp<4, kWindow>(c, sched + st * cap_s, nsrc_s[st], sh.v_info[ya].x, ya, yb, ring, t);
+      }
     } else switch (KV) {
       case 3: v_pass<3, kBulk, kWindow>(c); break;
       case 5: v_pass<5, kBulk, kWindow>(c); break;
@@ -1066,13 +1096,13 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
   off += align_up(s * a.kstride * 4, 16);
   a.off_tmp = off;
   off += align_up(kBandRows * a.pstr * 4, 128);
-  a.rmax = (kBandRows * ((H + s - 1) / s)) + 2 * (a.kstride + 4);   // one band-long or two half-band schedules
+  a.rmax = (kBandRows * ((H + s - 1) / s)) + 4 * (a.kstride + 4);   // one band-long or up to four sub-band schedules
   a.off_sched = off;
   off += align_up(a.rmax * (int)sizeof(SchedRow), 128);
   off = align_up(off, 128);
   a.off_ring = off;
   if (bulk) off += a.nch * a.slot_bytes;
-  else off += kCpDepth * kConsumerThreads * 8;     // per-thread cp.async ring of the non-TMA path
+  else off += kCpDepth * kConsumerThreads * kCpSlotBytes;     // per-thread cp.async ring of the non-TMA path
   const size_t smem = (size_t)off;
   MIS_REQUIRE(smem <= 227 * 1024, MIS_ERR_UNSUPPORTED,
               "mis_aug_two_view: needs %zu B of shared memory per CTA (H=%d W=%d s=%d)", smem, H, W, s);

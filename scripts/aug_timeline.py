@@ -29,5 +29,7 @@ tot = s[:, 6] - s[:, 0]
 print(f"CTAs {grid}; CTA duration clk: mean {tot.mean():.0f} median {np.median(tot):.0f} p90 {np.percentile(tot,90):.0f}")
 for i, n in enumerate(names):
     print(f"  {n:22s} mean {d[:, i].mean():8.0f} clk  ({100*d[:, i].mean()/tot.mean():5.1f}%)  median {np.median(d[:, i]):8.0f}")
+first = s[:, 7] - s[:, 1]
+print(f"  [V pass] first row landed after {first.mean():.0f} clk (median {np.median(first):.0f}) from V-pass start")
 span = s[:, 6].max() - s[:, 0].min()
 print("kernel span (clk, across SMs; clocks not synchronised between SMs):", span)
