@@ -193,7 +193,7 @@ struct Ctx {
 
 // ---- V pass: lanes over source column pairs, K taps unrolled, packed FMAs -----------------------
 template <int K, bool kBulk, bool kWindow>
-__device__ __forceinline__ void v_pass(const Ctx& c) {
+__device__ __forceinline__ void v_pass(const Ctx& c, int ya, int yb, int ysub0) {
   const Args& a = *c.a;
   SmemHeader& sh = *c.sh;
   const int ring_mask = a.nch * kChunkRows - 1;
@@ -201,7 +201,7 @@ __device__ __forceinline__ void v_pass(const Ctx& c) {
   int loaded = 0, released = 0;
   const uint64_t wsc = pack2(a.win_scale, a.win_scale);
   const uint64_t wof = pack2(-a.win_lo * a.win_scale, -a.win_lo * a.win_scale);
-  for (int yy = 0; yy < c.nrows; ++yy) {
+  for (int yy = ya; yy < yb; ++yy) {
     const int4 info = sh.v_info[yy];     // {ymin, n, need, first}
     if (kBulk) {
       while (loaded < info.z) {
@@ -215,7 +215,7 @@ __device__ __forceinline__ void v_pass(const Ctx& c) {
       }
     }
     const uint64_t* wrow = reinterpret_cast<const uint64_t*>(c.v_w + yy * a.kstride * 2);
-    float* trow = c.tmp + yy * a.pstr;
+    float* trow = c.tmp + (yy - ysub0) * a.pstr;
     for (int q = c.tid; q < npad; q += kConsumerThreads) {
       uint64_t acc = 0ull;   // (+0.f, +0.f)
       if (q < c.npairs) {
@@ -397,7 +397,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // VEC = source columns per thread (4 -> 8-byte copies, 8 -> 16-byte copies); `t` = thread index inside the stream.
 template <int VEC, bool kWindow>
 __device__ __forceinline__ void v_pass_cp(const Ctx& c, const SchedRow* __restrict__ sched, int nsrc, int r_first,
-                                          int ya, int yb, uint8_t* __restrict__ ring, int t) {
+                                          int ya, int yb, int ysub0, uint8_t* __restrict__ ring, int t) {
   constexpr int NP = VEC / 2;                                  // packed pairs per thread
   const Args& a = *c.a;
   const int ngroups = (c.coff + c.w + VEC - 1) / VEC;
@@ -408,9 +408,9 @@ __device__ __forceinline__ void v_pass_cp(const Ctx& c, const SchedRow* __restri
   const uint64_t wsc = pack2(a.win_scale, a.win_scale);
   const uint64_t wof = pack2(-a.win_lo * a.win_scale, -a.win_lo * a.win_scale);
   const uint8_t* gp = reinterpret_cast<const uint8_t*>(c.gplane + (int64_t)r_first * a.W) + (size_t)ta * VEC * 2;
-  uint8_t* myr = ring + (size_t)c.tid * kCpSlotBytes;          // slot k of this thread: myr + k * 256 * kCpSlotBytes
-  constexpr int kSlotStride = kConsumerThreads * kCpSlotBytes;
-  float* tp = c.tmp + ya * pstr + VEC * ta;
+  uint8_t* myr = ring + (size_t)c.tid * (VEC * 2);             // lanes contiguous: conflict-free LDGSTS / LDS
+  constexpr int kSlotStride = kConsumerThreads * kCpSlotBytes;  // slot k of this thread: myr + k * kSlotStride
+  float* tp = c.tmp + (ya - ysub0) * pstr + VEC * ta;    // the tile holds one sub-band starting at output row ysub0
   uint64_t acc[3][NP];
 #pragma unroll
   for (int k = 0; k < 3; ++k)
@@ -488,17 +488,18 @@ __device__ __forceinline__ void v_pass_cp(const Ctx& c, const SchedRow* __restri
     }
   }
   flush(yb);
+  cp_async_wait<0>();
 }
 
 // dynamic-length fallback (tap counts outside the unrolled set)
 template <bool kBulk, bool kWindow>
-__device__ __forceinline__ void v_pass_dyn(const Ctx& c) {
+__device__ __forceinline__ void v_pass_dyn(const Ctx& c, int ya, int yb, int ysub0) {
   const Args& a = *c.a;
   SmemHeader& sh = *c.sh;
   const int ring_mask = a.nch * kChunkRows - 1;
   const int npad = min(c.npairs + a.kstride / 2 + 1, a.pstr / 2);
   int loaded = 0, released = 0;
-  for (int yy = 0; yy < c.nrows; ++yy) {
+  for (int yy = ya; yy < yb; ++yy) {
     const int4 info = sh.v_info[yy];
     if (kBulk) {
       while (loaded < info.z) {
@@ -512,7 +513,7 @@ __device__ __forceinline__ void v_pass_dyn(const Ctx& c) {
       }
     }
     const float* wrow = c.v_w + yy * a.kstride * 2;
-    float* trow = c.tmp + yy * a.pstr;
+    float* trow = c.tmp + (yy - ysub0) * a.pstr;
     for (int q = c.tid; q < npad; q += kConsumerThreads) {
       float a0 = 0.f, a1 = 0.f;
       if (q < c.npairs) {
@@ -588,8 +589,96 @@ __device__ __forceinline__ void h_pass_dyn(const Ctx& c, float (&o)[kSeg], float
   }
 }
 
+
+// ---- H pass for 16-row sub-bands: lane = (row 0..15, column half 0..1); a warp still owns 32 output columns --------
+template <int K>
+__device__ __forceinline__ void h_pass16(const Ctx& c, float* __restrict__ o, float post) {
+  const Args& a = *c.a;
+  const int xh = c.warp * kSeg + 16 * (c.lane >> 4);            // first column of this thread's 16-column run
+  const float* trow = c.tmp + (c.lane & 15) * a.pstr + c.coff;
+  constexpr int K4 = (K + 3) / 4;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int x = xh + i;
+    if (x < a.s) {
+      const float* tp = trow + c.sh->h_min[x];
+      const float4* wp = reinterpret_cast<const float4*>(c.h_w + x * a.kstride);
+      float acc = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < K4; ++j4) {
+        const float4 w = wp[j4];
+        acc = fmaf(tp[4 * j4], w.x, acc);
+        if (4 * j4 + 1 < K) acc = fmaf(tp[4 * j4 + 1], w.y, acc);
+        if (4 * j4 + 2 < K) acc = fmaf(tp[4 * j4 + 2], w.z, acc);
+        if (4 * j4 + 3 < K) acc = fmaf(tp[4 * j4 + 3], w.w, acc);
+      }
+      o[i] = acc * post;
+    }
+  }
+}
+__device__ __forceinline__ void h_pass16_dyn(const Ctx& c, float* __restrict__ o, float post) {
+  const Args& a = *c.a;
+  const int xh = c.warp * kSeg + 16 * (c.lane >> 4);
+  const float* trow = c.tmp + (c.lane & 15) * a.pstr + c.coff;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int x = xh + i;
+    if (x < a.s) {
+      const float* tp = trow + c.sh->h_min[x];
+      const float* wp = c.h_w + x * a.kstride;
+      float acc = 0.f;
+      for (int j = 0; j < c.sh->kh_max; ++j) acc = fmaf(tp[j], wp[j], acc);
+      o[i] = acc * post;
+    }
+  }
+}
+
+// ---- write RUN consecutive output pixels of one row (normalised values in v[0..RUN)), mirrored when flipped -------
+template <int RUN>
+__device__ __forceinline__ void store_run(const float* __restrict__ v, void* out_base, size_t row_off, int xs, int s,
+                                          bool flip, bool f32) {
+  const bool full = (xs + RUN <= s) && ((s & 7) == 0);
+  if (f32) {
+    float* out = reinterpret_cast<float*>(out_base) + row_off;
+    if (full) {
+      if (!flip) {
+        float4* dst = reinterpret_cast<float4*>(out + xs);
+#pragma unroll
+        for (int i = 0; i < RUN / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      } else {
+        float4* dst = reinterpret_cast<float4*>(out + (s - xs - RUN));
+#pragma unroll
+        for (int i = 0; i < RUN / 4; ++i)
+          dst[i] = make_float4(v[RUN - 1 - 4 * i], v[RUN - 2 - 4 * i], v[RUN - 3 - 4 * i], v[RUN - 4 - 4 * i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < RUN; ++i)
+        if (xs + i < s) out[flip ? (s - 1 - xs - i) : (xs + i)] = v[i];
+    }
+  } else {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_base) + row_off;
+    if (full) {
+      uint32_t pk[RUN / 2];
+#pragma unroll
+      for (int i = 0; i < RUN / 2; ++i) {
+        __nv_bfloat162 h = flip ? __floats2bfloat162_rn(v[RUN - 1 - 2 * i], v[RUN - 2 - 2 * i])
+                                : __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(out + (flip ? (s - xs - RUN) : xs));
+#pragma unroll
+      for (int i = 0; i < RUN / 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < RUN; ++i)
+        if (xs + i < s) out[flip ? (s - 1 - xs - i) : (xs + i)] = __float2bfloat16_rn(v[i]);
+    }
+  }
+}
+
 template <bool kBulk, bool kWindow>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kBulk ? 2 : 3)
 aug_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CUtensorMap map128,
            const __grid_constant__ CUtensorMap map192, const __grid_constant__ CUtensorMap map256, const Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -770,9 +859,9 @@ aug_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CU
   // TMA path: one stream over the whole band.  cp.async path: NS independent streams of 32/NS output rows, each
   // owned by 256/NS threads: 4 streams x 8 columns per thread when the crop fits 64 x 8 columns and rows are
   // 16-byte aligned (W % 8 == 0), else 2 streams x 4 columns.
-  const bool wide8 = !kBulk && ((a.W & 7) == 0) && ((a.img_stride & 7) == 0) &&
-                     ((((P.left & 7) + P.w + 7) >> 3) <= kConsumerThreads / 4);
-  const int ns = wide8 ? 4 : 2;
+  // (the 8-columns-per-thread variant is kept for experiments; the sub-band layout below uses 4 columns)
+  const bool wide8 = false;
+  const int ns = 4;                                              // 2 sub-bands x 2 streams of 8 output rows
   const int rows_per_stream = kBandRows / ns;
   const int cap_s = a.rmax / 4;
   int nsrc_s[4] = {0, 0, 0, 0};
@@ -789,7 +878,7 @@ aug_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CU
   const bool use_is = kBulk ? ((sh.m_max <= 3) && (nsrc <= a.rmax) && ((a.W & 3) == 0) &&
                                ((((P.left & 7) + P.w + 3) >> 2) <= kConsumerThreads))
                             : ((sh.m_max <= 3) && (nsrc_max <= cap_s) && ((a.W & 3) == 0) && ((a.img_stride & 3) == 0) &&
-                               (wide8 || ((((P.left & 3) + P.w + 3) >> 2) <= kConsumerThreads / 2)));
+                               ((((P.left & 3) + P.w + 3) >> 2) <= kConsumerThreads / 2));
 
   MIS_STAMP(1);   // tables + schedule done
   float o[kSeg];     // this thread's 32 output pixels (row y0+lane, columns 32*warp ..)
@@ -827,32 +916,61 @@ aug_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CU
     c.coff = kBulk ? (P.left & 7) : (use_is ? (wide8 ? (P.left & 7) : (P.left & 3)) : lp);   // tmp column of crop column 0
     c.gplane = a.src + (e0 - c.coff);
     c.ring_byte0 = 0;
-    if (use_is && kBulk) {
-      v_pass_is<kBulk, kWindow>(c, sched, nsrc);
-    } else if (use_is) {
-      // zero the columns right of the crop that the unrolled H-pass taps may touch (their weights are 0)
-      const int vec = wide8 ? 8 : 4;
-      const int c0z = vec * ((c.coff + c.w + vec - 1) / vec), per = min(a.kstride + 2, a.pstr - c0z);
-      for (int i = tid; i < nrows * per; i += kConsumerThreads) tmp[(i / per) * a.pstr + c0z + (i % per)] = 0.f;
-      const int tps = kConsumerThreads / ns;                   // threads per stream
-      const int st = tid / tps, t = tid - st * tps;
-      const int ya = st * rows_per_stream, yb = min(ya + rows_per_stream, nrows);
-      if (ya < nrows) {
-        if (wide8) v_pass_cp<8, kWindow>(c, sched + st * cap_s, nsrc_s[st], sh.v_info[ya].x, ya, yb, ring, t);
-        else v_pass_cp<4, kWindow>(c, sched + st * cap_s, nsrc_s[st], sh.v_info[ya].x, ya, yb, ring, t);
+    if (kBulk) {
+      if (use_is) v_pass_is<kBulk, kWindow>(c, sched, nsrc);
+      else switch (KV) {
+        case 3: v_pass<3, kBulk, kWindow>(c, 0, nrows, 0); break;
+        case 5: v_pass<5, kBulk, kWindow>(c, 0, nrows, 0); break;
+        case 7: v_pass<7, kBulk, kWindow>(c, 0, nrows, 0); break;
+        case 9: v_pass<9, kBulk, kWindow>(c, 0, nrows, 0); break;
+        case 13: v_pass<13, kBulk, kWindow>(c, 0, nrows, 0); break;
+        default: v_pass_dyn<kBulk, kWindow>(c, 0, nrows, 0); break;
       }
-    } else switch (KV) {
-      case 3: v_pass<3, kBulk, kWindow>(c); break;
-      case 5: v_pass<5, kBulk, kWindow>(c); break;
-      case 7: v_pass<7, kBulk, kWindow>(c); break;
-      case 9: v_pass<9, kBulk, kWindow>(c); break;
-      case 13: v_pass<13, kBulk, kWindow>(c); break;
-      default: v_pass_dyn<kBulk, kWindow>(c); break;
+    } else {
+      // non-TMA path: the band is processed as two 16-row sub-bands through a 16-row tile (34 KB instead of 68 KB,
+      // which lets three CTAs share an SM); each sub-band = two 8-row cp.async streams of 128 threads (or the
+      // output-stationary fallback), then its H pass.
+      if (use_is) {   // zero the columns right of the crop that the unrolled H-pass taps may touch (weights are 0)
+        const int c0z = 4 * ((c.coff + c.w + 3) >> 2), per = min(a.kstride + 2, a.pstr - c0z);
+        for (int i = tid; i < 16 * per; i += kConsumerThreads) tmp[(i / per) * a.pstr + c0z + (i % per)] = 0.f;
+      }
+      const float post = kWindow ? 1.f : (1.f / 65535.f);
+#pragma unroll
+      for (int sb = 0; sb < 2; ++sb) {
+        if (sb * 16 < nrows) {                                  // uniform
+          const int yb16 = min(sb * 16 + 16, nrows);
+          if (use_is) {
+            const int st = sb * 2 + (tid >> 7), t = tid & 127;
+            const int ya = st * rows_per_stream, yb = min(ya + rows_per_stream, nrows);
+            if (ya < nrows)
+              v_pass_cp<4, kWindow>(c, sched + st * cap_s, nsrc_s[st], sh.v_info[ya].x, ya, yb, sb * 16, ring, t);
+          } else switch (KV) {
+            case 3: v_pass<3, false, kWindow>(c, sb * 16, yb16, sb * 16); break;
+            case 5: v_pass<5, false, kWindow>(c, sb * 16, yb16, sb * 16); break;
+            case 7: v_pass<7, false, kWindow>(c, sb * 16, yb16, sb * 16); break;
+            case 9: v_pass<9, false, kWindow>(c, sb * 16, yb16, sb * 16); break;
+            case 13: v_pass<13, false, kWindow>(c, sb * 16, yb16, sb * 16); break;
+            default: v_pass_dyn<false, kWindow>(c, sb * 16, yb16, sb * 16); break;
+          }
+          bar_sync(1, kConsumerThreads);
+          if (warp * kSeg < s) {
+            switch (KH) {
+              case 3: h_pass16<3>(c, &o[16 * sb], post); break;
+              case 5: h_pass16<5>(c, &o[16 * sb], post); break;
+              case 7: h_pass16<7>(c, &o[16 * sb], post); break;
+              case 9: h_pass16<9>(c, &o[16 * sb], post); break;
+              case 13: h_pass16<13>(c, &o[16 * sb], post); break;
+              default: h_pass16_dyn(c, &o[16 * sb], post); break;
+            }
+          }
+          bar_sync(1, kConsumerThreads);                        // the tile is reused by the next sub-band
+        }
+      }
     }
     MIS_STAMP(2);   // V pass done (this warp)
-    bar_sync(1, kConsumerThreads);
+    if (kBulk) bar_sync(1, kConsumerThreads);
     MIS_STAMP(3);   // all V warps done
-    if (warp * kSeg < s) {
+    if (kBulk && warp * kSeg < s) {
       const float post = kWindow ? 1.f : (1.f / 65535.f);
       switch (KH) {
         case 3: h_pass<3>(c, o, post); break;
@@ -868,8 +986,15 @@ aug_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CU
   MIS_STAMP(4);   // H pass done
   // ================================ colour ops =============================================
   cluster_wait_acquire();   // phase 1 done: all CTAs of the cluster are resident
-  const bool row_ok = (warp < kConsumerWarps) && (lane < nrows);
+  // element idx of o[] sits at output row y0 + elem_row(idx), column elem_x(idx):
+  //   TMA path      : lane = row, one run of 32 columns per thread
+  //   non-TMA path  : idx = 16*sub-band + i, lane = (row & 15, column half), two runs of 16 columns per thread
   const int x0 = warp * kSeg;
+  auto elem_ok = [&](int idx) {
+    const int row = kBulk ? lane : ((idx >> 4) * 16 + (lane & 15));
+    const int x = kBulk ? (x0 + idx) : (x0 + 16 * (lane >> 4) + (idx & 15));
+    return (warp < kConsumerWarps) && row < nrows && x < s;
+  };
   if (P.flags & MIS_VIEW_JITTER) {
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
@@ -881,11 +1006,9 @@ aug_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CU
       } else if (op == 1) {
         // mean over the whole view: thread -> warp -> CTA -> cluster (DSMEM)
         float part = 0.f;
-        if (row_ok) {
 #pragma unroll
-          for (int i = 0; i < kSeg; ++i)
-            if (x0 + i < s) part += o[i];
-        }
+        for (int i = 0; i < kSeg; ++i)
+          if (elem_ok(i)) part += o[i];
         part = warp_sum(part);
         if (warp < kConsumerWarps && lane == 0) sh.red[warp] = part;
         __syncthreads();
@@ -910,55 +1033,19 @@ aug_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CU
 
   MIS_STAMP(5);   // colour ops (incl. cluster reduction) done
   // ================================ normalise + store ======================================
-  if (row_ok && x0 < s) {
+  if (warp < kConsumerWarps && x0 < s) {
     const float mean = a.mean[chan], inv_std = a.inv_std[chan];
 #pragma unroll
     for (int i = 0; i < kSeg; ++i) o[i] = (o[i] - mean) * inv_std;
     const bool flip = (P.flags & MIS_VIEW_FLIP) != 0;
-    const size_t row_off = ((size_t)plane * s + (y0 + lane)) * s;
-    const bool full = (x0 + kSeg <= s) && ((s & 7) == 0);
-    if (a.out_f32) {
-      float* out = reinterpret_cast<float*>(a.out) + row_off;
-      if (full) {
-        if (!flip) {
-          float4* dst = reinterpret_cast<float4*>(out + x0);
-#pragma unroll
-          for (int i = 0; i < kSeg / 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-        } else {
-          float4* dst = reinterpret_cast<float4*>(out + (s - x0 - kSeg));
-#pragma unroll
-          for (int i = 0; i < kSeg / 4; ++i)
-            dst[i] = make_float4(o[kSeg - 1 - 4 * i], o[kSeg - 2 - 4 * i], o[kSeg - 3 - 4 * i], o[kSeg - 4 - 4 * i]);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < kSeg; ++i)
-          if (x0 + i < s) out[flip ? (s - 1 - x0 - i) : (x0 + i)] = o[i];
-      }
+    if (kBulk) {
+      if (lane < nrows) store_run<kSeg>(o, a.out, ((size_t)plane * s + (y0 + lane)) * s, x0, s, flip, a.out_f32 != 0);
     } else {
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out) + row_off;
-      if (full) {
-        uint32_t pk[kSeg / 2];
-        if (!flip) {
 #pragma unroll
-          for (int i = 0; i < kSeg / 2; ++i) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < kSeg / 2; ++i) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(o[kSeg - 1 - 2 * i], o[kSeg - 2 - 2 * i]);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h);
-          }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(out + (flip ? (s - x0 - kSeg) : x0));
-#pragma unroll
-        for (int i = 0; i < kSeg / 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < kSeg; ++i)
-          if (x0 + i < s) out[flip ? (s - 1 - x0 - i) : (x0 + i)] = __float2bfloat16_rn(o[i]);
+      for (int sb = 0; sb < 2; ++sb) {
+        const int row = sb * 16 + (lane & 15), xs = x0 + 16 * (lane >> 4);
+        if (row < nrows && xs < s)
+          store_run<16>(&o[16 * sb], a.out, ((size_t)plane * s + (y0 + row)) * s, xs, s, flip, a.out_f32 != 0);
       }
     }
   }
@@ -1095,8 +1182,13 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
   a.off_hw = off;
   off += align_up(s * a.kstride * 4, 16);
   a.off_tmp = off;
-  off += align_up(kBandRows * a.pstr * 4, 128);
-  a.rmax = (kBandRows * ((H + s - 1) / s)) + 4 * (a.kstride + 4);   // one band-long or up to four sub-band schedules
+  off += align_up((bulk ? kBandRows : kBandRows / 2) * a.pstr * 4, 128);   // transposition tile: band or 16-row sub-band
+  // schedule capacity: one band-long schedule (TMA path) or four quarter-band schedules (cp.async path)
+  {
+    const int sup = (H + s - 1) / s;
+    const bool bulk_path = use_tma && (W % 8 == 0) && (img_stride == (int64_t)C * H * W);
+    a.rmax = bulk_path ? (kBandRows * sup + a.kstride + 4) : 4 * ((kBandRows / 4) * sup + a.kstride + 4);
+  }
   a.off_sched = off;
   off += align_up(a.rmax * (int)sizeof(SchedRow), 128);
   off = align_up(off, 128);
