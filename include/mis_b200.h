@@ -104,8 +104,10 @@ int mis_draw_two_view_params(uint8_t* rng_state, int64_t rng_state_len, int n_im
  *   mean,std   host float[C]
  *   out        [n_views, C, s, s] in out_dtype (MIS_DTYPE_BF16 or MIS_DTYPE_F32), NCHW
  *   s          output crop size, 8 <= s <= 256
- *   use_tma    1: stage crop rows through shared memory with cp.async.bulk (TMA) -- default
- *              0: read crop rows through L1/L2 with plain loads (debug / A-B comparison)
+ *   use_tma    1: a producer warp stages crop rows with 2-D TMA tensor-map boxes (cp.async.bulk.tensor) into a
+ *                 shared-memory ring (needs W % 8 == 0 and dense images, otherwise falls back to 0)
+ *              0: every thread stages its own columns with cp.async into a private ring, two 16-row sub-bands
+ *                 per band (fastest measured on B200: 3 CTAs/SM)
  * ------------------------------------------------------------------------------------------ */
 int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H, int W, int64_t img_stride,
                      const MisViewParams* params, int n_views, float win_lo, float win_hi,
@@ -143,7 +145,8 @@ int64_t mis_aug_algorithmic_bytes(const MisViewParams* params_host, int n_views,
  *                     TMEM as the A operand of the second MMA; dU (128 x D fp32) stays in TMEM for
  *                     the whole column walk.  grad_out may be NULL (= 1).  dz has z's dtype.
  *
- * rows, cols, row0 multiples of 128; D a multiple of 32, 32 <= D <= 256; T >= 0.025.
+ * rows, cols, row0 multiples of 128; D a multiple of 32 (backward: D <= 256, or a multiple of 256 -- wider
+ * embeddings are walked in 256-column slices of dU, recomputing S per slice); T >= 0.025.
  * `scratch` must hold mis_ntxent_scratch_bytes(rows, cols, D) bytes.
  * ------------------------------------------------------------------------------------------ */
 int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D);

@@ -49,6 +49,7 @@ struct TileArgs {
   int rows, cols, D, row0;
   int col_tiles, tiles_per_split;
   float k1;                // log2(e) / T
+  int d0, ds;              // backward: columns [d0, d0 + ds) of dU are produced by this launch (ds <= 256)
   const float* cexp;       // [cols] exp(1/T - lse_j)            (backward)
   float* partial;          // fwd: [nsplit][rows]   bwd: [nsplit][rows][D]
 };
@@ -214,8 +215,8 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
       auto push_g = [&](int t) {   // U^T boxes [D x 32 columns] for dU += W . U_J
         for (int kb = 0; kb < kTile / kKBlock; ++kb) {
           mbar_wait(&bars.empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&bars.full[stage], a.D * 128);
-          tma_load_2d(smem + stage * kStageBytes, &map_ut, (t_begin + t) * kTile + kb * kKBlock, 0, &bars.full[stage]);
+          mbar_arrive_expect_tx(&bars.full[stage], a.ds * 128);
+          tma_load_2d(smem + stage * kStageBytes, &map_ut, (t_begin + t) * kTile + kb * kKBlock, a.d0, &bars.full[stage]);
           advance();
         }
       };
@@ -236,7 +237,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
         }
       };
       const uint32_t idesc_s = make_idesc(kTile, kTile);
-      const uint32_t idesc_g = make_idesc(kTile, a.D);
+      const uint32_t idesc_g = make_idesc(kTile, a.ds);
       auto mma_g = [&](int t) {    // dU += W(t) . U_J(t);  W lives in TMEM where S(t) was
         const int pb = t & 1;
         mbar_wait(&bars.epi_done[pb], (t >> 1) & 1);
@@ -346,8 +347,8 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
     } else {
       mbar_wait(&bars.du_full, 0);
       tc_fence_after();
-      float* dst = a.partial + ((size_t)split * a.rows + row_tile * kTile + r_in) * a.D;
-      for (int c = 0; c < a.D / 32; ++c) {
+      float* dst = a.partial + ((size_t)split * a.rows + row_tile * kTile + r_in) * a.D + a.d0;
+      for (int c = 0; c < a.ds / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem + tlane + (uint32_t)(kDuCol + c * 32), v);
         tmem_wait_ld();
@@ -449,34 +450,23 @@ __global__ void bwd_finalize_kernel(const float* __restrict__ partial, int nspli
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= rows) return;
-  const int half = rows >> 1;
   const float g = scale * (grad_out ? grad_out[0] : 1.f);
   const float r = rinv[i];
-  float du[8], uu[8];   // D <= 256
+  auto du_at = [&](int d) {
+    float s = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) s += partial[((size_t)sp * rows + i) * D + d];
+    return g * s;
+  };
   float dot = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int d = lane + 32 * k;
-    du[k] = 0.f;
-    uu[k] = 0.f;
-    if (d < D) {
-      float s = 0.f;
-      for (int sp = 0; sp < nsplit; ++sp) s += partial[((size_t)sp * rows + i) * D + d];
-      du[k] = g * s;
-      uu[k] = load_as_f32(z_rows, (size_t)i * D + d) * r;
-      dot = fmaf(uu[k], du[k], dot);
-    }
-  }
+  for (int d = lane; d < D; d += 32) dot = fmaf(load_as_f32(z_rows, (size_t)i * D + d) * r, du_at(d), dot);
   dot = warp_sum(dot);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int d = lane + 32 * k;
-    if (d < D) {
-      const float v = (du[k] - uu[k] * dot) * r;
-      if constexpr (sizeof(T) == 4) dz[(size_t)i * D + d] = v;
-      else dz[(size_t)i * D + d] = __float2bfloat16_rn(v);
-    }
+  for (int d = lane; d < D; d += 32) {
+    const float v = (du_at(d) - load_as_f32(z_rows, (size_t)i * D + d) * r * dot) * r;
+    if constexpr (sizeof(T) == 4) dz[(size_t)i * D + d] = v;
+    else dz[(size_t)i * D + d] = __float2bfloat16_rn(v);
   }
+  (void)u_all;
+  (void)row0;
 }
 
 // BYOL: loss = 2 - 2 mean cos(p_i,t_i); dp_i = -(2/n) (t^_i - cos_i p^_i)/|p_i|.  One warp per row.
@@ -569,11 +559,13 @@ static Plan make_plan(int rows, int cols) {
 }
 static inline size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
 
-static int check_shapes(const char* who, int rows, int cols, int D, int row0, float inv_T) {
+static int check_shapes(const char* who, int rows, int cols, int D, int row0, float inv_T, bool bwd) {
   MIS_REQUIRE(rows > 0 && cols > 0 && D > 0, MIS_ERR_INVALID_ARG, "%s: sizes must be positive", who);
   MIS_REQUIRE(rows % kTile == 0 && cols % kTile == 0 && row0 % kTile == 0, MIS_ERR_UNSUPPORTED,
               "%s: rows (%d), cols (%d) and row0 (%d) must be multiples of %d", who, rows, cols, row0, kTile);
-  MIS_REQUIRE(D % kKBlock == 0 && D <= 256, MIS_ERR_UNSUPPORTED, "%s: D=%d must be a multiple of 32 and <= 256", who, D);
+  MIS_REQUIRE(D % kKBlock == 0 && D <= 8192, MIS_ERR_UNSUPPORTED, "%s: D=%d must be a multiple of 32 (<= 8192)", who, D);
+  MIS_REQUIRE(!bwd || D <= 256 || D % 256 == 0, MIS_ERR_UNSUPPORTED,
+              "%s: D=%d > 256 must be a multiple of 256 (the backward walks dU in 256-column slices)", who, D);
   MIS_REQUIRE(row0 >= 0 && row0 + rows <= cols, MIS_ERR_INVALID_ARG, "%s: rows [%d,%d) outside [0,%d)", who, row0,
               row0 + rows, cols);
   MIS_REQUIRE(inv_T > 0.f && inv_T <= 40.f, MIS_ERR_UNSUPPORTED,
@@ -618,7 +610,7 @@ extern "C" int mis_ntxent_prep(const void* z, int z_dtype, int rows, int D, floa
 extern "C" int mis_ntxent_fwd(const float* u_all, int cols, int D, int row0, int rows, float inv_T, float* lse_rows,
                               float* loss, void* scratch, int64_t scratch_bytes, void* stream) {
   MIS_REQUIRE(u_all && lse_rows && loss && scratch, MIS_ERR_INVALID_ARG, "mis_ntxent_fwd: null pointer");
-  if (int rc = check_shapes("mis_ntxent_fwd", rows, cols, D, row0, inv_T)) return rc;
+  if (int rc = check_shapes("mis_ntxent_fwd", rows, cols, D, row0, inv_T, false)) return rc;
   MIS_REQUIRE(scratch_bytes >= mis_ntxent_scratch_bytes(rows, cols, D), MIS_ERR_INVALID_ARG,
               "mis_ntxent_fwd: scratch too small (%lld < %lld)", (long long)scratch_bytes,
               (long long)mis_ntxent_scratch_bytes(rows, cols, D));
@@ -652,7 +644,7 @@ extern "C" int mis_ntxent_bwd(const float* u_all, const float* lse_all, const vo
                               const float* grad_out, void* dz, void* scratch, int64_t scratch_bytes, void* stream) {
   MIS_REQUIRE(u_all && lse_all && z_rows && rinv_rows && dz && scratch, MIS_ERR_INVALID_ARG, "mis_ntxent_bwd: null pointer");
   MIS_REQUIRE(z_dtype == MIS_DTYPE_F32 || z_dtype == MIS_DTYPE_BF16, MIS_ERR_INVALID_ARG, "mis_ntxent_bwd: dtype %d", z_dtype);
-  if (int rc = check_shapes("mis_ntxent_bwd", rows, cols, D, row0, inv_T)) return rc;
+  if (int rc = check_shapes("mis_ntxent_bwd", rows, cols, D, row0, inv_T, true)) return rc;
   MIS_REQUIRE(scratch_bytes >= mis_ntxent_scratch_bytes(rows, cols, D), MIS_ERR_INVALID_ARG,
               "mis_ntxent_bwd: scratch too small (%lld < %lld)", (long long)scratch_bytes,
               (long long)mis_ntxent_scratch_bytes(rows, cols, D));
@@ -670,17 +662,23 @@ extern "C" int mis_ntxent_bwd(const float* u_all, const float* lse_all, const vo
 
   CUtensorMap map_u, map_ut;
   if (int rc = make_map(&map_u, u_all, (uint64_t)D, (uint64_t)cols, kTile)) return rc;
-  if (int rc = make_map(&map_ut, ut, (uint64_t)cols, (uint64_t)D, (uint32_t)D)) return rc;
+  const int ds = D <= 256 ? D : 256;     // dU lives in TMEM columns 256..511: at most 256 columns per launch;
+                                         // wider embeddings recompute S once per 256-column slice
+  if (int rc = make_map(&map_ut, ut, (uint64_t)cols, (uint64_t)D, (uint32_t)ds)) return rc;
   TileArgs a = {};
   a.rows = rows; a.cols = cols; a.D = D; a.row0 = row0;
   a.col_tiles = p.col_tiles; a.tiles_per_split = p.tiles_per_split;
   a.k1 = kLog2e * inv_T;
   a.cexp = cexp;
   a.partial = partial;
+  a.ds = ds;
   auto* fn = &ntxent_tile_kernel<true>;
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map_u, map_ut, a);
-  MIS_CUDA_TRY(cudaGetLastError());
+  for (int d0 = 0; d0 < D; d0 += ds) {
+    a.d0 = d0;
+    fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map_u, map_ut, a);
+    MIS_CUDA_TRY(cudaGetLastError());
+  }
 
   const float scale = grad_scale * inv_T / (float)rows;
   const int wpb = 8;

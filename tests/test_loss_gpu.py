@@ -29,7 +29,8 @@ def _grad_ok(got, ref, what):
 
 
 @pytest.mark.parametrize("n,d,clustered", [(64, 32, False), (128, 128, False), (256, 128, True), (1024, 128, False),
-                                           (1024, 128, True), (512, 256, False), (192, 64, True)])
+                                           (1024, 128, True), (512, 256, False), (192, 64, True),
+                                           (128, 512, False), (64, 2048, False)])
 def test_ntxent_matches_oracle(n, d, clustered):
     from medical_image_segmentation_b200 import nt_xent_loss
     z1, z2 = synth.embeddings(n, d, seed=n + d, clustered=clustered)
