@@ -170,6 +170,18 @@ int mis_ntxent_bwd(const float* u_all, const float* lse_all, const void* z_rows,
 int mis_byol_loss_fwd_bwd(const float* preds, const float* targets, int rows, int D, float* loss,
                           float* dpreds, float* scratch_rows, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Exact per-channel moments of uint16 slices: the statistics behind the normalisation constants.
+ * Replaces the float64 streaming sums of compute_mean_and_std
+ * (medical_image_segmentation/analyze_data/compute_dataset_metrics.py:12-29).
+ *
+ *   src    uint16 [n_images, C, plane_elems] (16-byte aligned, plane_elems % 8 == 0, n_images*C <= 65535)
+ *   sums   device uint64 [C][2], ACCUMULATED into (caller zeroes it): sums[c][0] += sum x, sums[c][1] += sum x^2
+ * Both sums are exact integers; mean = s0/n, std = sqrt(s1/n - mean^2) are formed by the caller in float64.
+ * ------------------------------------------------------------------------------------------ */
+int mis_u16_moments(const uint16_t* src, long long n_images, int C, long long plane_elems,
+                    unsigned long long* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,18 +5,20 @@ Public surface (mirrors the reference's transform / loss call sites, see DESIGN.
     FusedTwoViewTransforms(crop_size, mean, std, blur_prob=(0,0), solarize_prob=(0,0))(x) -> [view1, view2]
     nt_xent_loss(z_a, z_b, temperature=0.1, group=None) -> scalar
     byol_cosine_loss(preds, targets) -> scalar
+    compute_mean_and_std(loader) -> (mean, std)      (analyze_data/compute_dataset_metrics.py:12-29)
     register_datamodule / get_datamodule            (registry hook of lightning_module.py:21-36)
 
 Importing this package loads libmis_b200.so; there is no CPU fallback.
 """
 from . import _lib  # noqa: F401  (fails loudly when the CUDA library is missing)
 from .loss import byol_cosine_loss, nt_xent_loss, nt_xent_rows
+from .metrics import compute_mean_and_std
 from .params import draw_two_view_params, draw_two_view_params_torch
 from .registry import DATAMODULE_REGISTRY, get_datamodule, register_datamodule
 from .transforms import FusedTwoViewTransforms, algorithmic_bytes
 
 __all__ = [
     "FusedTwoViewTransforms", "algorithmic_bytes", "nt_xent_loss", "nt_xent_rows", "byol_cosine_loss",
-    "draw_two_view_params", "draw_two_view_params_torch", "register_datamodule", "get_datamodule",
+    "compute_mean_and_std", "draw_two_view_params", "draw_two_view_params_torch", "register_datamodule", "get_datamodule",
     "DATAMODULE_REGISTRY",
 ]

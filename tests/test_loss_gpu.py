@@ -119,3 +119,18 @@ def test_byol_loss_matches_reference_golden():
         pr = torch.from_numpy(g[f"preds_{i}"]).double().requires_grad_(True)
         L.byol_cosine_loss(pr, torch.from_numpy(g[f"targets_{i}"]).double()).backward()
         _grad_ok(p.grad.cpu().numpy(), pr.grad.numpy(), f"byol case {i}")
+
+
+def test_mean_std_matches_reference_formula():
+    """compute_mean_and_std (analyze_data/compute_dataset_metrics.py:12-29) restated in float64 on the CPU."""
+    from medical_image_segmentation_b200 import compute_mean_and_std
+    imgs = synth.batch_512(6, seed=9, H=200, W=256)
+    batches = [torch.from_numpy(imgs[i:i + 2])[:, None].cuda() for i in range(0, 6, 2)]
+    mean, std = compute_mean_and_std([(b, None) for b in batches])
+    x = torch.from_numpy(imgs.astype(np.int64)).to(torch.float64)
+    ref_mean = x.sum() / x.numel()
+    ref_std = torch.sqrt((x ** 2).sum() / x.numel() - ref_mean ** 2)
+    assert abs(float(mean[0]) - float(ref_mean)) <= 1e-9 * float(ref_mean)
+    assert abs(float(std[0]) - float(ref_std)) <= 1e-9 * float(ref_std)
+    m01, s01 = compute_mean_and_std(batches, scale=1.0 / 65535.0)
+    assert abs(float(m01[0]) - float(ref_mean) / 65535.0) < 1e-12
