@@ -257,8 +257,10 @@ __device__ __forceinline__ void v_pass(const Ctx& c, int ya, int yb, int ysub0) 
 }
 
 
-// Input-stationary schedule: source row rr of the band feeds output rows first .. first+2 of the band with the
-// (duplicated, FFMA2-ready) weights w[0..2]; rows before `first` are complete when rr is reached.
+// Input-stationary schedule: source row rr feeds output rows first .. first+2 with (duplicated, FFMA2-ready) weights.
+// TMA path: w[k] belongs to output row first + k and the three accumulators rotate when a row completes.
+// cp.async path: output row ya + j of a stream accumulates in the FIXED accumulator j % 3 and w[j % 3] holds its weight.
+// Rows before `first` are complete when rr is reached.
 struct __align__(16) SchedRow {
   float w[3][2];
   int first;
@@ -399,6 +401,7 @@ template <int VEC, bool kWindow>
 __device__ __forceinline__ void v_pass_cp(const Ctx& c, const SchedRow* __restrict__ sched, int nsrc, int r_first,
                                           int ya, int yb, int ysub0, uint8_t* __restrict__ ring, int t) {
   constexpr int NP = VEC / 2;                                  // packed pairs per thread
+  constexpr int kStreamRows = kBandRows / 4;                   // output rows per stream (8)
   const Args& a = *c.a;
   const int ngroups = (c.coff + c.w + VEC - 1) / VEC;
   const bool active = t < ngroups;
@@ -407,38 +410,16 @@ __device__ __forceinline__ void v_pass_cp(const Ctx& c, const SchedRow* __restri
   const size_t row_bytes = (size_t)a.W * 2;
   const uint64_t wsc = pack2(a.win_scale, a.win_scale);
   const uint64_t wof = pack2(-a.win_lo * a.win_scale, -a.win_lo * a.win_scale);
-  const uint8_t* gp = reinterpret_cast<const uint8_t*>(c.gplane + (int64_t)r_first * a.W) + (size_t)ta * VEC * 2;
+  const uint8_t* gnext = reinterpret_cast<const uint8_t*>(c.gplane + (int64_t)r_first * a.W) + (size_t)ta * VEC * 2;
   uint8_t* myr = ring + (size_t)c.tid * (VEC * 2);             // lanes contiguous: conflict-free LDGSTS / LDS
-  constexpr int kSlotStride = kConsumerThreads * kCpSlotBytes;  // slot k of this thread: myr + k * kSlotStride
+  constexpr int kSlotStride = kConsumerThreads * kCpSlotBytes;  // ring slot k of this thread: myr + k * kSlotStride
   float* tp = c.tmp + (ya - ysub0) * pstr + VEC * ta;    // the tile holds one sub-band starting at output row ysub0
-  uint64_t acc[3][NP];
+  uint64_t acc[3][NP];                                         // output row ya + j accumulates in acc[j % 3] (static)
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll
     for (int i = 0; i < NP; ++i) acc[k][i] = 0ull;
-  int ycur = ya;
 
-  auto flush = [&](int target) {
-#pragma unroll 1
-    for (; ycur < target; ++ycur) {
-      if (active) {
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          float v0, v1;
-          unpack2(acc[0][i], v0, v1);
-          tp[2 * i] = v0;
-          tp[2 * i + 1] = v1;
-        }
-      }
-      tp += pstr;
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        acc[0][i] = acc[1][i];
-        acc[1][i] = acc[2][i];
-        acc[2][i] = 0ull;
-      }
-    }
-  };
   auto conv = [&](uint32_t p) {
     uint64_t f = u16x2_to_f32x2(p);
     if (kWindow) {
@@ -449,33 +430,44 @@ __device__ __forceinline__ void v_pass_cp(const Ctx& c, const SchedRow* __restri
     }
     return f;
   };
-
+  int to_fetch = nsrc;                                         // rows not yet requested
 #pragma unroll
   for (int k = 0; k < kCpDepth; ++k) {
-    if (k < nsrc) cp_async<VEC * 2>(myr + k * kSlotStride, gp + k * row_bytes);
+    if (to_fetch > 0) cp_async<VEC * 2>(myr + k * kSlotStride, gnext);
     cp_async_commit();
+    gnext += row_bytes;
+    --to_fetch;
   }
-#pragma unroll 1
-  for (int rr0 = 0; rr0 < nsrc; rr0 += kCpDepth) {
+  const SchedRow* sp = sched;
+  const SchedRow* const sp_end = sched + nsrc;
+  uint8_t* slot = myr;                                         // ring slot of the next source row
+  uint8_t* const slot_end = myr + kCpDepth * kSlotStride;
+  // Static unroll over the stream's output rows: while the next source row still belongs to output row ya + j
+  // (its `first` open row is <= ya + j) it is accumulated into the three fixed accumulators; then row j is stored.
 #pragma unroll
-    for (int k = 0; k < kCpDepth; ++k) {
-      const int rr = rr0 + k;
-      if (rr < nsrc) {                                          // uniform
-        cp_async_wait<kCpDepth - 1>();                          // the copy of row rr has landed
-        if (a.dbg && rr == 0 && c.tid == 0) a.dbg[(size_t)blockIdx.x * 8 + 7] = clock64();
+  for (int j = 0; j < kStreamRows; ++j) {
+    if (ya + j < yb) {                                          // uniform
+#pragma unroll 1
+      while (sp < sp_end) {
+        const float4 s1 = *reinterpret_cast<const float4*>(&sp->w[2][0]);
+        if (__float_as_int(s1.z) > ya + j) break;              // uniform: this source row opens a later output row
+        const float4 s0 = *reinterpret_cast<const float4*>(&sp->w[0][0]);
+        cp_async_wait<kCpDepth - 1>();                          // the copy of this row has landed
         uint32_t p[NP];
         if (VEC == 8) {
-          const uint4 v = *reinterpret_cast<const uint4*>(myr + k * kSlotStride);
+          const uint4 v = *reinterpret_cast<const uint4*>(slot);
           p[0] = v.x; p[1] = v.y; p[NP - 2] = v.z; p[NP - 1] = v.w;
         } else {
-          const uint2 v = *reinterpret_cast<const uint2*>(myr + k * kSlotStride);
+          const uint2 v = *reinterpret_cast<const uint2*>(slot);
           p[0] = v.x; p[NP - 1] = v.y;
         }
-        const float4 s0 = *reinterpret_cast<const float4*>(&sched[rr].w[0][0]);
-        const float4 s1 = *reinterpret_cast<const float4*>(&sched[rr].w[2][0]);
-        if (rr + kCpDepth < nsrc) cp_async<VEC * 2>(myr + k * kSlotStride, gp + (size_t)(rr + kCpDepth) * row_bytes);
+        if (to_fetch > 0) cp_async<VEC * 2>(slot, gnext);       // refill the slot just read
         cp_async_commit();
-        flush(__float_as_int(s1.z));
+        gnext += row_bytes;
+        --to_fetch;
+        ++sp;
+        slot += kSlotStride;
+        if (slot == slot_end) slot = myr;
         const uint64_t w0 = pack2(s0.x, s0.y), w1 = pack2(s0.z, s0.w), w2 = pack2(s1.x, s1.y);
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
@@ -485,9 +477,19 @@ __device__ __forceinline__ void v_pass_cp(const Ctx& c, const SchedRow* __restri
           acc[2][i] = ffma2(f, w2, acc[2][i]);
         }
       }
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          float v0, v1;
+          unpack2(acc[j % 3][i], v0, v1);
+          tp[j * pstr + 2 * i] = v0;
+          tp[j * pstr + 2 * i + 1] = v1;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NP; ++i) acc[j % 3][i] = 0ull;
     }
   }
-  flush(yb);
   cp_async_wait<0>();
 }
 
@@ -841,12 +843,12 @@ aug_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CU
       if (last < 0) first = ya;   // cannot happen (windows overlap); keeps the flush logic monotone anyway
       SchedRow e;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        float w = 0.f;
-        const int yy = first + k;
-        if (yy <= last) w = v_w[(yy * a.kstride + (r - sh.v_info[yy].x)) * 2];
-        e.w[k][0] = w;
-        e.w[k][1] = w;
+      for (int k = 0; k < 3; ++k) e.w[k][0] = e.w[k][1] = 0.f;
+      for (int yy = first; yy <= last && yy < first + 3; ++yy) {     // output row yy accumulates in slot (yy - ya) % 3
+        const float w = v_w[(yy * a.kstride + (r - sh.v_info[yy].x)) * 2];
+        const int slot = kBulk ? (yy - first) : ((yy - ya) % 3);   // TMA path rotates accumulators, cp path keeps them fixed
+        e.w[slot][0] = w;
+        e.w[slot][1] = w;
       }
       e.first = first;
       e.pad = 0;
