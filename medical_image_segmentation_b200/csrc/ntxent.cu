@@ -37,9 +37,9 @@ namespace ntx {
 
 constexpr int kTile = 128;             // rows per CTA tile, columns per S tile
 constexpr int kKBlock = 32;            // fp32 elements per 128-byte swizzle row
-constexpr int kStageBytes = 32 * 1024; // A k-block (16 KB) + B k-block (16 KB), or one U^T k-block (D*128 B)
-constexpr int kStages = 6;
-constexpr int kThreads = 192;
+constexpr int kRingBytes = 192 * 1024;  // operand ring (+ resident row tile); see smem plan in the kernel
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 352;           // warps 0, 10: TMA producers; warp 1: MMA issuer; warps 2-5 / 6-9: two epilogue groups
 constexpr int kEpiThreads = 128;
 constexpr int kTmemCols = 512;
 constexpr int kDuCol = 256;            // TMEM column where the dU accumulator starts
@@ -55,8 +55,9 @@ struct TileArgs {
 };
 
 struct Bars {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t a_full;          // resident row tile U_I has landed
   uint64_t tmem_full[2];
   uint64_t epi_done[2];
   uint64_t du_full;
@@ -155,7 +156,19 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
                    const TileArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  Bars& bars = *reinterpret_cast<Bars*>(smem + kStages * kStageBytes);
+  Bars& bars = *reinterpret_cast<Bars*>(smem + kRingBytes);
+  // smem plan (192 KB).  D <= 128: the row tile U_I stays RESIDENT (D/32 k-blocks of 16 KB, loaded once) and the ring
+  // has 2 stages of 64 KB, each a WHOLE operand tile (all k-blocks of U_J, or all four U^T boxes): the MMA thread then
+  // issues 16 MMAs (~1k clk of tensor work) per barrier round trip -- with one 4-MMA k-block per stage its own
+  // wait/commit loop (~700 clk) left the tensor pipe idle 60 % of the time.  Wider D: 6 stages of 32 KB holding one
+  // (U_I, U_J) k-block pair or one U^T box of 256 rows.
+  const bool res_a = a.D <= 128;
+  const int kStages = res_a ? 2 : 6;
+  const int kStageBytes = res_a ? 64 * 1024 : 32 * 1024;
+  const int kps_s = res_a ? a.D / kKBlock : 1;                   // k-blocks per stage, S phase
+  const int kps_g = res_a ? kTile / kKBlock : 1;                 // k-blocks per stage, dU phase
+  uint8_t* const smem_a = smem;                                  // resident U_I (only when res_a)
+  uint8_t* const ring = smem + (res_a ? 64 * 1024 : 0);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row_tile = blockIdx.x, split = blockIdx.y;
@@ -170,10 +183,11 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < kStages; ++i) {
+      for (int i = 0; i < kMaxStages; ++i) {
         mbar_init(&bars.full[i], 1);
         mbar_init(&bars.empty[i], 1);
       }
+      mbar_init(&bars.a_full, 1);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bars.tmem_full[i], 1);
         mbar_init(&bars.epi_done[i], kEpiThreads);
@@ -192,31 +206,51 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
   tc_fence_after();
   const uint32_t tmem = bars.tmem_ptr;
 
-  if (warp == 0) {
-    // ===================================== TMA producer =====================================
+  if (warp == 0 || warp == 10) {
+    // ===================================== TMA producers =====================================
+    // One thread sustains only ~1 TMA box per 455 clk (measured, scripts/micro/tma_lat.cu), less than the MMA
+    // consumes, so two producer threads in different warps walk the same stage sequence and issue alternate stages.
     if (lane == 0) {
-      int stage = 0, phase = 0;
+      const int parity = warp == 0 ? 0 : 1;
+      int stage = 0, phase = 0, n = 0;
       auto advance = [&]() {
+        ++n;
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
       };
-      auto push_s = [&](int t) {   // operands of S = U_I . U_J^T, one stage per 32-wide k-block
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&bars.empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * kStageBytes;
-          mbar_arrive_expect_tx(&bars.full[stage], 2 * kTile * 128);
-          tma_load_2d(sa, &map_u, kb * kKBlock, g_row_tile0, &bars.full[stage]);
-          tma_load_2d(sa + kTile * 128, &map_u, kb * kKBlock, (t_begin + t) * kTile, &bars.full[stage]);
+      if (res_a && parity == 0) {    // resident row tile, loaded once
+        mbar_arrive_expect_tx(&bars.a_full, (uint32_t)KB * kTile * 128);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_a + kb * kTile * 128, &map_u, kb * kKBlock, g_row_tile0, &bars.a_full);
+      }
+      auto push_s = [&](int t) {   // operands of S = U_I . U_J^T
+        for (int kb = 0; kb < KB; kb += kps_s) {
+          if ((n & 1) == parity) {
+            mbar_wait(&bars.empty[stage], phase ^ 1);
+            uint8_t* sa = ring + stage * kStageBytes;
+            if (res_a) {             // the whole U_J tile in one stage
+              mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)KB * kTile * 128);
+              for (int k2 = 0; k2 < KB; ++k2)
+                tma_load_2d(sa + k2 * kTile * 128, &map_u, k2 * kKBlock, (t_begin + t) * kTile, &bars.full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&bars.full[stage], 2 * kTile * 128);
+              tma_load_2d(sa, &map_u, kb * kKBlock, g_row_tile0, &bars.full[stage]);
+              tma_load_2d(sa + kTile * 128, &map_u, kb * kKBlock, (t_begin + t) * kTile, &bars.full[stage]);
+            }
+          }
           advance();
         }
       };
-      auto push_g = [&](int t) {   // U^T boxes [D x 32 columns] for dU += W . U_J
-        for (int kb = 0; kb < kTile / kKBlock; ++kb) {
-          mbar_wait(&bars.empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&bars.full[stage], a.ds * 128);
-          tma_load_2d(smem + stage * kStageBytes, &map_ut, (t_begin + t) * kTile + kb * kKBlock, a.d0, &bars.full[stage]);
+      auto push_g = [&](int t) {   // U^T boxes [ds x 32 columns] for dU += W . U_J
+        for (int kb = 0; kb < kTile / kKBlock; kb += kps_g) {
+          if ((n & 1) == parity) {
+            mbar_wait(&bars.empty[stage], phase ^ 1);
+            uint8_t* sa = ring + stage * kStageBytes;
+            mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)kps_g * a.ds * 128);
+            for (int k2 = 0; k2 < kps_g; ++k2)
+              tma_load_2d(sa + k2 * a.ds * 128, &map_ut, (t_begin + t) * kTile + (kb + k2) * kKBlock, a.d0, &bars.full[stage]);
+          }
           advance();
         }
       };
@@ -242,32 +276,42 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
         const int pb = t & 1;
         mbar_wait(&bars.epi_done[pb], (t >> 1) & 1);
         tc_fence_after();
-        for (int kb = 0; kb < kTile / kKBlock; ++kb) {
+        for (int kb = 0; kb < kTile / kKBlock; kb += kps_g) {
           mbar_wait(&bars.full[stage], phase);
           tc_fence_after();
-          const uint64_t bd = make_desc(smem + stage * kStageBytes);
+          for (int k2 = 0; k2 < kps_g; ++k2) {
+            const uint64_t bd = make_desc(ring + stage * kStageBytes + k2 * a.ds * 128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_ts(tmem + kDuCol, tmem + pb * kTile + kb * kKBlock + k * 8, bd + (uint64_t)(k * 2), idesc_g,
-                   (uint32_t)((t | kb | k) != 0));
+            for (int k = 0; k < 4; ++k)
+              mma_ts(tmem + kDuCol, tmem + pb * kTile + (kb + k2) * kKBlock + k * 8, bd + (uint64_t)(k * 2), idesc_g,
+                     (uint32_t)((t | (kb + k2) | k) != 0));
+          }
           tc_commit(&bars.empty[stage]);
           advance();
         }
       };
+      if (res_a) {
+        mbar_wait(&bars.a_full, 0);
+        tc_fence_after();
+      }
       for (int t = 0; t < T; ++t) {
         const int buf = t & 1;
         if (!kBwd && t >= 2) {     // forward: S[buf] is free once the epilogue of tile t-2 has read it
           mbar_wait(&bars.epi_done[buf], ((t - 2) >> 1) & 1);
           tc_fence_after();
         }
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = 0; kb < KB; kb += kps_s) {
           mbar_wait(&bars.full[stage], phase);
           tc_fence_after();
-          const uint8_t* sa = smem + stage * kStageBytes;
-          const uint64_t ad = make_desc(sa), bd = make_desc(sa + kTile * 128);
+          const uint8_t* sa = ring + stage * kStageBytes;
+          for (int k2 = 0; k2 < kps_s; ++k2) {
+            const uint64_t ad = res_a ? make_desc(smem_a + (kb + k2) * kTile * 128) : make_desc(sa);
+            const uint64_t bd = res_a ? make_desc(sa + k2 * kTile * 128) : make_desc(sa + kTile * 128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_ss(tmem + buf * kTile, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_s, (uint32_t)((kb | k) != 0));
+            for (int k = 0; k < 4; ++k)
+              mma_ss(tmem + buf * kTile, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_s,
+                     (uint32_t)(((kb + k2) | k) != 0));
+          }
           tc_commit(&bars.empty[stage]);
           advance();
         }
@@ -279,23 +323,27 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
         tc_commit(&bars.du_full);
       }
     }
-  } else {
+  } else if (warp >= 2 && warp <= 9) {
     // ===================================== epilogue ==========================================
+    // Two groups of four warps: group g owns the tiles t with t & 1 == g, i.e. always TMEM buffer g, so the
+    // exp-bound epilogue of tile t overlaps the epilogue of tile t+1 (and the MMAs of both).
+    const int grp = (warp - 2) >> 2;
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int r_in = quad * 32 + lane;               // row inside the tile == TMEM lane
-    const int etid = tid - 64;
+    const int etid = (tid - 64) & 127;
     const uint32_t tlane = (uint32_t)(quad * 32) << 16;
     const float ci = kBwd ? a.cexp[g_row_tile0 + r_in] : 0.f;
     const float k1 = a.k1;
     const int il = row_tile * kTile + r_in;                       // local row index
     const int pos_col = a.row0 + (il + (a.rows >> 1)) % a.rows;   // global column of this row's positive
-    float rowsum = 0.f;
-    for (int t = 0; t < T; ++t) {
-      const int buf = t & 1;
+    float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;         // independent partial sums: no serial FADD chain
+    for (int t = grp; t < T; t += 2) {
+      const int buf = grp;
       const int col0 = (t_begin + t) * kTile;
       if (kBwd) {
+        bar_sync(2 + grp, kEpiThreads);                         // previous tile's readers of cj[buf] are done
         bars.cj[buf][etid] = a.cexp[col0 + etid];
-        bar_sync(2, kEpiThreads);
+        bar_sync(2 + grp, kEpiThreads);
       }
       mbar_wait(&bars.tmem_full[buf], (t >> 1) & 1);
       tc_fence_after();
@@ -315,10 +363,11 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float e = ex2f(fmaf(__uint_as_float(v[j]), k1, -k1));
-            if (kBwd)
-              v[j] = to_tf32(e * (ci + bars.cj[buf][c * 32 + j]));
-            else
-              rowsum += e;
+            if (kBwd) v[j] = to_tf32(e * (ci + bars.cj[buf][c * 32 + j]));
+            else if ((j & 3) == 0) rs0 += e;
+            else if ((j & 3) == 1) rs1 += e;
+            else if ((j & 3) == 2) rs2 += e;
+            else rs3 += e;
           }
         } else {
           const int jd = diag ? (r_in - c * 32) : -1;   // position of the diagonal inside this chunk
@@ -332,7 +381,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
               if (j == jp) w -= 2.f;
               v[j] = to_tf32(w);
             } else {
-              rowsum += e;
+              rs0 += e;
             }
           }
         }
@@ -343,12 +392,13 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
       mbar_arrive(&bars.epi_done[buf]);
     }
     if (!kBwd) {
-      a.partial[(size_t)split * a.rows + row_tile * kTile + r_in] = rowsum;
+      // each group writes its own partial row sums: partial[(2*split + grp)][row]
+      a.partial[(size_t)(2 * split + grp) * a.rows + row_tile * kTile + r_in] = (rs0 + rs1) + (rs2 + rs3);
     } else {
       mbar_wait(&bars.du_full, 0);
       tc_fence_after();
       float* dst = a.partial + ((size_t)split * a.rows + row_tile * kTile + r_in) * a.D + a.d0;
-      for (int c = 0; c < a.ds / 32; ++c) {
+      for (int c = grp; c < a.ds / 32; c += 2) {                // the two groups read alternate 32-column chunks
         uint32_t v[32];
         tmem_ld32(tmem + tlane + (uint32_t)(kDuCol + c * 32), v);
         tmem_wait_ld();
@@ -574,7 +624,7 @@ static int check_shapes(const char* who, int rows, int cols, int D, int row0, fl
   return MIS_OK;
 }
 
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + sizeof(Bars) + 1024;
+constexpr size_t kSmemBytes = (size_t)kRingBytes + sizeof(Bars) + 1024;
 
 }  // namespace ntx
 }  // namespace mis
@@ -632,7 +682,7 @@ extern "C" int mis_ntxent_fwd(const float* u_all, int cols, int D, int row0, int
   fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map_u, map_u, a);
   MIS_CUDA_TRY(cudaGetLastError());
   float* row_loss = reinterpret_cast<float*>(sc);     // reuses the (backward-only) cexp slot
-  fwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(partial, p.nsplit, u_all, D, row0, rows, inv_T, lse_rows, row_loss);
+  fwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(partial, 2 * p.nsplit, u_all, D, row0, rows, inv_T, lse_rows, row_loss);
   MIS_CUDA_TRY(cudaGetLastError());
   mean_kernel<<<1, 1024, 0, st>>>(row_loss, rows, loss);
   MIS_CUDA_TRY(cudaGetLastError());
