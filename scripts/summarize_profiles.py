@@ -39,7 +39,7 @@ def main():
     if os.path.exists(rep):
         with open(os.path.join(OUT, f"{tag}_aug_final_ncu.md"), "w") as f:
             f.write(f"# K1 aug_kernel, final build of {tag}: `ncu --set full --clock-control none`\n\n"
-                    "Command: `python scripts/prof_aug.py 1024 224 1` = the bench workload (1024 slices 512x512 u16 -> 2048 views 224x224 bf16).\n"
+                    "Command: `python scripts/prof_aug.py 1024 224 0` (default non-TMA staging) = the bench workload (1024 slices 512x512 u16 -> 2048 views 224x224 bf16).\n"
                     "Times under ncu are cold-cache/serialised; bench.py's CUDA-event time is the number of record.\n\n")
             for v, u in raw(rep):
                 f.write(f"## {v.get('Kernel Name', '')[:80]}\n\n")
