@@ -85,6 +85,13 @@ int mis_draw_two_view_params(uint8_t* rng_state, int64_t rng_state_len, int n_im
                              int H, int W, const float* blur_prob, const float* solarize_prob,
                              MisViewParams* out, int* n_done);
 
+/* Single-view "Resize((s,s)) + ColorJitter(brightness, contrast)" records (the Decathlon flavour of the chain,
+ * lightning_module.py:684-693): box = whole image, no flip, jitter always applied; consumes randperm(4) and one
+ * uniform per non-zero magnitude per image exactly like torchvision's ColorJitter.make_params
+ * (v2/_color.py:146-154).  out[i] for i < n_images. */
+int mis_draw_resize_jitter_params(uint8_t* rng_state, int64_t rng_state_len, int n_images, int img0,
+                                  int H, int W, float brightness, float contrast, MisViewParams* out);
+
 /* ------------------------------------------------------------------------------------------
  * Fused two-view augmentation (kernel K1).
  *

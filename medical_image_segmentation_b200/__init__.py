@@ -15,10 +15,10 @@ from .loss import byol_cosine_loss, nt_xent_loss, nt_xent_rows
 from .metrics import compute_mean_and_std
 from .params import draw_two_view_params, draw_two_view_params_torch
 from .registry import DATAMODULE_REGISTRY, get_datamodule, register_datamodule
-from .transforms import FusedTwoViewTransforms, algorithmic_bytes
+from .transforms import FusedResizeJitterTransforms, FusedTwoViewTransforms, algorithmic_bytes
 
 __all__ = [
-    "FusedTwoViewTransforms", "algorithmic_bytes", "nt_xent_loss", "nt_xent_rows", "byol_cosine_loss",
+    "FusedTwoViewTransforms", "FusedResizeJitterTransforms", "algorithmic_bytes", "nt_xent_loss", "nt_xent_rows", "byol_cosine_loss",
     "compute_mean_and_std", "draw_two_view_params", "draw_two_view_params_torch", "register_datamodule", "get_datamodule",
     "DATAMODULE_REGISTRY",
 ]

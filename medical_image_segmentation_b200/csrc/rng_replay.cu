@@ -220,3 +220,47 @@ extern "C" int mis_draw_two_view_params(uint8_t* rng_state, int64_t rng_state_le
   store(rng_state, e);
   return MIS_OK;
 }
+
+// Single-view "Resize + ColorJitter(brightness, contrast)" parameters: the Decathlon flavour of the chain
+// (lightning_module.py:684-693: Resize((s,s)) -> ColorJitter(brightness=0.2, contrast=0.2) -> ToDtype -> Normalize).
+// torchvision ColorJitter.make_params (v2/_color.py:146-154): randperm(4), then one uniform per non-None factor;
+// a magnitude of 0 makes the factor None (no draw), v2/_color.py _check_input.
+extern "C" int mis_draw_resize_jitter_params(uint8_t* rng_state, int64_t rng_state_len, int n_images, int img0, int H, int W,
+                                             float brightness, float contrast, MisViewParams* out) {
+  using namespace mis;
+  using namespace mis::rng;
+  MIS_REQUIRE(rng_state && out, MIS_ERR_INVALID_ARG, "mis_draw_resize_jitter_params: null pointer");
+  MIS_REQUIRE(rng_state_len == kStateLen, MIS_ERR_INVALID_ARG,
+              "mis_draw_resize_jitter_params: rng state is %lld bytes, expected %lld", (long long)rng_state_len,
+              (long long)kStateLen);
+  MIS_REQUIRE(n_images >= 0 && H > 0 && W > 0 && brightness >= 0.f && contrast >= 0.f, MIS_ERR_INVALID_ARG,
+              "mis_draw_resize_jitter_params: bad arguments");
+  Engine e;
+  load(rng_state, e);
+  for (int i = 0; i < n_images; ++i) {
+    MisViewParams& p = out[i];
+    p.img = img0 + i;
+    p.top = 0;
+    p.left = 0;
+    p.h = H;
+    p.w = W;
+    p.flags = MIS_VIEW_JITTER;
+    uint8_t perm[4] = {0, 1, 2, 3};
+    for (int k = 0; k < 3; ++k) {
+      const uint32_t z = e.random() % (uint32_t)(4 - k);
+      const uint8_t sav = perm[k];
+      perm[k] = perm[k + z];
+      perm[k + z] = sav;
+    }
+    memcpy(p.order, perm, 4);
+    const float blo = 1.f - brightness < 0.f ? 0.f : 1.f - brightness;
+    p.brightness = brightness > 0.f ? e.uniform(blo, 1.f + brightness) : 1.f;
+    const float clo = 1.f - contrast < 0.f ? 0.f : 1.f - contrast;
+    p.contrast = contrast > 0.f ? e.uniform(clo, 1.f + contrast) : 1.f;
+    p.saturation = 1.f;
+    p.hue = 0.f;
+    p.reserved = 0;
+  }
+  store(rng_state, e);
+  return MIS_OK;
+}

@@ -164,3 +164,54 @@ def algorithmic_bytes(params: np.ndarray, C_: int, crop_size: int, out_dtype=tor
     p = np.ascontiguousarray(params)
     return int(_lib.lib.mis_aug_algorithmic_bytes(p.ctypes.data, p.shape[0], C_, crop_size,
                                                   MIS_DTYPE_F32 if out_dtype == torch.float32 else MIS_DTYPE_BF16))
+
+
+class FusedResizeJitterTransforms(FusedTwoViewTransforms):
+    """Single-view flavour of the chain used by the reference's Decathlon data module
+    (train/data_loaders/lightning_module.py:684-712): ``Resize((s, s))`` (antialiased bilinear) ->
+    ``ColorJitter(brightness, contrast)`` (train) or nothing (default/val) -> ``ToDtype(float32, scale=True)`` ->
+    ``Normalize(mean, std)``.  Runs on the same fused kernel K1 with one record per image (box = whole slice).
+
+    ``__call__(x) -> [B, C, s, s]``.  ``brightness=contrast=None`` reproduces ``default_transforms`` (no RNG use).
+    """
+
+    def __init__(self, size, mean, std, brightness=None, contrast=None, *, out_dtype=torch.bfloat16, window=None,
+                 use_tma: bool = False):
+        super().__init__(size, mean, std, (0.0, 0.0), (0.0, 0.0), out_dtype=out_dtype, window=window, use_tma=use_tma)
+        self.brightness = brightness
+        self.contrast = contrast
+
+    def draw_params(self, B: int, H: int, W: int) -> np.ndarray:
+        out = np.zeros(B, VIEW_PARAMS_DTYPE)
+        if self.brightness is None and self.contrast is None:          # default_transforms: no ColorJitter in the chain
+            out["img"] = np.arange(B)
+            out["h"], out["w"] = H, W
+            out["order"] = (0, 1, 2, 3)
+            out["brightness"] = out["contrast"] = out["saturation"] = 1.0
+            return out
+        state = torch.get_rng_state()
+        blob = state.numpy()
+        rc = _lib.lib.mis_draw_resize_jitter_params(blob.ctypes.data, blob.nbytes, B, 0, H, W,
+                                                    float(self.brightness or 0.0), float(self.contrast or 0.0),
+                                                    out.ctypes.data)
+        _lib.check(rc, "mis_draw_resize_jitter_params")
+        torch.set_rng_state(state)
+        return out
+
+    def __call__(self, x) -> torch.Tensor:
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(x)
+        if x.dim() == 2:
+            x = x[None, None]
+        elif x.dim() == 3:
+            x = x[:, None]
+        if not x.is_cuda:
+            if not torch.cuda.is_available():
+                raise RuntimeError("FusedResizeJitterTransforms has no CPU path: a CUDA device is required")
+            x = (x if x.is_pinned() else x.pin_memory()).cuda(non_blocking=True)
+        B, _, H, W = x.shape
+        params = self.draw_params(B, H, W)
+        self.last_params = params
+        out = self.apply(x, params)
+        self.views_buffer = out
+        return out

@@ -85,6 +85,22 @@ class TwoViewChainTV:
         return [view(x) for view in self.views]
 
 
+class ResizeJitterChainTV:
+    """Restates DecathlonDataModule.train_transforms / default_transforms (image branch,
+    lightning_module.py:684-693, 703-711) with torchvision v2: Resize((s,s)) -> [ColorJitter(b, c)] -> ToDtype -> Normalize."""
+
+    def __init__(self, size, mean, std, brightness=None, contrast=None):
+        from torchvision.transforms import v2 as T
+        ops = [T.ToImage(), T.Resize((size, size))]
+        if brightness is not None or contrast is not None:
+            ops.append(T.ColorJitter(brightness=brightness or 0, contrast=contrast or 0))
+        ops += [T.ToDtype(torch.float32, scale=True), T.Normalize(mean=mean, std=std)]
+        self.chain = T.Compose(ops)
+
+    def __call__(self, x):
+        return self.chain(x)
+
+
 def u16_to_tv_image(x_u16: np.ndarray | torch.Tensor):
     """uint16 [H,W] or [C,H,W] -> tv_tensors.Image float32 [C,H,W] in [0,1]."""
     from torchvision import tv_tensors

@@ -184,3 +184,20 @@ def test_determinism_and_view_halves():
     assert torch.equal(buf_a, t.views_buffer)
     assert a1.data_ptr() == buf_a.data_ptr() or True
     assert torch.equal(torch.cat([b1, b2]), t.views_buffer)
+
+
+@pytest.mark.parametrize("jitter", [True, False])
+def test_resize_jitter_flavour_matches_torchvision_chain(jitter):
+    """Decathlon image branch (lightning_module.py:684-693 / 703-711) vs the torchvision chain on the same RNG stream."""
+    from medical_image_segmentation_b200 import FusedResizeJitterTransforms
+    H, W, s = 320, 320, 224
+    imgs = synth.batch_512(3, seed=41, H=H, W=W)
+    kw = dict(brightness=0.2, contrast=0.2) if jitter else {}
+    t = FusedResizeJitterTransforms(s, (0.1181,), (0.1720,), out_dtype=torch.float32, **kw)
+    chain = A.ResizeJitterChainTV(s, (0.1181,), (0.1720,), **kw)
+    torch.manual_seed(5)
+    out = t(torch.from_numpy(imgs).cuda()).cpu().numpy()
+    torch.manual_seed(5)
+    for i in range(3):
+        ref = chain(A.u16_to_tv_image(imgs[i]))[0].numpy()
+        _check(out[i, 0], ref, f"decathlon flavour img {i}")

@@ -94,3 +94,30 @@ def test_handback_images_are_drawn_by_torch_and_stay_bit_exact(monkeypatch):
     ref = orig(3, 512, 512, img0=i)              # pure torch replay of image i and its two successors
     for name in VIEW_PARAMS_DTYPE.names:
         assert np.array_equal(ref[name], p[name][2 * i:2 * i + 6]), name
+
+
+def test_resize_jitter_params_match_torchvision_colorjitter():
+    """Decathlon flavour (lightning_module.py:689): ColorJitter(brightness=0.2, contrast=0.2).make_params stream."""
+    from torchvision.transforms import v2 as T
+    from medical_image_segmentation_b200 import FusedResizeJitterTransforms
+    cj = T.ColorJitter(brightness=0.2, contrast=0.2)
+    torch.manual_seed(11)
+    ref = [cj.make_params([]) for _ in range(300)]
+    nxt = torch.rand(2)
+    t = FusedResizeJitterTransforms(224, (0.1,), (0.2,), brightness=0.2, contrast=0.2)
+    torch.manual_seed(11)
+    p = t.draw_params(300, 320, 320)
+    assert torch.equal(nxt, torch.rand(2))
+    for i, r in enumerate(ref):
+        assert tuple(int(v) for v in r["fn_idx"]) == tuple(int(v) for v in p["order"][i])
+        assert np.float32(r["brightness_factor"]) == p["brightness"][i]
+        assert np.float32(r["contrast_factor"]) == p["contrast"][i]
+        assert r["saturation_factor"] is None and r["hue_factor"] is None
+    assert np.all(p["h"] == 320) and np.all(p["top"] == 0) and np.all(p["flags"] == 2)
+    # default_transforms: no jitter, no RNG consumption
+    t0 = FusedResizeJitterTransforms(224, (0.1,), (0.2,))
+    torch.manual_seed(3)
+    a = torch.rand(1)
+    torch.manual_seed(3)
+    p0 = t0.draw_params(5, 64, 64)
+    assert torch.equal(a, torch.rand(1)) and np.all(p0["flags"] == 0)
