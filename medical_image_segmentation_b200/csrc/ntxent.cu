@@ -39,7 +39,8 @@ constexpr int kTile = 128;             // rows per CTA tile, columns per S tile
 constexpr int kKBlock = 32;            // fp32 elements per 128-byte swizzle row
 constexpr int kRingBytes = 192 * 1024;  // operand ring (+ resident row tile); see smem plan in the kernel
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 352;           // warps 0, 10: TMA producers; warp 1: MMA issuer; warps 2-5 / 6-9: two epilogue groups
+constexpr int kThreads = 416;           // warps 0, 10, 11, 12: TMA producers; warp 1: MMA issuer; warps 2-5 / 6-9: epilogue groups
+constexpr int kProducers = 4;
 constexpr int kEpiThreads = 128;
 constexpr int kTmemCols = 512;
 constexpr int kDuCol = 256;            // TMEM column where the dU accumulator starts
@@ -206,36 +207,39 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
   tc_fence_after();
   const uint32_t tmem = bars.tmem_ptr;
 
-  if (warp == 0 || warp == 10) {
+  if (warp == 0 || warp >= 10) {
     // ===================================== TMA producers =====================================
-    // One thread sustains only ~1 TMA box per 455 clk (measured, scripts/micro/tma_lat.cu), less than the MMA
-    // consumes, so two producer threads in different warps walk the same stage sequence and issue alternate stages.
+    // One thread sustains only ~1 TMA box per 455 clk (measured, scripts/micro/tma_lat.cu) and a stage is refilled
+    // only after its MMAs retire, so the refill latency (boxes x 455 clk + memory latency) bounds the tile rate.  Four
+    // producer threads in different warps therefore walk the same stage sequence and each issues one box of every
+    // stage; producer 0 also posts the stage's arrive.expect_tx.
     if (lane == 0) {
-      const int parity = warp == 0 ? 0 : 1;
-      int stage = 0, phase = 0, n = 0;
+      const int pidx = warp == 0 ? 0 : warp - 9;               // 0..3
+      int stage = 0, phase = 0;
       auto advance = [&]() {
-        ++n;
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
       };
-      if (res_a && parity == 0) {    // resident row tile, loaded once
-        mbar_arrive_expect_tx(&bars.a_full, (uint32_t)KB * kTile * 128);
-        for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_a + kb * kTile * 128, &map_u, kb * kKBlock, g_row_tile0, &bars.a_full);
+      if (res_a) {    // resident row tile, loaded once
+        if (pidx == 0) mbar_arrive_expect_tx(&bars.a_full, (uint32_t)KB * kTile * 128);
+        for (int kb = pidx; kb < KB; kb += kProducers)
+          tma_load_2d(smem_a + kb * kTile * 128, &map_u, kb * kKBlock, g_row_tile0, &bars.a_full);
       }
       auto push_s = [&](int t) {   // operands of S = U_I . U_J^T
         for (int kb = 0; kb < KB; kb += kps_s) {
-          if ((n & 1) == parity) {
-            mbar_wait(&bars.empty[stage], phase ^ 1);
-            uint8_t* sa = ring + stage * kStageBytes;
-            if (res_a) {             // the whole U_J tile in one stage
-              mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)KB * kTile * 128);
-              for (int k2 = 0; k2 < KB; ++k2)
-                tma_load_2d(sa + k2 * kTile * 128, &map_u, k2 * kKBlock, (t_begin + t) * kTile, &bars.full[stage]);
-            } else {
+          mbar_wait(&bars.empty[stage], phase ^ 1);
+          uint8_t* sa = ring + stage * kStageBytes;
+          if (res_a) {             // the whole U_J tile in one stage, one box per producer
+            if (pidx == 0) mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)KB * kTile * 128);
+            for (int k2 = pidx; k2 < KB; k2 += kProducers)
+              tma_load_2d(sa + k2 * kTile * 128, &map_u, k2 * kKBlock, (t_begin + t) * kTile, &bars.full[stage]);
+          } else {
+            if (pidx == 0) {
               mbar_arrive_expect_tx(&bars.full[stage], 2 * kTile * 128);
               tma_load_2d(sa, &map_u, kb * kKBlock, g_row_tile0, &bars.full[stage]);
+            } else if (pidx == 1) {
               tma_load_2d(sa + kTile * 128, &map_u, kb * kKBlock, (t_begin + t) * kTile, &bars.full[stage]);
             }
           }
@@ -244,13 +248,11 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
       };
       auto push_g = [&](int t) {   // U^T boxes [ds x 32 columns] for dU += W . U_J
         for (int kb = 0; kb < kTile / kKBlock; kb += kps_g) {
-          if ((n & 1) == parity) {
-            mbar_wait(&bars.empty[stage], phase ^ 1);
-            uint8_t* sa = ring + stage * kStageBytes;
-            mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)kps_g * a.ds * 128);
-            for (int k2 = 0; k2 < kps_g; ++k2)
-              tma_load_2d(sa + k2 * a.ds * 128, &map_ut, (t_begin + t) * kTile + (kb + k2) * kKBlock, a.d0, &bars.full[stage]);
-          }
+          mbar_wait(&bars.empty[stage], phase ^ 1);
+          uint8_t* sa = ring + stage * kStageBytes;
+          if (pidx == 0) mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)kps_g * a.ds * 128);
+          for (int k2 = pidx; k2 < kps_g; k2 += kProducers)
+            tma_load_2d(sa + k2 * a.ds * 128, &map_ut, (t_begin + t) * kTile + (kb + k2) * kKBlock, a.d0, &bars.full[stage]);
           advance();
         }
       };
