@@ -51,7 +51,8 @@ struct TileArgs {
   int col_tiles, tiles_per_split;
   float k1;                // log2(e) / T
   int d0, ds;              // backward: columns [d0, d0 + ds) of dU are produced by this launch (ds <= 256)
-  const float* cexp;       // [cols] exp(1/T - lse_j)            (backward)
+  const float* lse;        // [cols] all-gathered log-sum-exp (backward): c_j = exp(1/T - lse_j) is formed on the fly
+  float inv_T;
   float* partial;          // fwd: [nsplit][rows]   bwd: [nsplit][rows][D]
 };
 
@@ -334,7 +335,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
     const int r_in = quad * 32 + lane;               // row inside the tile == TMEM lane
     const int etid = (tid - 64) & 127;
     const uint32_t tlane = (uint32_t)(quad * 32) << 16;
-    const float ci = kBwd ? a.cexp[g_row_tile0 + r_in] : 0.f;
+    const float ci = kBwd ? __expf(a.inv_T - a.lse[g_row_tile0 + r_in]) : 0.f;
     const float k1 = a.k1;
     const int il = row_tile * kTile + r_in;                       // local row index
     const int pos_col = a.row0 + (il + (a.rows >> 1)) % a.rows;   // global column of this row's positive
@@ -344,7 +345,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
       const int col0 = (t_begin + t) * kTile;
       if (kBwd) {
         bar_sync(2 + grp, kEpiThreads);                         // previous tile's readers of cj[buf] are done
-        bars.cj[buf][etid] = a.cexp[col0 + etid];
+        bars.cj[buf][etid] = __expf(a.inv_T - a.lse[col0 + etid]);
         bar_sync(2 + grp, kEpiThreads);
       }
       mbar_wait(&bars.tmem_full[buf], (t >> 1) & 1);
@@ -453,43 +454,45 @@ __global__ void transpose_kernel(const float* __restrict__ u, float* __restrict_
   for (int i = threadIdx.y; i < 32; i += blockDim.y) ut[(size_t)(d0 + i) * cols + c0 + threadIdx.x] = tile[threadIdx.x][i];
 }
 
-__global__ void cexp_kernel(const float* __restrict__ lse, float* __restrict__ cexp, int cols, float inv_T) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < cols) cexp[j] = expf(inv_T - lse[j]);
-}
-
 // lse_i = 1/T + log(sum of split partials); pos_i = <u_i,u_p(i)>/T; per-row loss term lse_i - pos_i.  One warp per row.
 __global__ void fwd_rows_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ u_all, int D,
                                 int row0, int rows, float inv_T, float* __restrict__ lse_rows,
-                                float* __restrict__ row_loss) {
+                                float* __restrict__ row_loss, unsigned int* __restrict__ counter, float* __restrict__ loss) {
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (i >= rows) return;
-  float s = 0.f;
-  for (int k = 0; k < nsplit; ++k) s += partial[(size_t)k * rows + i];
-  const float lse = inv_T + logf(s);
-  const float* ui = u_all + (size_t)(row0 + i) * D;
-  const float* up = u_all + (size_t)(row0 + (i + (rows >> 1)) % rows) * D;
-  float dot = 0.f;
-  for (int d = lane; d < D; d += 32) dot = fmaf(ui[d], up[d], dot);
-  dot = warp_sum(dot);
-  if (lane == 0) {
-    lse_rows[i] = lse;
-    row_loss[i] = lse - dot * inv_T;
+  if (i < rows) {
+    float s = 0.f;
+    for (int k = 0; k < nsplit; ++k) s += partial[(size_t)k * rows + i];
+    const float lse = inv_T + logf(s);
+    const float* ui = u_all + (size_t)(row0 + i) * D;
+    const float* up = u_all + (size_t)(row0 + (i + (rows >> 1)) % rows) * D;
+    float dot = 0.f;
+    for (int d = lane; d < D; d += 32) dot = fmaf(ui[d], up[d], dot);
+    dot = warp_sum(dot);
+    if (lane == 0) {
+      lse_rows[i] = lse;
+      row_loss[i] = lse - dot * inv_T;
+    }
   }
-}
-// loss = mean(row_loss): one block, fixed summation order (deterministic)
-__global__ void mean_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  // loss = mean(row_loss): the last block to finish sums all rows in a fixed order (deterministic, no extra launch)
+  __shared__ bool last;
   __shared__ float red[32];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
   float acc = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += v[i];
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) acc += __ldcg(row_loss + r);
   acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  if (lane == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     float tot = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
-    out[0] = tot / (float)n;
+    loss[0] = tot / (float)rows;
+    *counter = 0u;                                   // ready for the next call on this scratch buffer
   }
 }
 
@@ -638,7 +641,7 @@ extern "C" int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D) {
   if (rows <= 0 || cols <= 0 || D <= 0) return -1;
   const Plan p = make_plan(rows < kTile ? kTile : rows, cols < kTile ? kTile : cols);
   size_t b = 0;
-  b += al256((size_t)cols * 4);                       // cexp
+  b += al256((size_t)cols * 4 + 256);                 // block counter + per-row loss terms
   b += al256((size_t)D * cols * 4);                   // U^T
   b += al256((size_t)p.nsplit * rows * D * 4);        // dU partials (also covers the forward's row-sum partials)
   return (int64_t)b;
@@ -669,7 +672,7 @@ extern "C" int mis_ntxent_fwd(const float* u_all, int cols, int D, int row0, int
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const Plan p = make_plan(rows, cols);
   uint8_t* sc = static_cast<uint8_t*>(scratch);
-  float* partial = reinterpret_cast<float*>(sc + al256((size_t)cols * 4) + al256((size_t)D * cols * 4));
+  float* partial = reinterpret_cast<float*>(sc + al256((size_t)cols * 4 + 256) + al256((size_t)D * cols * 4));
 
   CUtensorMap map_u;
   if (int rc = make_map(&map_u, u_all, (uint64_t)D, (uint64_t)cols, kTile)) return rc;
@@ -677,16 +680,18 @@ extern "C" int mis_ntxent_fwd(const float* u_all, int cols, int D, int row0, int
   a.rows = rows; a.cols = cols; a.D = D; a.row0 = row0;
   a.col_tiles = p.col_tiles; a.tiles_per_split = p.tiles_per_split;
   a.k1 = kLog2e * inv_T;
-  a.cexp = nullptr;
+  a.lse = nullptr;
+  a.inv_T = inv_T;
   a.partial = partial;
   auto* fn = &ntxent_tile_kernel<false>;
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map_u, map_u, a);
   MIS_CUDA_TRY(cudaGetLastError());
-  float* row_loss = reinterpret_cast<float*>(sc);     // reuses the (backward-only) cexp slot
-  fwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(partial, 2 * p.nsplit, u_all, D, row0, rows, inv_T, lse_rows, row_loss);
-  MIS_CUDA_TRY(cudaGetLastError());
-  mean_kernel<<<1, 1024, 0, st>>>(row_loss, rows, loss);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(sc);                 // first 256 B of the scratch
+  float* row_loss = reinterpret_cast<float*>(sc + 256);
+  MIS_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));         // scratch arrives uninitialised
+  fwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(partial, 2 * p.nsplit, u_all, D, row0, rows, inv_T, lse_rows, row_loss,
+                                                  counter, loss);
   MIS_CUDA_TRY(cudaGetLastError());
   return MIS_OK;
 }
@@ -703,12 +708,9 @@ extern "C" int mis_ntxent_bwd(const float* u_all, const float* lse_all, const vo
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const Plan p = make_plan(rows, cols);
   uint8_t* sc = static_cast<uint8_t*>(scratch);
-  float* cexp = reinterpret_cast<float*>(sc);
-  float* ut = reinterpret_cast<float*>(sc + al256((size_t)cols * 4));
-  float* partial = reinterpret_cast<float*>(sc + al256((size_t)cols * 4) + al256((size_t)D * cols * 4));
+  float* ut = reinterpret_cast<float*>(sc + al256((size_t)cols * 4 + 256));
+  float* partial = reinterpret_cast<float*>(sc + al256((size_t)cols * 4 + 256) + al256((size_t)D * cols * 4));
 
-  cexp_kernel<<<(cols + 255) / 256, 256, 0, st>>>(lse_all, cexp, cols, inv_T);
-  MIS_CUDA_TRY(cudaGetLastError());
   transpose_kernel<<<dim3(cols / 32, D / 32), dim3(32, 8), 0, st>>>(u_all, ut, cols, D);
   MIS_CUDA_TRY(cudaGetLastError());
 
@@ -721,7 +723,8 @@ extern "C" int mis_ntxent_bwd(const float* u_all, const float* lse_all, const vo
   a.rows = rows; a.cols = cols; a.D = D; a.row0 = row0;
   a.col_tiles = p.col_tiles; a.tiles_per_split = p.tiles_per_split;
   a.k1 = kLog2e * inv_T;
-  a.cexp = cexp;
+  a.lse = lse_all;
+  a.inv_T = inv_T;
   a.partial = partial;
   a.ds = ds;
   auto* fn = &ntxent_tile_kernel<true>;

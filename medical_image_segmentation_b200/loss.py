@@ -37,6 +37,21 @@ def _stream(t: torch.Tensor):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+class _on_device:
+    """`with torch.cuda.device(d)` costs ~10 us per entry; only switch when d is not already current."""
+
+    def __init__(self, device):
+        self.ctx = None if device.index is None or device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
 class CudaKernels:
     """The three device steps of NT-Xent, bound to the C ABI (include/mis_b200.h)."""
 
@@ -50,7 +65,7 @@ class CudaKernels:
         rows, D = z.shape
         u = torch.empty((rows, D), dtype=torch.float32, device=z.device)
         rinv = torch.empty((rows,), dtype=torch.float32, device=z.device)
-        with torch.cuda.device(z.device):
+        with _on_device(z.device):
             rc = _lib.lib.mis_ntxent_prep(z.data_ptr(), _dt(z), rows, D, u.data_ptr(), rinv.data_ptr(), _stream(z))
         _lib.check(rc, "mis_ntxent_prep")
         CudaKernels.launches += 1
@@ -66,11 +81,11 @@ class CudaKernels:
         cols, D = u_all.shape
         lse = torch.empty((rows,), dtype=torch.float32, device=u_all.device)
         loss = torch.empty((1,), dtype=torch.float32, device=u_all.device)
-        with torch.cuda.device(u_all.device):
+        with _on_device(u_all.device):
             rc = _lib.lib.mis_ntxent_fwd(u_all.data_ptr(), cols, D, row0, rows, inv_T, lse.data_ptr(), loss.data_ptr(),
                                          scratch.data_ptr(), scratch.numel(), _stream(u_all))
         _lib.check(rc, "mis_ntxent_fwd")
-        CudaKernels.launches += 3
+        CudaKernels.launches += 2
         return lse, loss
 
     @staticmethod
@@ -79,12 +94,12 @@ class CudaKernels:
         rows = z.shape[0]
         dz = torch.empty_like(z)
         g = grad_out.to(torch.float32).reshape(1).contiguous()
-        with torch.cuda.device(z.device):
+        with _on_device(z.device):
             rc = _lib.lib.mis_ntxent_bwd(u_all.data_ptr(), lse_all.data_ptr(), z.data_ptr(), _dt(z), rinv.data_ptr(),
                                          cols, D, row0, rows, inv_T, 1.0, g.data_ptr(), dz.data_ptr(),
                                          scratch.data_ptr(), scratch.numel(), _stream(z))
         _lib.check(rc, "mis_ntxent_bwd")
-        CudaKernels.launches += 4
+        CudaKernels.launches += 3
         return dz
 
 
@@ -153,7 +168,7 @@ class _BYOLCosine(torch.autograd.Function):
         loss = torch.empty((1,), dtype=torch.float32, device=p.device)
         dp = torch.empty_like(p)
         scratch = torch.empty((rows,), dtype=torch.float32, device=p.device)
-        with torch.cuda.device(p.device):
+        with _on_device(p.device):
             rc = _lib.lib.mis_byol_loss_fwd_bwd(p.data_ptr(), t.data_ptr(), rows, D, loss.data_ptr(), dp.data_ptr(),
                                                 scratch.data_ptr(), _stream(p))
         _lib.check(rc, "mis_byol_loss_fwd_bwd")
