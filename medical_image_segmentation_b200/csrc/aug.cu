@@ -32,6 +32,8 @@
 #include <cstdlib>
 #include <mutex>
 
+#include "aug_math.cuh"
+#include "aug_tile.cuh"
 #include "common.cuh"
 
 namespace mis {
@@ -83,35 +85,6 @@ struct SmemHeader {
   int m_max;                  // most output rows any single source row of this band feeds
 };
 
-// ---- packed fp32 pairs (Blackwell FFMA2 / FADD2) ---------------------------------------------
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-// two packed uint16 -> two exact floats without the (slow, XU-pipe) I2F:
-// 0x4B000000 | v is the float 2^23 + v; subtracting 2^23 is exact.
-__device__ __forceinline__ uint64_t u16x2_to_f32x2(uint32_t p) {
-  const uint32_t lo = (p & 0xffffu) | 0x4B000000u;
-  const uint32_t hi = __byte_perm(p, 0x4B000000u, 0x7632);
-  return fadd2(pack2(__uint_as_float(lo), __uint_as_float(hi)), pack2(-8388608.f, -8388608.f));
-}
-
-
 // ---- TMA-staged ring --------------------------------------------------------------------------
 // A ring slot holds kChunkRows source rows of the crop.  The crop's columns are fetched as 2-D TMA boxes of
 // up to 256 columns (box b covers crop columns [256b, 256b + wb)), wb rounded up to 64 so that one of four
@@ -144,16 +117,8 @@ __device__ __forceinline__ void tma_box_2d(void* dst, const CUtensorMap* map, in
       : "memory");
 }
 
-// Tap table of one output index.  n = input size, scale = n/m in fp32.
+// Tap table of one output index (window arithmetic in aug_math.cuh).
 // Writes kstride weights (zero padded) with element stride `wstep` (2 = duplicated pairs).
-__device__ __forceinline__ void aa_window(int i, int n, float scale, float support, int& lo, int& hi, float& center) {
-  center = (float)((double)scale * ((double)i + 0.5));
-  lo = (int)((double)center - (double)support + 0.5);
-  lo = lo < 0 ? 0 : lo;
-  hi = (int)((double)center + (double)support + 0.5);
-  hi = hi > n ? n : hi;
-}
-
 __device__ __forceinline__ void aa_taps(int i, int n, float scale, float support, float invscale, int kstride,
                                         int wstep, int& lo_out, int& size_out, float* w) {
   float center;
@@ -635,50 +600,6 @@ __device__ __forceinline__ void h_pass16_dyn(const Ctx& c, float* __restrict__ o
   }
 }
 
-// ---- write RUN consecutive output pixels of one row (normalised values in v[0..RUN)), mirrored when flipped -------
-template <int RUN>
-__device__ __forceinline__ void store_run(const float* __restrict__ v, void* out_base, size_t row_off, int xs, int s,
-                                          bool flip, bool f32) {
-  const bool full = (xs + RUN <= s) && ((s & 7) == 0);
-  if (f32) {
-    float* out = reinterpret_cast<float*>(out_base) + row_off;
-    if (full) {
-      if (!flip) {
-        float4* dst = reinterpret_cast<float4*>(out + xs);
-#pragma unroll
-        for (int i = 0; i < RUN / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      } else {
-        float4* dst = reinterpret_cast<float4*>(out + (s - xs - RUN));
-#pragma unroll
-        for (int i = 0; i < RUN / 4; ++i)
-          dst[i] = make_float4(v[RUN - 1 - 4 * i], v[RUN - 2 - 4 * i], v[RUN - 3 - 4 * i], v[RUN - 4 - 4 * i]);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < RUN; ++i)
-        if (xs + i < s) out[flip ? (s - 1 - xs - i) : (xs + i)] = v[i];
-    }
-  } else {
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_base) + row_off;
-    if (full) {
-      uint32_t pk[RUN / 2];
-#pragma unroll
-      for (int i = 0; i < RUN / 2; ++i) {
-        __nv_bfloat162 h = flip ? __floats2bfloat162_rn(v[RUN - 1 - 2 * i], v[RUN - 2 - 2 * i])
-                                : __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        pk[i] = *reinterpret_cast<uint32_t*>(&h);
-      }
-      uint4* dst = reinterpret_cast<uint4*>(out + (flip ? (s - xs - RUN) : xs));
-#pragma unroll
-      for (int i = 0; i < RUN / 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < RUN; ++i)
-        if (xs + i < s) out[flip ? (s - 1 - xs - i) : (xs + i)] = __float2bfloat16_rn(v[i]);
-    }
-  }
-}
-
 template <bool kBulk, bool kWindow>
 __global__ void __launch_bounds__(kThreads, kBulk ? 2 : 3)
 aug_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CUtensorMap map128,
@@ -1139,6 +1060,30 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
   for (int c = 0; c < C; ++c)
     MIS_REQUIRE(std[c] != 0.f, MIS_ERR_INVALID_ARG, "mis_aug_two_view: std[%d] == 0", c);
   if (n_views == 0) return MIS_OK;
+
+  // staging 0 (default): warp-tile kernel (aug_tile.cu) wherever it applies; 1: TMA band kernel; 2: cp.async band kernel
+  if (use_tma == 0 && mis::augt::tile_supported(C, H, W, img_stride, s)) {
+    mis::augt::TileArgs t = {};
+    t.src = src;
+    t.img_stride = img_stride;
+    t.C = C;
+    t.H = H;
+    t.W = W;
+    t.params = params;
+    t.win_lo = win_lo;
+    t.win_scale = 1.0f / (win_hi - win_lo);
+    for (int c = 0; c < C; ++c) {
+      t.mean[c] = mean[c];
+      t.inv_std[c] = 1.0f / std[c];
+    }
+    t.out = out;
+    t.s = s;
+    t.out_f32 = out_dtype == MIS_DTYPE_F32 ? 1 : 0;
+    t.nbands = (s + kBandRows - 1) / kBandRows;
+    t.debug_no_cluster = std::getenv("MIS_DEBUG_NO_CLUSTER") != nullptr;
+    return mis::augt::launch_tile(t, n_views, !(win_lo == 0.f && win_hi == 65535.f), reinterpret_cast<cudaStream_t>(stream));
+  }
+  use_tma = (use_tma == 1) ? 1 : 0;
 
   Args a = {};
   a.src = src;

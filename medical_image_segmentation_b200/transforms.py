@@ -12,9 +12,9 @@ per-sample CPU callable to a per-batch GPU kernel:
   train/model/byol_pytorch.py:207 is free.
 * random parameters are drawn from torch's global CPU generator in exactly the reference's order
   (params.py), so ``torch.manual_seed(k)`` gives the same crops / flips / jitter as the reference.
-* ``use_tma`` selects how crop rows are staged into shared memory: ``False`` (default, fastest measured:
-  per-thread cp.async rings, 16-row sub-bands, 3 CTAs/SM) or ``True`` (2-D TMA tensor-map boxes fed by a
-  producer warp).  Both are parity-tested against the same oracle.
+* ``use_tma`` selects the K1 variant: ``False``/``0`` (default: the warp-tile kernel, csrc/aug_tile.cu, wherever it
+  applies), ``True``/``1`` (band kernel, 2-D TMA tensor-map boxes fed by a producer warp) or ``2`` (band kernel,
+  per-thread cp.async rings, 16-row sub-bands).  All three are parity-tested against the same oracle.
 * GaussianBlur and Solarize (lightning_module.py:53-54) are not implemented on the device yet:
   ``blur_prob`` / ``solarize_prob`` must be 0 (their RNG draws are still consumed).  The CIFAR data
   modules of the reference run with exactly this setting (lightning_module.py:482-488).
@@ -46,7 +46,7 @@ def _as_float_seq(v, n: int, name: str) -> list[float]:
 class FusedTwoViewTransforms:
     def __init__(self, crop_size: int, mean: Sequence[float], std: Sequence[float],
                  blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0), *, out_dtype=torch.bfloat16,
-                 window: tuple[float, float] | None = None, use_tma: bool = False):
+                 window: tuple[float, float] | None = None, use_tma: bool | int = False):
         assert len(blur_prob) == 2 and len(solarize_prob) == 2, "atm only 2 views are supported"
         if any(p != 0 for p in blur_prob) or any(p != 0 for p in solarize_prob):
             raise NotImplementedError(
@@ -65,7 +65,9 @@ class FusedTwoViewTransforms:
             raise ValueError("out_dtype must be torch.bfloat16 or torch.float32")
         self.out_dtype = out_dtype
         self.window = (0.0, _U16_MAX) if window is None else (float(window[0]), float(window[1]))
-        self.use_tma = bool(use_tma)
+        self.use_tma = int(use_tma)
+        if self.use_tma not in (0, 1, 2):
+            raise ValueError("use_tma must be 0 (tile kernel), 1 (TMA band kernel) or 2 (cp.async band kernel)")
         self.views_buffer: torch.Tensor | None = None
         self.last_params: np.ndarray | None = None
         self.launches = 0
@@ -115,7 +117,7 @@ class FusedTwoViewTransforms:
                 x.data_ptr(), B, Cc, H, W, Cc * H * W, dev.data_ptr(), n_views,
                 self.window[0], self.window[1], C.cast(mean_c, C.c_void_p), C.cast(std_c, C.c_void_p),
                 out.data_ptr(), s, MIS_DTYPE_F32 if self.out_dtype == torch.float32 else MIS_DTYPE_BF16,
-                1 if self.use_tma else 0, C.c_void_p(stream))
+                self.use_tma, C.c_void_p(stream))
         _lib.check(rc, "mis_aug_two_view")
         self.launches += 1
         return out
@@ -176,7 +178,7 @@ class FusedResizeJitterTransforms(FusedTwoViewTransforms):
     """
 
     def __init__(self, size, mean, std, brightness=None, contrast=None, *, out_dtype=torch.bfloat16, window=None,
-                 use_tma: bool = False):
+                 use_tma: bool | int = False):
         super().__init__(size, mean, std, (0.0, 0.0), (0.0, 0.0), out_dtype=out_dtype, window=window, use_tma=use_tma)
         self.brightness = brightness
         self.contrast = contrast

@@ -6,7 +6,7 @@ from oracle import aug_oracle as A
 from tests import synth
 from medical_image_segmentation_b200.transforms import FusedTwoViewTransforms, algorithmic_bytes
 
-use_tma = bool(int(sys.argv[1]))
+use_tma = int(sys.argv[1])
 MEAN, STD = 0.227358, 0.237160
 for (H, W, crop, B) in ((96, 128, 32, 4), (512, 512, 224, 4), (512, 512, 96, 4), (512, 512, 256, 2), (256, 768, 112, 2)):
     imgs = synth.batch_512(B, seed=77, H=H, W=W)

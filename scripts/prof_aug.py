@@ -6,7 +6,7 @@ from medical_image_segmentation_b200.transforms import FusedTwoViewTransforms
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 crop = int(sys.argv[2]) if len(sys.argv) > 2 else 224
-use_tma = bool(int(sys.argv[3])) if len(sys.argv) > 3 else False
+use_tma = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 g = torch.Generator(device="cuda").manual_seed(1234)
 x = torch.randint(0, 65536, (B, 1, 512, 512), dtype=torch.int32, device="cuda", generator=g).to(torch.uint16)
 t = FusedTwoViewTransforms(crop, (0.227358,), (0.237160,), use_tma=use_tma)

@@ -36,7 +36,7 @@ def _check(got, ref, what):
     return float(err.max())
 
 
-@pytest.mark.parametrize("use_tma", [True, False])
+@pytest.mark.parametrize("use_tma", [0, 1, 2])      # tile kernel, TMA band kernel, cp.async band kernel
 @pytest.mark.parametrize("crop", [32, 48])
 def test_matches_reference_golden_small(crop, use_tma):
     g = np.load(os.path.join(GOLD, "aug_small.npz"))
@@ -83,13 +83,16 @@ def test_matches_reference_golden_512(crop):
 
 
 @pytest.mark.parametrize("shape,crop", [((512, 512), 224), ((512, 512), 96), ((512, 512), 256), ((256, 768), 112),
-                                        ((448, 448), 56), ((130, 70), 40), ((64, 64), 8)])
-def test_batch_matches_oracle(shape, crop):
-    """A whole batch in one launch vs the numpy restatement, every pixel."""
+                                        ((448, 448), 56), ((130, 70), 40), ((64, 64), 8), ((512, 512), 100),
+                                        ((200, 360), 72), ((96, 96), 224)])
+@pytest.mark.parametrize("use_tma", [0, 2])
+def test_batch_matches_oracle(shape, crop, use_tma):
+    """A whole batch in one launch vs the numpy restatement, every pixel (0: tile kernel where it applies -- the
+    8x downscaling shapes fall back to the band kernel; 2: cp.async band kernel)."""
     H, W = shape
     B = 6
     imgs = synth.batch_512(B, seed=77, H=H, W=W)
-    t = _mk(crop, out_dtype=torch.float32)
+    t = _mk(crop, out_dtype=torch.float32, use_tma=use_tma)
     torch.manual_seed(31)
     v1, v2 = t(torch.from_numpy(imgs).cuda())
     out = t.views_buffer.cpu().numpy()
@@ -102,24 +105,25 @@ def test_batch_matches_oracle(shape, crop):
 
 
 @pytest.mark.parametrize("shape,crop", [((512, 512), 224), ((512, 512), 96), ((300, 500), 64)])
-def test_cp_async_path_matches_tma_path_and_oracle(shape, crop):
-    """use_tma=False (per-thread cp.async ring, two 16-row streams) against use_tma=True and the oracle."""
+def test_kernel_variants_agree_and_match_oracle(shape, crop):
+    """The three K1 variants (0 tile kernel, 1 TMA band kernel, 2 cp.async band kernel) against each other and the oracle."""
     H, W = shape
     imgs = synth.batch_512(4, seed=13, H=H, W=W)
     x = torch.from_numpy(imgs).cuda()
-    ta = _mk(crop, out_dtype=torch.float32, use_tma=True)
-    tb = _mk(crop, out_dtype=torch.float32, use_tma=False)
-    torch.manual_seed(77)
-    ta(x)
-    torch.manual_seed(77)
-    tb(x)
-    a, b = ta.views_buffer.cpu().numpy(), tb.views_buffer.cpu().numpy()
-    assert np.abs(a - b).max() <= 2e-6
+    outs = []
+    for variant in (1, 2, 0):
+        tb = _mk(crop, out_dtype=torch.float32, use_tma=variant)
+        torch.manual_seed(77)
+        tb(x)
+        outs.append(tb.views_buffer.cpu().numpy())
+    a, c, b = outs
+    assert np.abs(a - c).max() <= 2e-6
+    assert np.abs(a - b).max() <= 4e-6
     p = tb.last_params
     for i in range(4):
         for v in range(2):
             ref = A.apply_view(imgs[i], _oracle_params(p[2 * i + v]), crop, MEAN, STD)
-            _check(b[v * 4 + i, 0], ref, f"cp path {shape} img {i} view {v}")
+            _check(b[v * 4 + i, 0], ref, f"tile kernel {shape} img {i} view {v}")
 
 
 def test_bf16_output_is_rounded_fp32_output():
