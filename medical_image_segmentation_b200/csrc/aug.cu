@@ -1080,7 +1080,7 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
     t.s = s;
     t.out_f32 = out_dtype == MIS_DTYPE_F32 ? 1 : 0;
     t.nbands = (s + kBandRows - 1) / kBandRows;
-    t.debug_no_cluster = std::getenv("MIS_DEBUG_NO_CLUSTER") != nullptr;
+    t.debug_no_cluster = std::getenv("MIS_DEBUG_FLAGS") ? std::atoi(std::getenv("MIS_DEBUG_FLAGS")) : 0;
     return mis::augt::launch_tile(t, n_views, !(win_lo == 0.f && win_hi == 65535.f), reinterpret_cast<cudaStream_t>(stream));
   }
   use_tma = (use_tma == 1) ? 1 : 0;

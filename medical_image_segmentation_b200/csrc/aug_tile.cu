@@ -120,7 +120,10 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
     for (int i = 0; i < 2 * NS; ++i) hw[i] = pack2(w[2 * i], w[2 * i + 1]);
   }
   // the row buffers must hold finite values where zero-weight taps may read
-  for (int i = lane; i < 2 * kRowBuf; i += 32) (&ws.row[0][0])[i] = 0.f;
+  if (lane < 24) {
+    const int c = (t.span & ~1) + lane;             // columns at and behind the staged span (active lanes write < span + 1)
+    if (c < kRowBuf) ws.row[0][c] = ws.row[1][c] = 0.f;
+  }
   __syncwarp();
 
   bool act[NL];
@@ -136,8 +139,8 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
   uint64_t A[NL], B[NL], Cc[NL];    // output rows ycur, ycur+1, ycur+2 of this lane's column pair(s)
 #pragma unroll
   for (int i = 0; i < NL; ++i) A[i] = B[i] = Cc[i] = 0ull;
-  int ycur = 0;
   float sum = 0.f;
+  const float vscale_out = t.has_pre ? t.post * t.pre_b : t.post;
   // running shared-memory cursors (32-bit shared addresses): the intermediate row alternates between two buffers,
   // the output tile advances one row per completed output row
   // (idle lanes park their finite garbage in the zero-weight slack columns behind the staged span)
@@ -167,13 +170,13 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
     }
     float lo, hi;
     unpack2(acc, lo, hi);
-    float val = (lo + hi) * t.post;
-    if (t.has_pre) val = __saturatef(val * t.pre_b);
+    // 1/65535 (and a brightness factor that precedes contrast) in one saturating multiply; without brightness the
+    // clamp only trims the one-ulp overshoot a normalised filter can produce
+    const float val = __saturatef((lo + hi) * vscale_out);
     sum += val;                                   // lanes beyond the view's last column carry zero weights
     sts32(op, val);
     op += kOPitch * 4;
     sel ^= (uint32_t)(kRowBuf * 4);
-    ++ycur;
   };
 
   if (t.use_is) {
@@ -230,8 +233,9 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
       }
       sp += G;
     }
+    const uint32_t op_end = smem_u32(ws.o) + 4u * lane + (uint32_t)t.nrows * (kOPitch * 4);
 #pragma unroll 1
-    while (ycur < t.nrows) {
+    while (op != op_end) {
       hrow();
 #pragma unroll
       for (int i = 0; i < NL; ++i) {
@@ -277,7 +281,7 @@ __global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs
   const int chan = plane - view * a.C;
   const int s = a.s;
 
-  const bool nocl = a.debug_no_cluster != 0;
+  const bool nocl = (a.debug_no_cluster & 1) != 0;
   if (!nocl) cluster_arrive_relaxed();   // phase 1: "every CTA of the cluster is running" (waited before DSMEM use)
 
   const MisViewParams P = a.params[view];
@@ -291,7 +295,7 @@ __global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs
   const float hsup = hscale >= 1.f ? hscale : 1.f, hinv = hscale >= 1.f ? 1.f / hscale : 1.f;
 
   // ---- pull the band's crop rows into L2 right away (every thread derives the row range itself) -------------
-  {
+  if (!(a.debug_no_cluster & 2)) {
     int lo0, hi0, lo1, hi1;
     float ctr;
     aa_window(y0, P.h, vscale, vsup, lo0, hi0, ctr);
@@ -498,7 +502,7 @@ int launch_tile(const TileArgs& a, int n_views, bool window, cudaStream_t stream
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = a.debug_no_cluster ? 1u : (unsigned)a.nbands;
+  attr[0].val.clusterDim.x = (a.debug_no_cluster & 1) ? 1u : (unsigned)a.nbands;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
