@@ -1,26 +1,29 @@
 // K1 (tile variant) -- fused two-view augmentation for 16-bit slices, warp-autonomous tiles (sm_100a).
 //
 // One thread-block CLUSTER per output view plane, one CTA per band of 32 output rows, and inside the CTA one WARP per
-// 32 x 32 output tile.  After a short CTA prologue (vertical tap tables / schedule, one barrier) a warp never
+// 32-row x 64-column output tile.  After a short CTA prologue (vertical tap tables / schedule) a warp never
 // synchronises with another warp until the contrast mean:
 //
-//   V pass   : lane = two adjacent source columns (x NL when the crop is wide), read straight from global memory with
-//              4-byte loads (a warp reads 128 contiguous bytes per source row), G rows in flight per lane in registers
-//              after an L2 prefetch of the band; input-stationary: every source pixel is loaded and converted once
-//              (exact magic-number u16 -> f32) and scattered with packed FFMA2 into the <= 3 output rows whose window
-//              contains it; the three accumulators rotate when an output row completes;
+//   V pass   : lane = NL pairs of adjacent source columns (columns 2*lane + 64*i), read straight from global memory
+//              with 4-byte loads (a warp reads 128 contiguous bytes per source row and pair), G rows in flight per lane
+//              in register slots that are refilled as soon as they are consumed, after an L2 prefetch of the band;
+//              input-stationary: every source pixel is loaded and converted once (exact magic-number u16 -> f32) and
+//              scattered with packed FFMA2 into the <= 3 output rows whose window contains it; the accumulators rotate
+//              through the FMA operands when an output row completes (a precomputed bit mask says when);
 //   H pass   : a completed intermediate row (<= 192 floats) goes to a warp-private double-buffered row in shared
-//              memory; lane = one output column, its tap weights live in REGISTERS for the whole tile, laid out
-//              against the 16-byte-aligned window start so a row costs NS 16-byte shared loads + 2*NS FFMA2;
-//              the result is parked in a warp-private 32 x 32 fp32 tile (row pitch 36 floats);
-//   colour   : brightness before contrast is applied on the fly; the contrast mean over the whole view is reduced
-//              lane -> warp -> CTA -> cluster through distributed shared memory, so each view is written exactly once;
+//              memory; lane = NO output columns (x0 + lane, x0 + 32 + lane), their tap weights live in REGISTERS for
+//              the whole tile, laid out against the 16-byte-aligned window start so an output costs NS 16-byte shared
+//              loads + 2*NS FFMA2; results are parked in a warp-private 32 x 64 fp32 tile (row pitch 68 floats);
+//   colour   : 1/65535 and a brightness that precedes contrast are one saturating multiply on the fly; the contrast
+//              mean over the whole view is reduced lane -> warp -> CTA -> cluster through distributed shared memory,
+//              so each view is written exactly once;
 //   store    : the tile is re-read 8 pixels per lane (conflict-free), contrast / brightness / normalise / flip,
 //              16-byte stores.
 //
-// Classes (warp-uniform, chosen from the crop's horizontal scale): (NL, NS) = (1,2) up to ~1.85x, (2,3) up to 3x,
-// (3,4) up to 5.5x downscaling.  Vertical upscaling (and any window that would feed more than three output rows)
-// uses an output-stationary V pass over the same H pass.
+// Classes (warp-uniform, from the strip's source span): (NL, NS, NO) = (2,2,2) up to ~1.85x and (3,3,2) up to ~2.8x
+// downscaling for 64-column strips; (1,2,1), (2,3,1), (3,4,1) up to 5.5x for 32-column strips (the last strip of a
+// view, or both halves of a 64-column strip whose span is too wide).  Vertical upscaling (and any window that would
+// feed more than three output rows) uses an output-stationary V pass over the same H pass.
 //
 // Arithmetic restated from torchvision 0.26 / ATen (see oracle/aug_oracle.py):
 //   taps   : _upsample_bilinear2d_aa (triangle filter, support = max(scale,1), weights normalised)
@@ -38,14 +41,15 @@ namespace augt {
 using namespace mis::aug;
 
 constexpr int kBand = 32;          // output rows per CTA
+constexpr int kStrip = 32;         // output columns per warp (64: two outputs per lane, measured slower: 16 warps/SM)
 constexpr int kSchedCap = 200;     // source rows of one band (31*5.5 + window + group padding); <= 256 mask bits
 constexpr int kVK = 16;            // widest vertical window kept in the weight table (2*ceil(5.5)+1 = 13)
 constexpr int kRowBuf = 208;       // floats per intermediate-row buffer: 3*64 columns + slack for the aligned H reads
-constexpr int kOPitch = 36;        // output-tile row pitch in floats: 16-byte aligned rows, conflict-free 8-pixel reads
-constexpr int kMaxWarps = 8;       // s <= 256
+constexpr int kOPitch = kStrip + 4; // output-tile row pitch in floats: 16-byte aligned rows, conflict-free 8-pixel reads
+constexpr int kMaxWarps = 256 / kStrip;   // s <= 256
 
 // Input-stationary schedule entry of one source row: it feeds output rows first .. first+2 of the band with the
-// (duplicated, FFMA2-ready) weights w[0..2]; rows before `first` are complete when it is reached.
+// (duplicated, FFMA2-ready) weights w[0..2].
 struct __align__(16) Sched {
   float w[3][2];
   int first;
@@ -59,8 +63,9 @@ struct Smem {
   float part[8];            // per-CTA partial sums of the contrast mean (written by the cluster peers)
   float red[kMaxWarps];
   uint32_t fmask[8];        // bit rr: source row rr completes an output row (the one before its first open row)
-  int m_max;                // most output rows any single source row of this band feeds
-  int pad[3];
+  int m_max;                // most output rows any single source row of this band feeds (4 = schedule unusable)
+  int kv_max;               // widest vertical window of the band
+  int pad[2];
 };
 struct WarpSmem {
   float row[2][kRowBuf];
@@ -68,21 +73,24 @@ struct WarpSmem {
 };
 static_assert(sizeof(Smem) % 16 == 0 && sizeof(WarpSmem) % 16 == 0, "16-byte aligned shared-memory blocks");
 
+// what a warp needs to know about its strip of NO x 32 output columns
 struct Tile {
   float win_lo, win_scale;
   Smem* sh;
   WarpSmem* ws;
-  const uint32_t* g0;      // this lane's first column pair of source row r_lo (crop coordinates)
-  int wq;                  // source row pitch in 4-byte words
-  int lane;
-  int nrows, nsrc, r_lo;
-  int span;                // source columns this warp stages (from the even-aligned column `ca`)
-  int xa;                  // float index of this lane's 16-byte-aligned window start inside the row buffer
-  int off, hlo, hsize;     // window start relative to xa, first source column, taps
-  float hctr, hinv;
-  bool valid, use_is;
-  float post, pre_b;
-  bool has_pre;
+  const uint16_t* crop;    // crop (0, 0) of this plane in global memory
+  int W;                   // source row pitch in elements
+  int ca;                  // first staged source column (crop coordinates, 4-byte aligned address)
+  int lane, nthreads;
+  int nrows;
+  int span;                // source columns this warp stages, from `ca`
+  int ocol;                // first column of this strip inside the warp's output tile (0 or 32)
+  int hlo[2], hsize[2];    // per output: first source column, taps
+  float hctr[2];
+  float hinv;
+  float out_scale;         // 1/65535, times the brightness factor when brightness precedes contrast
+  bool down;               // vertical downscaling and the schedule fits
+  bool sync_sched;         // this call waits for the schedule barrier
 };
 
 template <bool kWindow>
@@ -96,63 +104,98 @@ __device__ __forceinline__ uint64_t conv_px(uint32_t p, uint64_t wsc, uint64_t w
   }
   return f;
 }
+__device__ __forceinline__ uint64_t ptr_add(uint64_t p, uint32_t bytes) {     // one IMAD.WIDE instead of an add pair
+  uint64_t r;
+  asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(bytes), "l"(p));
+  return r;
+}
 
-// The whole tile of one warp: returns this lane's share of the tile's pixel sum (for the contrast mean).
-template <int NL, int NS, bool kWindow>
-__device__ __forceinline__ float run_tile(const Tile& t) {
+// One strip of one warp: NO x 32 output columns, all rows of the band.  Returns this lane's share of the pixel sum.
+template <int NL, int NS, int NO, bool kWindow>
+__device__ __forceinline__ float run_tile(const Tile& t, const uint32_t (&p0)[8], bool have_p0) {
   Smem& sh = *t.sh;
   WarpSmem& ws = *t.ws;
   const int lane = t.lane;
 
   // ---- this lane's horizontal taps, in registers, aligned to the 16-byte window start ------------------
-  uint64_t hw[2 * NS];
-  {
+  uint64_t hw[NO][2 * NS];
+  uint32_t rbase[NO];
+#pragma unroll
+  for (int o = 0; o < NO; ++o) {
+    const int off = (t.hlo[o] - t.ca) & 3;
+    const int xa = t.hsize[o] > 0 ? ((t.hlo[o] - t.ca) & ~3) : 0;
     float tot = 0.f;
-    for (int j = 0; j < t.hsize; ++j) tot += aa_tri(j + t.hlo, t.hctr, t.hinv);
+    for (int j = 0; j < t.hsize[o]; ++j) tot += aa_tri(j + t.hlo[o], t.hctr[o], t.hinv);
     float w[4 * NS];
 #pragma unroll
     for (int jj = 0; jj < 4 * NS; ++jj) {
-      const int j = jj - t.off;
-      const float wj = aa_tri(j + t.hlo, t.hctr, t.hinv);
-      w[jj] = (j >= 0 && j < t.hsize) ? (tot != 0.f ? wj / tot : wj) : 0.f;
+      const int j = jj - off;
+      const float wj = aa_tri(j + t.hlo[o], t.hctr[o], t.hinv);
+      w[jj] = (j >= 0 && j < t.hsize[o]) ? (tot != 0.f ? wj / tot : wj) : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 2 * NS; ++i) hw[i] = pack2(w[2 * i], w[2 * i + 1]);
+    for (int i = 0; i < 2 * NS; ++i) hw[o][i] = pack2(w[2 * i], w[2 * i + 1]);
+    rbase[o] = opaque(smem_u32(&ws.row[0][0]) + 4u * xa);          // aligned window start in buffer 0
   }
-  // the row buffers must hold finite values where zero-weight taps may read
+  // zero-weight taps may read up to 15 columns behind the staged span: those must hold finite values
   if (lane < 24) {
-    const int c = (t.span & ~1) + lane;             // columns at and behind the staged span (active lanes write < span + 1)
+    const int c = (t.span & ~1) + lane;
     if (c < kRowBuf) ws.row[0][c] = ws.row[1][c] = 0.f;
   }
   __syncwarp();
 
   bool act[NL];
-  int lofs[NL];
+  uint32_t wb[NL];
+  uint64_t gl[NL];
+  const int64_t rowe = t.W;
+  // (idle lanes read a valid address and park their finite garbage in the zero-weight slack behind the span)
 #pragma unroll
   for (int i = 0; i < NL; ++i) {
     act[i] = (2 * lane + 64 * i) < t.span;
-    lofs[i] = act[i] ? lane + 32 * i : 0;      // idle lanes read a valid address and never store
+    wb[i] = opaque(smem_u32(&ws.row[0][0]) + (act[i] ? 8u * lane + 256u * i : 4u * (kRowBuf - 8)));
   }
   const uint64_t wsc = pack2(t.win_scale, t.win_scale);
   const uint64_t wof = pack2(-t.win_lo * t.win_scale, -t.win_lo * t.win_scale);
+  const uint32_t rowb = 2u * (uint32_t)t.W;                          // source row pitch in bytes
 
-  uint64_t A[NL], B[NL], Cc[NL];    // output rows ycur, ycur+1, ycur+2 of this lane's column pair(s)
+  const int r_lo = sh.vinfo[0].x;
+  const int nsrc = sh.vinfo[t.nrows - 1].x + sh.vinfo[t.nrows - 1].y - r_lo;
+#pragma unroll
+  for (int i = 0; i < NL; ++i)
+    gl[i] = reinterpret_cast<uint64_t>(t.crop + (int64_t)r_lo * rowe + t.ca + (act[i] ? 2 * lane + 64 * i : 0));
+
+  // G register slots per lane hold the next G source rows of the input-stationary stream; issued before the
+  // schedule barrier so their latency overlaps it
+  constexpr int G = (NL == 1 || (NL == 2 && NO == 2)) ? 8 : 4;
+  uint32_t p[G][NL];
+  uint64_t gq[NL];                                  // next row to fetch, this lane's columns
+  if (t.down) {
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      if (i == 0 && have_p0) {                        // the first pair's rows were requested at kernel entry
+#pragma unroll
+        for (int k = 0; k < G; ++k) p[k][0] = p0[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < G; ++k) p[k][i] = ldg_nc_u32(gl[i] + (uint64_t)((uint32_t)min(k, nsrc - 1) * rowb));
+      }
+      gq[i] = gl[i] + (uint64_t)((uint32_t)G * rowb);
+    }
+  }
+  if (t.sync_sched) bar_sync(1, t.nthreads);        // the schedule (built by the CTA's first threads) is complete
+  const bool use_is = t.down && sh.m_max <= 3;
+
+  uint64_t A[NL], B[NL], Cc[NL];    // the three open output rows of this lane's column pair(s)
 #pragma unroll
   for (int i = 0; i < NL; ++i) A[i] = B[i] = Cc[i] = 0ull;
   float sum = 0.f;
-  const float vscale_out = t.has_pre ? t.post * t.pre_b : t.post;
   // running shared-memory cursors (32-bit shared addresses): the intermediate row alternates between two buffers,
   // the output tile advances one row per completed output row
-  // (idle lanes park their finite garbage in the zero-weight slack columns behind the staged span)
-  uint32_t wb[NL];
-#pragma unroll
-  for (int i = 0; i < NL; ++i)
-    wb[i] = opaque(smem_u32(&ws.row[0][0]) + (act[i] ? 8u * lane + 256u * i : 4u * (kRowBuf - 8)));
-  const uint32_t rbase = opaque(smem_u32(&ws.row[0][0]) + 4u * t.xa);  // aligned window start
   uint32_t sel = 0;                                                    // 0 / kRowBuf * 4: buffer in use
-  uint32_t op = opaque(smem_u32(ws.o) + 4u * lane);
+  const uint32_t op0 = smem_u32(ws.o) + 4u * (t.ocol + lane);
+  uint32_t op = opaque(op0);
 
-  // output row ycur is complete in A: H pass over the intermediate row, park the result in the output tile
+  // the oldest open output row is complete in A: H pass over the intermediate row, park the results in the tile
   auto hrow = [&]() {
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
@@ -161,42 +204,32 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
       sts64(wb[i] + sel, v0, v1);
     }
     __syncwarp();
-    uint64_t acc = 0ull;
 #pragma unroll
-    for (int j = 0; j < NS; ++j) {
-      const float4 v = lds128(rbase + sel + 16u * j);
-      acc = ffma2(pack2(v.x, v.y), hw[2 * j], acc);
-      acc = ffma2(pack2(v.z, v.w), hw[2 * j + 1], acc);
+    for (int o = 0; o < NO; ++o) {
+      uint64_t acc = 0ull;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const float4 v = lds128(rbase[o] + sel + 16u * j);
+        acc = ffma2(pack2(v.x, v.y), hw[o][2 * j], acc);
+        acc = ffma2(pack2(v.z, v.w), hw[o][2 * j + 1], acc);
+      }
+      float lo, hi;
+      unpack2(acc, lo, hi);
+      // 1/65535 (and a brightness factor that precedes contrast) in one saturating multiply; without brightness the
+      // clamp only trims the one-ulp overshoot a normalised filter can produce
+      const float val = __saturatef((lo + hi) * t.out_scale);
+      sum += val;                                   // columns beyond the view's last column carry zero weights
+      sts32(op + 128u * o, val);
     }
-    float lo, hi;
-    unpack2(acc, lo, hi);
-    // 1/65535 (and a brightness factor that precedes contrast) in one saturating multiply; without brightness the
-    // clamp only trims the one-ulp overshoot a normalised filter can produce
-    const float val = __saturatef((lo + hi) * vscale_out);
-    sum += val;                                   // lanes beyond the view's last column carry zero weights
-    sts32(op, val);
     op += kOPitch * 4;
     sel ^= (uint32_t)(kRowBuf * 4);
   };
 
-  if (t.use_is) {
-    // ---- input-stationary stream over the band's source rows, G rows in flight per lane ------------------
-    // (the schedule guarantees at most one completed output row per source row)
-    // G register slots per lane hold the next G source rows; a slot is refilled (row + G) as soon as it is consumed,
-    // so the loads stay G rows ahead without a second buffer.  Whether a source row completes an output row comes
-    // from a precomputed bit mask (no dependence of the branch on a shared-memory load).
-    constexpr int G = NL == 1 ? 8 : 4;
-    const int nsrc = t.nsrc;
-    const uint32_t rowb = 4u * (uint32_t)t.wq;          // source row pitch in bytes
-    uint64_t gq[NL];                                  // next row to fetch, this lane's columns
-    uint32_t p[G][NL];
-#pragma unroll
-    for (int i = 0; i < NL; ++i) {
-      const uint64_t gl = reinterpret_cast<uint64_t>(t.g0 + lofs[i]);
-#pragma unroll
-      for (int k = 0; k < G; ++k) p[k][i] = ldg_nc_u32(gl + (uint64_t)((uint32_t)min(k, nsrc - 1) * rowb));
-      gq[i] = gl + (uint64_t)((uint32_t)G * rowb);
-    }
+  if (use_is) {
+    // ---- input-stationary stream over the band's source rows --------------------------------------------
+    // A slot is refilled (row + G) as soon as it is consumed, so the loads stay G rows ahead without a second
+    // buffer.  Whether a source row completes an output row comes from a precomputed bit mask (the branch does not
+    // wait for a shared-memory load); the schedule guarantees at most one completed output row per source row.
     const Sched* sp = sh.sched;
 #pragma unroll 1
     for (int rr0 = 0; rr0 < nsrc; rr0 += G) {
@@ -212,9 +245,9 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
         for (int i = 0; i < NL; ++i) {
           f[i] = conv_px<kWindow>(p[k][i], wsc, wof);
           if (k < rem) p[k][i] = ldg_nc_u32(gq[i]);
-          gq[i] += rowb;
+          gq[i] = ptr_add(gq[i], rowb);
         }
-        if (m & (1u << k)) {                            // warp-uniform: output row ycur is complete
+        if (m & (1u << k)) {                            // warp-uniform: the oldest open output row is complete
           hrow();
 #pragma unroll
           for (int i = 0; i < NL; ++i) {                // rotate the accumulators through the FMA operands
@@ -233,7 +266,7 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
       }
       sp += G;
     }
-    const uint32_t op_end = smem_u32(ws.o) + 4u * lane + (uint32_t)t.nrows * (kOPitch * 4);
+    const uint32_t op_end = op0 + (uint32_t)t.nrows * (kOPitch * 4);
 #pragma unroll 1
     while (op != op_end) {
       hrow();
@@ -244,8 +277,36 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
         Cc[i] = 0ull;
       }
     }
+  } else if (sh.kv_max <= 3) {
+    // ---- output-stationary, three taps (vertical upscaling): the taps of the next output row are fetched while
+    // the current one is accumulated
+    uint32_t q[3][NL];
+    auto fetch = [&](int y) {
+      const int2 info = sh.vinfo[y];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const uint32_t rr = (uint32_t)min(info.x - r_lo + k, nsrc - 1);
+#pragma unroll
+        for (int i = 0; i < NL; ++i) q[k][i] = ldg_nc_u32(gl[i] + (uint64_t)(rr * rowb));
+      }
+    };
+    fetch(0);
+#pragma unroll 1
+    for (int y = 0; y < t.nrows; ++y) {
+      uint64_t f[3][NL];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int i = 0; i < NL; ++i) f[k][i] = conv_px<kWindow>(q[k][i], wsc, wof);
+      const float4 wv = *reinterpret_cast<const float4*>(sh.vw[y]);      // zero beyond the window
+      if (y + 1 < t.nrows) fetch(y + 1);
+      const uint64_t w0 = pack2(wv.x, wv.x), w1 = pack2(wv.y, wv.y), w2 = pack2(wv.z, wv.z);
+#pragma unroll
+      for (int i = 0; i < NL; ++i) A[i] = ffma2(f[2][i], w2, ffma2(f[1][i], w1, ffma2(f[0][i], w0, 0ull)));
+      hrow();
+    }
   } else {
-    // ---- output-stationary fallback: vertical upscaling, or a source row feeding more than three output rows ------
+    // ---- output-stationary, any window (a source row feeding more than three output rows) --------------------
 #pragma unroll 1
     for (int y = 0; y < t.nrows; ++y) {
       const int2 info = sh.vinfo[y];
@@ -256,9 +317,9 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
       for (int k = 0; k < info.y; ++k) {
         const float w = wv[k];
         const uint64_t wp = pack2(w, w);
-        const uint32_t ro = (uint32_t)(info.x - t.r_lo + k) * (uint32_t)t.wq;
+        const uint64_t ro = (uint64_t)((uint32_t)(info.x - r_lo + k) * rowb);
 #pragma unroll
-        for (int i = 0; i < NL; ++i) A[i] = ffma2(conv_px<kWindow>(__ldg(t.g0 + ro + lofs[i]), wsc, wof), wp, A[i]);
+        for (int i = 0; i < NL; ++i) A[i] = ffma2(conv_px<kWindow>(ldg_nc_u32(gl[i] + ro), wsc, wof), wp, A[i]);
       }
       hrow();
     }
@@ -267,7 +328,7 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
 }
 
 template <bool kWindow>
-__global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs a) {
+__global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __grid_constant__ TileArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   Smem& sh = *reinterpret_cast<Smem*>(smem);
   const int tid = threadIdx.x;
@@ -294,12 +355,16 @@ __global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs
   const float vsup = vscale >= 1.f ? vscale : 1.f, vinv = vscale >= 1.f ? 1.f / vscale : 1.f;
   const float hsup = hscale >= 1.f ? hscale : 1.f, hinv = hscale >= 1.f ? 1.f / hscale : 1.f;
 
-  // ---- pull the band's crop rows into L2 right away (every thread derives the row range itself) -------------
-  if (!(a.debug_no_cluster & 2)) {
-    int lo0, hi0, lo1, hi1;
+  // ---- the band's source rows ---------------------------------------------------------------------------------
+  int lo0, hi0, lo1, hi1;
+  {
     float ctr;
     aa_window(y0, P.h, vscale, vsup, lo0, hi0, ctr);
     aa_window(y0 + nrows - 1, P.h, vscale, vsup, lo1, hi1, ctr);
+  }
+  const uint32_t p0[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // (early request of the first rows: measured slower, the slots spill)
+  // ---- pull the band's crop rows into L2 (every thread derives the row range itself) --------------------------
+  if (!(a.debug_no_cluster & 2)) {
     const uint8_t* base = reinterpret_cast<const uint8_t*>(a.src + e0);
     const int head = (int)(reinterpret_cast<uintptr_t>(base) & 127);
     const int lines = (head + 2 * P.w + 127) >> 7;               // 128-byte lines per crop row
@@ -310,56 +375,130 @@ __global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs
     }
   }
 
-  // ---- vertical tap tables of the band (one thread per output row) ------------------------------------------
-  if (tid == 0) sh.m_max = 0;
-  if (tid < 8) sh.fmask[tid] = 0u;
-  if (tid < nrows) {
-    int lo, hi;
-    float ctr;
-    aa_window(y0 + tid, P.h, vscale, vsup, lo, hi, ctr);
-    const int kcap = min(2 * (int)ceilf(vsup) + 1, kVK);
+  // ---- this warp's strip: horizontal windows and class (independent of the tables above) --------------------
+  Tile t;
+  t.win_lo = a.win_lo;
+  t.win_scale = a.win_scale;
+  t.sh = &sh;
+  t.ws = &ws;
+  t.crop = a.src + e0;
+  t.W = a.W;
+  t.lane = lane;
+  t.nthreads = nthreads;
+  t.nrows = nrows;
+  t.hinv = hinv;
+  const bool jitter = (P.flags & MIS_VIEW_JITTER) != 0;
+  // brightness (op 0) before contrast (op 1) is applied while the tile is produced: the contrast mean needs it
+  int pos_b = 0, pos_c = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (P.order[k] == 0) pos_b = k;
+    if (P.order[k] == 1) pos_c = k;
+  }
+  const float post = kWindow ? 1.f : (1.f / 65535.f);
+  t.out_scale = opaque((jitter && pos_b < pos_c) ? post * P.brightness : post);
+  const bool has_post = jitter && pos_b > pos_c;
+
+  const int x0 = warp * kStrip;
+  int wlo[2], wsize[2];
+  float wctr[2];
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    const int x = x0 + 32 * o + lane;
+    int lo = 0, hi = 0;
+    float ctr = 0.f;
+    if (x < s) aa_window(x, P.w, hscale, hsup, lo, hi, ctr);
+    const int kcap = 2 * (int)ceilf(hsup) + 1;
     int size = hi - lo;
     size = size < 0 ? 0 : (size > kcap ? kcap : size);
-    float* w = sh.vw[tid];
-    float total = 0.f;
-    for (int j = 0; j < size; ++j) {
-      const float wj = aa_tri(j + lo, ctr, vinv);
-      w[j] = wj;
-      total += wj;
-    }
-    for (int j = 0; j < kVK; ++j) w[j] = (j < size) ? (total != 0.f ? w[j] / total : w[j]) : 0.f;
-    sh.vinfo[tid] = make_int2(lo, size);
+    wlo[o] = lo;
+    wsize[o] = (x < s) ? size : 0;
+    wctr[o] = ctr;
   }
-  __syncthreads();
+  // ---- vertical tap tables of the band: warp 0, one lane per output row ----------------------------------------
+  if (tid == 0) sh.m_max = 0;
+  if (tid < 8) sh.fmask[tid] = 0u;
+  if (warp == 0) {
+    int size = 0;
+    if (tid < nrows) {
+      int lo, hi;
+      float ctr;
+      aa_window(y0 + tid, P.h, vscale, vsup, lo, hi, ctr);
+      const int kcap = min(2 * (int)ceilf(vsup) + 1, kVK);
+      size = hi - lo;
+      size = size < 0 ? 0 : (size > kcap ? kcap : size);
+      float* w = sh.vw[tid];
+      {
+        float total = 0.f;
+        for (int j = 0; j < size; ++j) {
+          const float t0 = aa_tri(j + lo, ctr, vinv);
+          w[j] = t0;
+          total += t0;
+        }
+        if (total != 0.f)
+          for (int j = 0; j < size; ++j) w[j] = w[j] / total;
+        for (int j = size; j < kVK; ++j) w[j] = 0.f;
+      }
+      sh.vinfo[tid] = make_int2(lo, size);
+    }
+    size = __reduce_max_sync(0xffffffffu, size);
+    if (lane == 0) sh.kv_max = size;
+  }
+
+  // staged span of a strip of outputs [o_first, o_last]: from the 4-byte aligned column at or before the first window
+  auto strip = [&](int o_first, int o_last, int& ca, int& span, int& need) {
+    const int c_lo = __shfl_sync(0xffffffffu, wlo[o_first], 0);
+    ca = c_lo - (int)((e0 + c_lo) & 1);
+    int hi = 0, nd = 0;
+    for (int o = o_first; o <= o_last; ++o) {
+      hi = max(hi, wsize[o] > 0 ? wlo[o] + wsize[o] : 0);
+      nd = max(nd, wsize[o] > 0 ? ((wlo[o] - ca) & 3) + wsize[o] : 0);
+    }
+    span = __reduce_max_sync(0xffffffffu, hi) - ca;
+    need = __reduce_max_sync(0xffffffffu, nd);
+  };
+  const bool two = kStrip == 64 && x0 + 32 < s;      // this warp's strip has a second 32-column half
+
+  __syncthreads();                                  // tables of the band are complete
   const int r_lo = sh.vinfo[0].x;
-  const int r_hi = sh.vinfo[nrows - 1].x + sh.vinfo[nrows - 1].y;
-  const int nsrc = r_hi - r_lo;
-  const bool down = (vscale >= 1.f) && (nsrc + 8 <= kSchedCap) && (nsrc > 0);
-  if (down) {
-    // input-stationary schedule (windows are monotone in y): one entry per source row, padded to a whole group
+  const int nsrc = sh.vinfo[nrows - 1].x + sh.vinfo[nrows - 1].y - r_lo;
+  t.down = (vscale >= 1.f) && (nsrc + 8 <= kSchedCap) && (nsrc > 0);
+  if (t.down) {
+    // input-stationary schedule (windows are monotone in y): one entry per source row, padded to a whole group.
+    // Source row r can only lie in the windows of the output rows around (r + 0.5) / vscale - 0.5.
     const int npad = (nsrc + 7) & ~7;
+    const float inv_vs = 1.f / vscale;
     for (int rr = tid; rr < npad; rr += nthreads) {
       float w0 = 0.f, w1 = 0.f, w2 = 0.f;
       int first = 0;
       if (rr < nsrc) {
         const int r = r_lo + rr;
+        const int yc = (int)floorf(((float)r + 0.5f) * inv_vs - 0.5f) - y0;
         int last = -1, prev = nrows;
         first = nrows;
-        for (int yy = 0; yy < nrows; ++yy) {
-          const int2 info = sh.vinfo[yy];
-          if (info.x <= r && r < info.x + info.y) {
-            first = min(first, yy);
-            last = yy;
+#pragma unroll
+        for (int d = -3; d <= 3; ++d) {
+          const int yy = yc + d;
+          if (yy >= 0 && yy < nrows) {
+            const int2 info = sh.vinfo[yy];
+            if (info.x <= r && r < info.x + info.y) {
+              first = min(first, yy);
+              last = max(last, yy);
+            }
+            if (info.x <= r - 1 && r - 1 < info.x + info.y) prev = min(prev, yy);
           }
-          if (info.x <= r - 1 && r - 1 < info.x + info.y) prev = min(prev, yy);
         }
-        if (last < 0) first = 0;       // cannot happen (windows overlap); keeps the stream monotone anyway
+        // the stream handles at most three open output rows and completes at most ONE output row per source row;
+        // anything else (never seen for downscaling windows) sends the band to the output-stationary pass
+        int m = last - first + 1;
+        if (last < 0 || (rr == 0 ? (first != 0) : (prev >= nrows || first - prev > 1 || first < prev))) {
+          m = 4;
+          first = 0;
+          last = -1;
+        }
         if (first <= last) w0 = sh.vw[first][r - sh.vinfo[first].x];
         if (first + 1 <= last) w1 = sh.vw[first + 1][r - sh.vinfo[first + 1].x];
         if (first + 2 <= last) w2 = sh.vw[first + 2][r - sh.vinfo[first + 2].x];
-        // the stream handles at most three open output rows and completes at most ONE output row per source row
-        int m = last - first + 1;
-        if (rr == 0 ? (first != 0) : (first - prev > 1)) m = 4;
         atomicMax(&sh.m_max, m);
         if (rr > 0 && first > prev) atomicOr(&sh.fmask[rr >> 5], 1u << (rr & 31));
       }
@@ -372,61 +511,52 @@ __global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs
       sh.sched[rr] = e;
     }
   }
-  __syncthreads();
 
-  // ---- this warp's tile -------------------------------------------------------------------------------------
-  Tile t;
-  t.win_lo = a.win_lo;
-  t.win_scale = a.win_scale;
-  t.sh = &sh;
-  t.ws = &ws;
-  t.lane = lane;
-  t.nrows = nrows;
-  t.nsrc = nsrc;
-  t.r_lo = r_lo;
-  t.use_is = down && sh.m_max <= 3;
-  t.post = kWindow ? 1.f : (1.f / 65535.f);
-  t.hinv = hinv;
-  const bool jitter = (P.flags & MIS_VIEW_JITTER) != 0;
-  // brightness (op 0) before contrast (op 1) is applied while the tile is produced: the contrast mean needs it
-  int pos_b = 0, pos_c = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (P.order[k] == 0) pos_b = k;
-    if (P.order[k] == 1) pos_c = k;
-  }
-  t.has_pre = jitter && pos_b < pos_c;
-  t.pre_b = P.brightness;
-  const bool has_post = jitter && pos_b > pos_c;
-
-  const int x0 = warp * 32;
-  const int x = x0 + lane;
-  t.valid = x < s;
-  int hlo = 0, hhi = 0;
-  float hctr = 0.f;
-  if (t.valid) aa_window(x, P.w, hscale, hsup, hlo, hhi, hctr);
+  // ---- the tile: class dispatch (the schedule barrier sits inside, behind the per-warp set-up) ---------------
+  float sum = 0.f;
   {
-    const int kcap = 2 * (int)ceilf(hsup) + 1;
-    int size = hhi - hlo;
-    size = size < 0 ? 0 : (size > kcap ? kcap : size);
-    t.hsize = t.valid ? size : 0;
+    int ca, span, need;
+    strip(0, two ? 1 : 0, ca, span, need);
+    auto fill = [&](int o_first, int n) {
+      for (int o = 0; o < 2; ++o) {
+        const int src = o_first + o;
+        const bool on = o < n;
+        t.hlo[o] = on ? wlo[src < 2 ? src : 1] : 0;
+        t.hsize[o] = on ? wsize[src < 2 ? src : 1] : 0;
+        t.hctr[o] = on ? wctr[src < 2 ? src : 1] : 0.f;
+      }
+    };
+    t.ca = ca;
+    t.span = span;
+    t.ocol = 0;
+    t.sync_sched = true;
+    bool done = false;
+    if constexpr (kStrip == 64) {
+      if (two && span <= 128 && need <= 8) {
+        fill(0, 2);
+        sum = run_tile<2, 2, 2, kWindow>(t, p0, false);
+        done = true;
+      } else if (two && span <= 192 && need <= 12) {
+        fill(0, 2);
+        sum = run_tile<3, 3, 2, kWindow>(t, p0, false);
+        done = true;
+      }
+    }
+    if (!done) {
+      // 32-column strips: the only half of the view's last strip, or both halves one after the other
+      for (int h = 0; h < (two ? 2 : 1); ++h) {
+        strip(h, h, ca, span, need);
+        fill(h, 1);
+        t.ca = ca;
+        t.span = span;
+        t.ocol = 32 * h;
+        t.sync_sched = (h == 0);
+        if (span <= 64 && need <= 8) sum += run_tile<1, 2, 1, kWindow>(t, p0, false);
+        else if (span <= 128 && need <= 12) sum += run_tile<2, 3, 1, kWindow>(t, p0, false);
+        else sum += run_tile<3, 4, 1, kWindow>(t, p0, false);
+      }
+    }
   }
-  t.hlo = hlo;
-  t.hctr = hctr;
-  const int c_lo = __shfl_sync(0xffffffffu, hlo, 0);
-  const int ca = c_lo - (int)((e0 + c_lo) & 1);                       // 4-byte aligned first staged column
-  const int c_hi = __reduce_max_sync(0xffffffffu, t.valid ? hlo + t.hsize : 0);
-  t.span = c_hi - ca;
-  t.off = t.valid ? ((hlo - ca) & 3) : 0;
-  t.xa = t.valid ? ((hlo - ca) & ~3) : 0;
-  const int need = __reduce_max_sync(0xffffffffu, t.off + t.hsize);
-  t.wq = a.W >> 1;
-  t.g0 = reinterpret_cast<const uint32_t*>(a.src + e0 + (int64_t)r_lo * a.W + ca);
-
-  float sum;
-  if (t.span <= 64 && need <= 8) sum = run_tile<1, 2, kWindow>(t);
-  else if (t.span <= 128 && need <= 12) sum = run_tile<2, 3, kWindow>(t);
-  else sum = run_tile<3, 4, kWindow>(t);
 
   // ================================ contrast mean over the view ===========================================
   if (!nocl) cluster_wait_acquire();   // phase 1 done: all CTAs of the cluster are resident
@@ -459,39 +589,42 @@ __global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs
   const float mean = a.mean[chan], inv_std = a.inv_std[chan];
   const bool flip = (P.flags & MIS_VIEW_FLIP) != 0;
   const float pb = P.brightness;
+#pragma unroll 1
+  for (int h = 0; h < (two ? 2 : 1); ++h) {
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int id = it * 32 + lane;
-    const int row = id >> 2, xs = x0 + 8 * (id & 3);
-    if (row < nrows && xs < s) {
-      const float* src = ws.o + row * kOPitch + 8 * (id & 3);
-      const float4 v0 = *reinterpret_cast<const float4*>(src);
-      const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
-      float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-      if (jitter) {
+    for (int it = 0; it < 4; ++it) {
+      const int id = it * 32 + lane;
+      const int row = id >> 2, xs = x0 + 32 * h + 8 * (id & 3);
+      if (row < nrows && xs < s) {
+        const float* src = ws.o + row * kOPitch + 32 * h + 8 * (id & 3);
+        const float4 v0 = *reinterpret_cast<const float4*>(src);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        if (jitter) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __saturatef(fmaf(v[i], cf, cadd));
-        if (has_post) {
+          for (int i = 0; i < 8; ++i) v[i] = __saturatef(fmaf(v[i], cf, cadd));
+          if (has_post) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __saturatef(v[i] * pb);
+            for (int i = 0; i < 8; ++i) v[i] = __saturatef(v[i] * pb);
+          }
         }
-      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * inv_std;
-      store_run<8>(v, a.out, ((size_t)plane * s + (y0 + row)) * s, xs, s, flip, a.out_f32 != 0);
+        for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * inv_std;
+        store_run<8>(v, a.out, ((size_t)plane * s + (y0 + row)) * s, xs, s, flip, a.out_f32 != 0);
+      }
     }
   }
 }
 
 bool tile_supported(int C, int H, int W, int64_t img_stride, int s) {
-  // class (3,4) covers 5.5x downscaling per axis: 31*5.5 + 2*5.5 + 2 <= 192 staged columns, 3 + 13 <= 16 aligned taps,
-  // 31*5.5 + 13 + 8 <= kSchedCap schedule rows
-  return C == 1 && s >= 8 && s <= kBand * kMaxWarps && (W & 1) == 0 && (img_stride & 1) == 0 && 2 * W <= 11 * s &&
+  // class (3,4,1) covers 5.5x downscaling per axis: 31*5.5 + 2*5.5 + 2 <= 192 staged columns, 3 + 13 <= 16 aligned
+  // taps, 31*5.5 + 13 + 8 <= kSchedCap schedule rows
+  return C == 1 && s >= 8 && s <= kStrip * kMaxWarps && (W & 1) == 0 && (img_stride & 1) == 0 && 2 * W <= 11 * s &&
          2 * H <= 11 * s;
 }
 
 int launch_tile(const TileArgs& a, int n_views, bool window, cudaStream_t stream) {
-  const int nxw = (a.s + 31) / 32;
+  const int nxw = (a.s + kStrip - 1) / kStrip;
   const size_t smem = sizeof(Smem) + (size_t)nxw * sizeof(WarpSmem);
   auto* fn = window ? &aug_tile_kernel<true> : &aug_tile_kernel<false>;
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -59,6 +59,10 @@ __device__ __forceinline__ uint32_t opaque(uint32_t v) {
   asm volatile("mov.u32 %0, %0;" : "+r"(v));
   return v;
 }
+__device__ __forceinline__ float opaque(float v) {
+  asm volatile("mov.f32 %0, %0;" : "+f"(v));
+  return v;
+}
 
 // mbarrier ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
