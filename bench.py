@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 MEAN, STD = 57.9764 / 255.0, 60.4759 / 255.0      # lightning_module.py:212-213 on the [0,1] scale
 METRIC = "aug views/sec + NT-Xent fwd+bwd ms"
-GPU_LAUNCHES_PER_STEP = 7      # K1 + prep + (tile fwd, rows+mean) + (transpose, tile bwd, finalize)
+GPU_LAUNCHES_PER_STEP = 7      # K1 (aug_tile_kernel) + prep + (tile fwd, rows+mean) + (transpose, tile bwd, finalize)
 
 
 def parse():
@@ -351,7 +351,7 @@ def run_b200(args):
             "aug_ms": ms_aug, "aug_views_per_s_per_gpu": 2 * B / (ms_aug * 1e-3),
             "ntxent_fwd_bwd_ms": ms_loss,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": load_traffic(B, s), "kernel": "aug_kernel (K1)",
+                         "frac": achieved / hbm_peak, "traffic": load_traffic(B, s), "kernel": "aug_tile_kernel (K1)",
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
             "roofline_ntxent": {"bound": "tensor", "achieved": flops_rank / (ms_loss * 1e-3) / 1e12, "peak": tc_peak,
                                 "unit": "TFLOP/s", "frac": flops_rank / (ms_loss * 1e-3) / 1e12 / tc_peak,

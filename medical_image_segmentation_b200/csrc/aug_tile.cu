@@ -126,12 +126,14 @@ __device__ __forceinline__ float run_tile(const Tile& t, const uint32_t (&p0)[8]
     const int xa = t.hsize[o] > 0 ? ((t.hlo[o] - t.ca) & ~3) : 0;
     float tot = 0.f;
     for (int j = 0; j < t.hsize[o]; ++j) tot += aa_tri(j + t.hlo[o], t.hctr[o], t.hinv);
+    // (one reciprocal instead of a division per tap: weights differ from w / total by at most one ulp)
+    const float rtot = tot != 0.f ? __frcp_rn(tot) : 1.f;
     float w[4 * NS];
 #pragma unroll
     for (int jj = 0; jj < 4 * NS; ++jj) {
       const int j = jj - off;
       const float wj = aa_tri(j + t.hlo[o], t.hctr[o], t.hinv);
-      w[jj] = (j >= 0 && j < t.hsize[o]) ? (tot != 0.f ? wj / tot : wj) : 0.f;
+      w[jj] = (j >= 0 && j < t.hsize[o]) ? wj * rtot : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 2 * NS; ++i) hw[o][i] = pack2(w[2 * i], w[2 * i + 1]);
@@ -237,9 +239,6 @@ __device__ __forceinline__ float run_tile(const Tile& t, const uint32_t (&p0)[8]
       const int rem = nsrc - G - rr0;                 // slot k is refilled while k < rem
 #pragma unroll
       for (int k = 0; k < G; ++k) {
-        const float4 s0 = *reinterpret_cast<const float4*>(&sp[k].w[0][0]);
-        const float2 s1 = *reinterpret_cast<const float2*>(&sp[k].w[2][0]);
-        const uint64_t w0 = pack2(s0.x, s0.y), w1 = pack2(s0.z, s0.w), w2 = pack2(s1.x, s1.y);
         uint64_t f[NL];
 #pragma unroll
         for (int i = 0; i < NL; ++i) {
@@ -247,8 +246,12 @@ __device__ __forceinline__ float run_tile(const Tile& t, const uint32_t (&p0)[8]
           if (k < rem) p[k][i] = ldg_nc_u32(gq[i]);
           gq[i] = ptr_add(gq[i], rowb);
         }
+        // (the row's weights are fetched behind the H pass: six fewer live registers across it)
         if (m & (1u << k)) {                            // warp-uniform: the oldest open output row is complete
           hrow();
+          const float4 s0 = *reinterpret_cast<const float4*>(&sp[k].w[0][0]);
+          const float2 s1 = *reinterpret_cast<const float2*>(&sp[k].w[2][0]);
+          const uint64_t w0 = pack2(s0.x, s0.y), w1 = pack2(s0.z, s0.w), w2 = pack2(s1.x, s1.y);
 #pragma unroll
           for (int i = 0; i < NL; ++i) {                // rotate the accumulators through the FMA operands
             A[i] = ffma2(f[i], w0, B[i]);
@@ -256,6 +259,9 @@ __device__ __forceinline__ float run_tile(const Tile& t, const uint32_t (&p0)[8]
             Cc[i] = ffma2(f[i], w2, 0ull);
           }
         } else {
+          const float4 s0 = *reinterpret_cast<const float4*>(&sp[k].w[0][0]);
+          const float2 s1 = *reinterpret_cast<const float2*>(&sp[k].w[2][0]);
+          const uint64_t w0 = pack2(s0.x, s0.y), w1 = pack2(s0.z, s0.w), w2 = pack2(s1.x, s1.y);
 #pragma unroll
           for (int i = 0; i < NL; ++i) {
             A[i] = ffma2(f[i], w0, A[i]);
@@ -407,15 +413,16 @@ __global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __gri
     const int x = x0 + 32 * o + lane;
     int lo = 0, hi = 0;
     float ctr = 0.f;
-    if (x < s) aa_window(x, P.w, hscale, hsup, lo, hi, ctr);
+    if (o < kStrip / 32 && x < s) aa_window(x, P.w, hscale, hsup, lo, hi, ctr);
     const int kcap = 2 * (int)ceilf(hsup) + 1;
     int size = hi - lo;
     size = size < 0 ? 0 : (size > kcap ? kcap : size);
     wlo[o] = lo;
-    wsize[o] = (x < s) ? size : 0;
+    wsize[o] = (o < kStrip / 32 && x < s) ? size : 0;
     wctr[o] = ctr;
   }
-  // ---- vertical tap tables of the band: warp 0, one lane per output row ----------------------------------------
+  // ---- vertical tap tables of the band: warp 0, one lane per output row.  First thing after the parameters: every
+  // other warp needs them at the first barrier and has the prefetch and its strip windows to do meanwhile ---------
   if (tid == 0) sh.m_max = 0;
   if (tid < 8) sh.fmask[tid] = 0u;
   if (warp == 0) {
@@ -435,8 +442,10 @@ __global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __gri
           w[j] = t0;
           total += t0;
         }
-        if (total != 0.f)
-          for (int j = 0; j < size; ++j) w[j] = w[j] / total;
+        if (total != 0.f) {
+          const float rtot = __frcp_rn(total);
+          for (int j = 0; j < size; ++j) w[j] = w[j] * rtot;
+        }
         for (int j = size; j < kVK; ++j) w[j] = 0.f;
       }
       sh.vinfo[tid] = make_int2(lo, size);
