@@ -168,6 +168,15 @@ int mis_ntxent_bwd(const float* u_all, const float* lse_all, const void* z_rows,
                    float grad_scale, const float* grad_out, void* dz, void* scratch,
                    int64_t scratch_bytes, void* stream);
 
+/* Single-rank NT-Xent (cols == rows, row0 == 0): prep, forward and backward with grad_out = 1 in ONE call --
+ * the loss slot of byol_pytorch.py:217 when no cross-GPU gather is involved.  loss[0] and dz (z's dtype) are the
+ * outputs; `workspace` (256-byte aligned, mis_ntxent_fwd_bwd_workspace_bytes(rows, D) bytes) holds u, rinv, lse
+ * and the kernels' scratch and may be reused by the next call on the same stream. */
+int64_t mis_ntxent_fwd_bwd_workspace_bytes(int rows, int D);
+
+int mis_ntxent_fwd_bwd(const void* z, int z_dtype, int rows, int D, float inv_T, float* loss, void* dz,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * BYOL cosine loss, fused forward + backward (the loss the reference actually trains with):
  *   loss[0] = 2 - 2 * mean_i <p_i/|p_i|, t_i/|t_i|>        byol_pytorch.py:196-198

@@ -45,6 +45,9 @@ EXPORTS = {
     "mis_ntxent_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                  C.c_void_p]),
+    "mis_ntxent_fwd_bwd_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
+    "mis_ntxent_fwd_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_void_p]),
     "mis_u16_moments": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "mis_byol_loss_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),

@@ -750,6 +750,35 @@ extern "C" int mis_ntxent_bwd(const float* u_all, const float* lse_all, const vo
   return MIS_OK;
 }
 
+// ---- single-rank convenience: prep -> forward -> backward in one call (7 launches, one host round trip) ----------
+static inline size_t ws_u_bytes(int rows, int D) { return al256((size_t)rows * D * 4); }
+static inline size_t ws_row_bytes(int rows) { return al256((size_t)rows * 4); }
+
+extern "C" int64_t mis_ntxent_fwd_bwd_workspace_bytes(int rows, int D) {
+  const int64_t sc = mis_ntxent_scratch_bytes(rows, rows, D);
+  if (sc < 0) return -1;
+  return (int64_t)(ws_u_bytes(rows, D) + 2 * ws_row_bytes(rows)) + sc;
+}
+
+extern "C" int mis_ntxent_fwd_bwd(const void* z, int z_dtype, int rows, int D, float inv_T, float* loss, void* dz,
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
+  MIS_REQUIRE(z && loss && dz && workspace, MIS_ERR_INVALID_ARG, "mis_ntxent_fwd_bwd: null pointer");
+  const int64_t need = mis_ntxent_fwd_bwd_workspace_bytes(rows, D);
+  MIS_REQUIRE(need > 0 && workspace_bytes >= need, MIS_ERR_INVALID_ARG,
+              "mis_ntxent_fwd_bwd: workspace of %lld bytes, %lld needed", (long long)workspace_bytes, (long long)need);
+  MIS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, MIS_ERR_INVALID_ARG,
+              "mis_ntxent_fwd_bwd: workspace must be 256-byte aligned");
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  float* u = reinterpret_cast<float*>(w);
+  float* rinv = reinterpret_cast<float*>(w + ws_u_bytes(rows, D));
+  float* lse = reinterpret_cast<float*>(w + ws_u_bytes(rows, D) + ws_row_bytes(rows));
+  void* scratch = w + ws_u_bytes(rows, D) + 2 * ws_row_bytes(rows);
+  const int64_t sc = mis_ntxent_scratch_bytes(rows, rows, D);
+  if (int rc = mis_ntxent_prep(z, z_dtype, rows, D, u, rinv, stream)) return rc;
+  if (int rc = mis_ntxent_fwd(u, rows, D, 0, rows, inv_T, lse, loss, scratch, sc, stream)) return rc;
+  return mis_ntxent_bwd(u, lse, z, z_dtype, rinv, rows, D, 0, rows, inv_T, 1.0f, nullptr, dz, scratch, sc, stream);
+}
+
 extern "C" int mis_byol_loss_fwd_bwd(const float* preds, const float* targets, int rows, int D, float* loss,
                                      float* dpreds, float* scratch_rows, void* stream) {
   MIS_REQUIRE(preds && targets && loss && scratch_rows, MIS_ERR_INVALID_ARG, "mis_byol_loss_fwd_bwd: null pointer");

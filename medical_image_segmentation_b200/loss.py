@@ -71,6 +71,31 @@ class CudaKernels:
         CudaKernels.launches += 1
         return z, u, rinv
 
+    _workspaces: dict = {}   # (device, rows, D) -> uint8 workspace of the single-rank fused path (stream-ordered reuse)
+
+    @staticmethod
+    def fwd_bwd_local(z: torch.Tensor, inv_T: float):
+        """Single-rank loss and dL/dz in one call (mis_ntxent_fwd_bwd): 7 kernel launches, one host round trip."""
+        if not z.is_cuda:
+            raise RuntimeError("nt_xent_loss has no CPU path: embeddings must be CUDA tensors")
+        z = z.detach().contiguous()
+        rows, D = z.shape
+        key = (z.device, rows, D)
+        ws = CudaKernels._workspaces.get(key)
+        if ws is None:
+            n = int(_lib.lib.mis_ntxent_fwd_bwd_workspace_bytes(rows, D))
+            if n <= 0:
+                raise ValueError(f"nt_xent_loss: unsupported shape {(rows, D)}")
+            ws = CudaKernels._workspaces[key] = torch.empty((n,), dtype=torch.uint8, device=z.device)
+        loss = torch.empty((1,), dtype=torch.float32, device=z.device)
+        dz = torch.empty_like(z)
+        with _on_device(z.device):
+            rc = _lib.lib.mis_ntxent_fwd_bwd(z.data_ptr(), _dt(z), rows, D, inv_T, loss.data_ptr(), dz.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _stream(z))
+        _lib.check(rc, "mis_ntxent_fwd_bwd")
+        CudaKernels.launches += 6
+        return loss, dz
+
     @staticmethod
     def scratch(rows: int, cols: int, D: int, device) -> torch.Tensor:
         n = int(_lib.lib.mis_ntxent_scratch_bytes(rows, cols, D))
@@ -121,6 +146,12 @@ class _NTXent(torch.autograd.Function):
         rank = dist.get_rank(group) if distributed else 0
         rows = z.shape[0]
         inv_T = 1.0 / float(temperature)
+        if not distributed and kernels is CudaKernels and ctx.needs_input_grad[0]:
+            # single rank: prep + forward + backward (grad_out = 1) in one ABI call; backward() only scales
+            loss, dz = kernels.fwd_bwd_local(z, inv_T)
+            ctx.save_for_backward(dz)
+            ctx.meta = None
+            return loss.reshape(())
         z, u, rinv = kernels.prep(z)
         u_all = _all_gather_rows(u, group) if distributed else u
         scratch = kernels.scratch(rows, u_all.shape[0], u_all.shape[1], z.device)
@@ -131,6 +162,9 @@ class _NTXent(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.meta is None:
+            (dz,) = ctx.saved_tensors
+            return (dz * grad_out.to(dz.dtype)), None, None, None
         z, u_all, rinv, lse = ctx.saved_tensors
         inv_T, group, distributed, rank, kernels, scratch = ctx.meta
         lse_all = _all_gather_rows(lse, group) if distributed else lse

@@ -15,6 +15,8 @@ per-sample CPU callable to a per-batch GPU kernel:
 * ``use_tma`` selects the K1 variant: ``False``/``0`` (default: the warp-tile kernel, csrc/aug_tile.cu, wherever it
   applies), ``True``/``1`` (band kernel, 2-D TMA tensor-map boxes fed by a producer warp) or ``2`` (band kernel,
   per-thread cp.async rings, 16-row sub-bands).  All three are parity-tested against the same oracle.
+* ``prefetch_params=True`` draws the next batch's parameters on a helper thread while the GPU works on the current
+  one (same records in the same order; see ``next_params``).
 * GaussianBlur and Solarize (lightning_module.py:53-54) are not implemented on the device yet:
   ``blur_prob`` / ``solarize_prob`` must be 0 (their RNG draws are still consumed).  The CIFAR data
   modules of the reference run with exactly this setting (lightning_module.py:482-488).
@@ -46,7 +48,8 @@ def _as_float_seq(v, n: int, name: str) -> list[float]:
 class FusedTwoViewTransforms:
     def __init__(self, crop_size: int, mean: Sequence[float], std: Sequence[float],
                  blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0), *, out_dtype=torch.bfloat16,
-                 window: tuple[float, float] | None = None, use_tma: bool | int = False):
+                 window: tuple[float, float] | None = None, use_tma: bool | int = False,
+                 prefetch_params: bool = False):
         assert len(blur_prob) == 2 and len(solarize_prob) == 2, "atm only 2 views are supported"
         if any(p != 0 for p in blur_prob) or any(p != 0 for p in solarize_prob):
             raise NotImplementedError(
@@ -68,6 +71,9 @@ class FusedTwoViewTransforms:
         self.use_tma = int(use_tma)
         if self.use_tma not in (0, 1, 2):
             raise ValueError("use_tma must be 0 (tile kernel), 1 (TMA band kernel) or 2 (cp.async band kernel)")
+        self.prefetch_params = bool(prefetch_params)
+        self._pool = None                     # one helper thread drawing the NEXT batch's parameters
+        self._pending = None                  # ((B, H, W), future)
         self.views_buffer: torch.Tensor | None = None
         self.last_params: np.ndarray | None = None
         self.launches = 0
@@ -78,6 +84,35 @@ class FusedTwoViewTransforms:
     def draw_params(self, B: int, H: int, W: int) -> np.ndarray:
         """Image-major records [2*i+v], drawn like B calls of the reference's __call__."""
         return draw_two_view_params(B, H, W, self.blur_prob, self.solarize_prob)
+
+    def next_params(self, B: int, H: int, W: int) -> np.ndarray:
+        """``draw_params`` with the draw of the FOLLOWING batch started on a helper thread (``prefetch_params=True``):
+        the host RNG replay (~0.4 ms per 1024 slices) then overlaps the GPU work of the current batch.  The records are
+        the same, in the same order, as back-to-back ``draw_params`` calls -- as long as nothing else consumes torch's
+        global CPU generator between calls (the helper thread reads and writes its state)."""
+        if not self.prefetch_params:
+            return self.draw_params(B, H, W)
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mis-params")
+        key = (B, H, W)
+        params = None
+        if self._pending is not None:
+            pkey, fut = self._pending
+            self._pending = None
+            got = fut.result()                       # always joined: the generator is never touched concurrently
+            if pkey == key:
+                params = got
+        if params is None:
+            params = self.draw_params(B, H, W)
+        self._pending = (key, self._pool.submit(self.draw_params, B, H, W))
+        return params
+
+    def drain_prefetch(self) -> None:
+        """Wait for (and drop) a parameter draw in flight, e.g. before re-seeding the generator."""
+        if self._pending is not None:
+            self._pending[1].result()
+            self._pending = None
 
     @staticmethod
     def to_view_major(params: np.ndarray) -> np.ndarray:
@@ -154,7 +189,7 @@ class FusedTwoViewTransforms:
                 raise RuntimeError("FusedTwoViewTransforms has no CPU path: a CUDA device is required")
             x = (x if x.is_pinned() else x.pin_memory()).cuda(non_blocking=True)
         B, _, H, W = x.shape
-        params = self.draw_params(B, H, W)
+        params = self.next_params(B, H, W)
         self.last_params = params
         out = self.apply(x, self.to_view_major(params))
         self.views_buffer = out

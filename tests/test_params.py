@@ -121,3 +121,24 @@ def test_resize_jitter_params_match_torchvision_colorjitter():
     torch.manual_seed(3)
     p0 = t0.draw_params(5, 64, 64)
     assert torch.equal(a, torch.rand(1)) and np.all(p0["flags"] == 0)
+
+
+def test_prefetched_parameter_stream_is_the_same_stream():
+    """prefetch_params=True draws batch k+1 on a helper thread while batch k is in flight: same records, same order."""
+    from medical_image_segmentation_b200 import FusedTwoViewTransforms
+    a = FusedTwoViewTransforms(64, (0.2,), (0.2,))
+    b = FusedTwoViewTransforms(64, (0.2,), (0.2,), prefetch_params=True)
+    torch.manual_seed(99)
+    ref = [a.draw_params(37, 256, 320) for _ in range(5)] + [a.draw_params(8, 128, 128)]
+    torch.manual_seed(99)
+    got = [b.next_params(37, 256, 320) for _ in range(5)]
+    b.drain_prefetch()
+    # the helper thread had already drawn a 6th (37, 256, 320) batch: a shape change redraws from the generator as it
+    # stands, so only the first five batches are comparable one to one
+    for r, g in zip(ref[:5], got):
+        assert r.tobytes() == g.tobytes()
+    torch.manual_seed(5)
+    x = a.draw_params(4, 64, 64)
+    torch.manual_seed(5)
+    assert b.next_params(4, 64, 64).tobytes() == x.tobytes()
+    b.drain_prefetch()
