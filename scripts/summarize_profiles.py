@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 G = os.path.join(ROOT, "gpurun_out")
 
-KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
+KEYS = ['gpu__time_duration.sum', 'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__occupancy_limit_shared_mem',
         'launch__shared_mem_per_block_dynamic', 'launch__cluster_size', 'launch__grid_size', 'launch__block_size',
@@ -38,8 +38,9 @@ def main():
     rep = os.path.join(G, f"aug_{tag}_final.ncu-rep")
     if os.path.exists(rep):
         with open(os.path.join(OUT, f"{tag}_aug_final_ncu.md"), "w") as f:
-            f.write(f"# K1 aug_kernel, final build of {tag}: `ncu --set full --clock-control none`\n\n"
-                    "Command: `python scripts/prof_aug.py 1024 224 0` (default non-TMA staging) = the bench workload (1024 slices 512x512 u16 -> 2048 views 224x224 bf16).\n"
+            f.write(f"# K1 aug_tile_kernel (warp-tile kernel, the default), final build of {tag}: `ncu --set full --clock-control none`\n\n"
+                    "Command: `python scripts/prof_aug.py 1024 224 0` = the bench workload (1024 slices 512x512 u16 -> 2048 views 224x224 bf16).\n"
+                    "(The band kernel it replaced is summarised in r01_aug_band_kernel_ncu.md.)\n"
                     "Times under ncu are cold-cache/serialised; bench.py's CUDA-event time is the number of record.\n\n")
             for v, u in raw(rep):
                 f.write(f"## {v.get('Kernel Name', '')[:80]}\n\n")
