@@ -168,6 +168,36 @@ int mis_ntxent_bwd(const float* u_all, const float* lse_all, const void* z_rows,
                    float grad_scale, const float* grad_out, void* dz, void* scratch,
                    int64_t scratch_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * NT-Xent exchange over NVLink peer memory (one node, world <= 8): the two all-gathers of the loss
+ * (normalised rows in the forward, log-sum-exp scalars for the backward; reference template:
+ * concat_all_gather, train/callback/knn.py:143-144) fused into the kernels that PRODUCE the data.
+ * Every rank passes the same-shaped buffers of all ranks (peer pointers of one symmetric allocation):
+ *
+ *   u_all_peers[r]   rank r's gathered matrix [world*rows, D] f32  (this epoch's buffer)
+ *   lse_all_peers[r] rank r's gathered lse [world*rows] f32        (this epoch's buffer)
+ *   flag_peers[r]    rank r's flag block: uint32 [2][8] flags (slot 0: rows, slot 1: lse; entry = source
+ *                    rank, value = epoch), then 2 producer counters and 1 timeout word; zeroed once
+ *
+ * mis_ntxent_prep_gather   prep + store of the local rows into every rank's matrix at row rank*rows, then
+ *                          flag[0][rank] = epoch on every rank (st.release.sys by the last CTA)
+ * mis_ntxent_fwd_gather    forward over the local copy of the gathered matrix; lse rows are stored into every
+ *                          rank's lse vector, then flag[1][rank] = epoch
+ * mis_peer_wait            enqueue a one-warp kernel that returns once flag[slot][r] >= epoch for all r < world
+ *                          (acquire loads; gives up after ~2 s and sets the timeout word instead of hanging)
+ * `epoch` increases by one per loss evaluation on every rank; buffers alternate with its parity, which is
+ * enough to make reuse safe (a rank reaches epoch k+1 only after every peer finished epoch k-1).
+ * ------------------------------------------------------------------------------------------ */
+int mis_ntxent_prep_gather(const void* z, int z_dtype, int rows, int D, int world, int rank,
+                           void* const* u_all_peers, float* rinv, void* const* flag_peers, uint32_t epoch,
+                           void* stream);
+
+int mis_ntxent_fwd_gather(const float* u_all, int cols, int D, int rows, float inv_T, int world, int rank,
+                          void* const* lse_all_peers, void* const* flag_peers, uint32_t epoch, float* loss,
+                          void* scratch, int64_t scratch_bytes, void* stream);
+
+int mis_peer_wait(const void* flags_local, int slot, int world, uint32_t epoch, void* stream);
+
 /* Single-rank NT-Xent (cols == rows, row0 == 0): prep, forward and backward with grad_out = 1 in ONE call --
  * the loss slot of byol_pytorch.py:217 when no cross-GPU gather is involved.  loss[0] and dz (z's dtype) are the
  * outputs; `workspace` (256-byte aligned, mis_ntxent_fwd_bwd_workspace_bytes(rows, D) bytes) holds u, rinv, lse

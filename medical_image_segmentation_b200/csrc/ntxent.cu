@@ -427,22 +427,77 @@ __device__ __forceinline__ float load_as_f32<float>(const float* p, size_t i) { 
 template <>
 __device__ __forceinline__ float load_as_f32<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) { return __bfloat162float(p[i]); }
 
-// one warp per row: rinv = 1/max(|z|,1e-12), u = tf32(z * rinv)
+// ---- peer-memory exchange (NVLink stores, no NCCL call on the data path) --------------------------------------------
+// A producer kernel writes its rows straight into the same buffer of EVERY rank of the node (peer pointers from CUDA
+// IPC / symmetric memory; dst[rank] is the local copy) and its last CTA raises flag[slot][rank] = epoch in every
+// rank's flag array with a system-scope release; consumers wait for all `world` flags with acquire loads
+// (peer_wait_kernel).  world == 1 degenerates to a plain local store with no signalling.
+constexpr int kMaxPeers = 8;
+struct Peers {
+  float* dst[kMaxPeers];        // per rank: destination buffer (all-gathered layout)
+  uint32_t* flag[kMaxPeers];    // per rank: flag array [2][kMaxPeers]; null when world == 1
+  int world, rank, slot;
+  uint32_t epoch;
+  unsigned int* counter;        // local: CTAs of the producer kernel that have finished (self-resetting)
+};
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// called by every thread of every CTA after its peer stores; the last CTA to arrive signals all ranks
+__device__ __forceinline__ void peers_signal(const Peers& pe) {
+  if (pe.world <= 1) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    if (atomicAdd(pe.counter, 1u) == total - 1) {
+      __threadfence_system();
+      *pe.counter = 0u;
+      for (int r = 0; r < pe.world; ++r) st_release_sys(pe.flag[r] + pe.slot * kMaxPeers + pe.rank, pe.epoch);
+    }
+  }
+}
+// one warp: lane r < world waits until rank r has raised flag[slot][r] to `epoch` (bounded: ~2 s, then *timeout = 1)
+__global__ void peer_wait_kernel(const uint32_t* flags, int slot, int world, uint32_t epoch, uint32_t* timeout) {
+  const int r = threadIdx.x;
+  if (r < world) {
+    const uint32_t* f = flags + slot * kMaxPeers + r;
+    long long spins = 0;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+      __nanosleep(200);
+      if (++spins > 10000000ll) {
+        *timeout = 1u;
+        break;
+      }
+    }
+  }
+}
+
+// one warp per row: rinv = 1/max(|z|,1e-12), u = tf32(z * rinv), written to every rank's gathered matrix at row row0 + i
 template <typename T>
-__global__ void prep_kernel(const T* __restrict__ z, int rows, int D, float* __restrict__ u, float* __restrict__ rinv) {
+__global__ void prep_kernel(const T* __restrict__ z, int rows, int D, int row0, float* __restrict__ rinv, const Peers pe) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  float ss = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    const float v = load_as_f32(z, (size_t)row * D + d);
-    ss = fmaf(v, v, ss);
+  if (row < rows) {
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float v = load_as_f32(z, (size_t)row * D + d);
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    const float r = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int d = lane; d < D; d += 32) {
+      const float v = __uint_as_float(to_tf32(load_as_f32(z, (size_t)row * D + d) * r));
+      for (int q = 0; q < pe.world; ++q) pe.dst[q][(size_t)(row0 + row) * D + d] = v;
+    }
+    if (lane == 0) rinv[row] = r;
   }
-  ss = warp_sum(ss);
-  const float r = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-  for (int d = lane; d < D; d += 32)
-    u[(size_t)row * D + d] = __uint_as_float(to_tf32(load_as_f32(z, (size_t)row * D + d) * r));
-  if (lane == 0) rinv[row] = r;
+  peers_signal(pe);
 }
 
 // U [cols, D] -> U^T [D, cols]
@@ -456,7 +511,7 @@ __global__ void transpose_kernel(const float* __restrict__ u, float* __restrict_
 
 // lse_i = 1/T + log(sum of split partials); pos_i = <u_i,u_p(i)>/T; per-row loss term lse_i - pos_i.  One warp per row.
 __global__ void fwd_rows_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ u_all, int D,
-                                int row0, int rows, float inv_T, float* __restrict__ lse_rows,
+                                int row0, int rows, float inv_T, const Peers lse_pe, int lse_off,
                                 float* __restrict__ row_loss, unsigned int* __restrict__ counter, float* __restrict__ loss) {
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -470,10 +525,11 @@ __global__ void fwd_rows_kernel(const float* __restrict__ partial, int nsplit, c
     for (int d = lane; d < D; d += 32) dot = fmaf(ui[d], up[d], dot);
     dot = warp_sum(dot);
     if (lane == 0) {
-      lse_rows[i] = lse;
+      for (int q = 0; q < lse_pe.world; ++q) lse_pe.dst[q][lse_off + i] = lse;     // every rank's gathered lse
       row_loss[i] = lse - dot * inv_T;
     }
   }
+  peers_signal(lse_pe);
   // loss = mean(row_loss): the last block to finish sums all rows in a fixed order (deterministic, no extra launch)
   __shared__ bool last;
   __shared__ float red[32];
@@ -647,24 +703,73 @@ extern "C" int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D) {
   return (int64_t)b;
 }
 
+static int launch_prep(const void* z, int z_dtype, int rows, int D, int row0, float* rinv, const Peers& pe, cudaStream_t st) {
+  const int wpb = 8;
+  const dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
+  if (z_dtype == MIS_DTYPE_F32)
+    prep_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(z), rows, D, row0, rinv, pe);
+  else
+    prep_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(z), rows, D, row0, rinv, pe);
+  MIS_CUDA_TRY(cudaGetLastError());
+  return MIS_OK;
+}
+static Peers local_peers(float* dst) {
+  Peers pe = {};
+  pe.dst[0] = dst;
+  pe.world = 1;
+  return pe;
+}
+// flag arrays are [2][kMaxPeers] uint32 followed by the producer counter and the timeout word (local only)
+static int make_peers(Peers* pe, const char* who, int world, int rank, void* const* dst_peers, void* const* flag_peers,
+                      int slot, uint32_t epoch) {
+  MIS_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, MIS_ERR_INVALID_ARG,
+              "%s: world %d / rank %d (at most %d ranks of one node)", who, world, rank, kMaxPeers);
+  MIS_REQUIRE(dst_peers && flag_peers && (slot == 0 || slot == 1), MIS_ERR_INVALID_ARG, "%s: null peer table", who);
+  *pe = Peers{};
+  for (int r = 0; r < world; ++r) {
+    MIS_REQUIRE(dst_peers[r] && flag_peers[r], MIS_ERR_INVALID_ARG, "%s: null peer pointer for rank %d", who, r);
+    pe->dst[r] = static_cast<float*>(dst_peers[r]);
+    pe->flag[r] = static_cast<uint32_t*>(flag_peers[r]);
+  }
+  pe->world = world;
+  pe->rank = rank;
+  pe->slot = slot;
+  pe->epoch = epoch;
+  pe->counter = reinterpret_cast<unsigned int*>(pe->flag[rank] + 2 * kMaxPeers + slot);
+  return MIS_OK;
+}
+
 extern "C" int mis_ntxent_prep(const void* z, int z_dtype, int rows, int D, float* u, float* rinv, void* stream) {
   MIS_REQUIRE(z && u && rinv, MIS_ERR_INVALID_ARG, "mis_ntxent_prep: null pointer");
   MIS_REQUIRE(rows > 0 && D > 0, MIS_ERR_INVALID_ARG, "mis_ntxent_prep: sizes must be positive");
   MIS_REQUIRE(z_dtype == MIS_DTYPE_F32 || z_dtype == MIS_DTYPE_BF16, MIS_ERR_INVALID_ARG, "mis_ntxent_prep: dtype %d", z_dtype);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int wpb = 8;
-  const dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
-  if (z_dtype == MIS_DTYPE_F32)
-    prep_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(z), rows, D, u, rinv);
-  else
-    prep_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(z), rows, D, u, rinv);
+  return launch_prep(z, z_dtype, rows, D, 0, rinv, local_peers(u), reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mis_ntxent_prep_gather(const void* z, int z_dtype, int rows, int D, int world, int rank,
+                                      void* const* u_all_peers, float* rinv, void* const* flag_peers, uint32_t epoch,
+                                      void* stream) {
+  MIS_REQUIRE(z && rinv, MIS_ERR_INVALID_ARG, "mis_ntxent_prep_gather: null pointer");
+  MIS_REQUIRE(rows > 0 && D > 0, MIS_ERR_INVALID_ARG, "mis_ntxent_prep_gather: sizes must be positive");
+  MIS_REQUIRE(z_dtype == MIS_DTYPE_F32 || z_dtype == MIS_DTYPE_BF16, MIS_ERR_INVALID_ARG, "mis_ntxent_prep_gather: dtype %d", z_dtype);
+  Peers pe;
+  if (int rc = make_peers(&pe, "mis_ntxent_prep_gather", world, rank, u_all_peers, flag_peers, 0, epoch)) return rc;
+  return launch_prep(z, z_dtype, rows, D, rank * rows, rinv, pe, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mis_peer_wait(const void* flags_local, int slot, int world, uint32_t epoch, void* stream) {
+  MIS_REQUIRE(flags_local && (slot == 0 || slot == 1) && world >= 1 && world <= kMaxPeers, MIS_ERR_INVALID_ARG,
+              "mis_peer_wait: bad arguments");
+  const uint32_t* f = static_cast<const uint32_t*>(flags_local);
+  uint32_t* timeout = const_cast<uint32_t*>(f) + 2 * kMaxPeers + 2;
+  peer_wait_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(f, slot, world, epoch, timeout);
   MIS_CUDA_TRY(cudaGetLastError());
   return MIS_OK;
 }
 
-extern "C" int mis_ntxent_fwd(const float* u_all, int cols, int D, int row0, int rows, float inv_T, float* lse_rows,
-                              float* loss, void* scratch, int64_t scratch_bytes, void* stream) {
-  MIS_REQUIRE(u_all && lse_rows && loss && scratch, MIS_ERR_INVALID_ARG, "mis_ntxent_fwd: null pointer");
+static int ntxent_fwd_impl(const float* u_all, int cols, int D, int row0, int rows, float inv_T, const Peers& lse_pe,
+                           int lse_off, float* loss, void* scratch, int64_t scratch_bytes, void* stream) {
+  MIS_REQUIRE(u_all && loss && scratch, MIS_ERR_INVALID_ARG, "mis_ntxent_fwd: null pointer");
   if (int rc = check_shapes("mis_ntxent_fwd", rows, cols, D, row0, inv_T, false)) return rc;
   MIS_REQUIRE(scratch_bytes >= mis_ntxent_scratch_bytes(rows, cols, D), MIS_ERR_INVALID_ARG,
               "mis_ntxent_fwd: scratch too small (%lld < %lld)", (long long)scratch_bytes,
@@ -690,10 +795,25 @@ extern "C" int mis_ntxent_fwd(const float* u_all, int cols, int D, int row0, int
   unsigned int* counter = reinterpret_cast<unsigned int*>(sc);                 // first 256 B of the scratch
   float* row_loss = reinterpret_cast<float*>(sc + 256);
   MIS_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));         // scratch arrives uninitialised
-  fwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(partial, 2 * p.nsplit, u_all, D, row0, rows, inv_T, lse_rows, row_loss,
-                                                  counter, loss);
+  fwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(partial, 2 * p.nsplit, u_all, D, row0, rows, inv_T, lse_pe, lse_off,
+                                                  row_loss, counter, loss);
   MIS_CUDA_TRY(cudaGetLastError());
   return MIS_OK;
+}
+
+extern "C" int mis_ntxent_fwd(const float* u_all, int cols, int D, int row0, int rows, float inv_T, float* lse_rows,
+                              float* loss, void* scratch, int64_t scratch_bytes, void* stream) {
+  MIS_REQUIRE(lse_rows, MIS_ERR_INVALID_ARG, "mis_ntxent_fwd: null pointer");
+  return ntxent_fwd_impl(u_all, cols, D, row0, rows, inv_T, local_peers(lse_rows), 0, loss, scratch, scratch_bytes, stream);
+}
+
+extern "C" int mis_ntxent_fwd_gather(const float* u_all, int cols, int D, int rows, float inv_T, int world, int rank,
+                                     void* const* lse_all_peers, void* const* flag_peers, uint32_t epoch, float* loss,
+                                     void* scratch, int64_t scratch_bytes, void* stream) {
+  Peers pe;
+  if (int rc = make_peers(&pe, "mis_ntxent_fwd_gather", world, rank, lse_all_peers, flag_peers, 1, epoch)) return rc;
+  MIS_REQUIRE(cols == world * rows, MIS_ERR_INVALID_ARG, "mis_ntxent_fwd_gather: cols %d != world %d x rows %d", cols, world, rows);
+  return ntxent_fwd_impl(u_all, cols, D, rank * rows, rows, inv_T, pe, rank * rows, loss, scratch, scratch_bytes, stream);
 }
 
 extern "C" int mis_ntxent_bwd(const float* u_all, const float* lse_all, const void* z_rows, int z_dtype,

@@ -21,7 +21,7 @@ import ctypes as C
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, peer
 from ._lib import MIS_DTYPE_BF16, MIS_DTYPE_F32
 
 
@@ -97,6 +97,37 @@ class CudaKernels:
         return loss, dz
 
     @staticmethod
+    def fwd_peer(z: torch.Tensor, ex, par: int, inv_T: float):
+        """Forward with the NVLink exchange fused into the producing kernels (mis_ntxent_prep_gather / _fwd_gather)."""
+        z = z.contiguous()
+        rows, D = z.shape
+        rinv = torch.empty((rows,), dtype=torch.float32, device=z.device)
+        loss = torch.empty((1,), dtype=torch.float32, device=z.device)
+        scratch = CudaKernels.scratch(rows, ex.cols, D, z.device)
+        st = _stream(z)
+        with _on_device(z.device):
+            rc = _lib.lib.mis_ntxent_prep_gather(z.data_ptr(), _dt(z), rows, D, ex.world, ex.rank, ex.u_peers[par],
+                                                 rinv.data_ptr(), ex.flag_peers, ex.epoch, st)
+            _lib.check(rc, "mis_ntxent_prep_gather")
+            _lib.check(_lib.lib.mis_peer_wait(ex.flags_ptr, 0, ex.world, ex.epoch, st), "mis_peer_wait")
+            rc = _lib.lib.mis_ntxent_fwd_gather(ex.u_all[par].data_ptr(), ex.cols, D, rows, inv_T, ex.world, ex.rank,
+                                                ex.l_peers[par], ex.flag_peers, ex.epoch, loss.data_ptr(),
+                                                scratch.data_ptr(), scratch.numel(), st)
+            _lib.check(rc, "mis_ntxent_fwd_gather")
+        ex.scratch = scratch
+        CudaKernels.launches += 4
+        return z, rinv, loss
+
+    @staticmethod
+    def bwd_peer(z, rinv, ex, epoch: int, inv_T: float, grad_out: torch.Tensor):
+        par = epoch & 1
+        st = _stream(z)
+        with _on_device(z.device):
+            _lib.check(_lib.lib.mis_peer_wait(ex.flags_ptr, 1, ex.world, epoch, st), "mis_peer_wait")
+        CudaKernels.launches += 1
+        return CudaKernels.bwd(ex.u_all[par], ex.lse_all[par], z, rinv, ex.rank * z.shape[0], inv_T, grad_out, ex.scratch)
+
+    @staticmethod
     def scratch(rows: int, cols: int, D: int, device) -> torch.Tensor:
         n = int(_lib.lib.mis_ntxent_scratch_bytes(rows, cols, D))
         return torch.empty((n,), dtype=torch.uint8, device=device)
@@ -152,6 +183,17 @@ class _NTXent(torch.autograd.Function):
             ctx.save_for_backward(dz)
             ctx.meta = None
             return loss.reshape(())
+        if distributed and kernels is CudaKernels:
+            ex = peer.get_exchange(group, rows, z.shape[1], z.device)
+            if ex is not None and ex.in_flight[(ex.epoch + 1) & 1] == 0:
+                # NVLink peer stores: prep writes the rows into every rank's matrix, the forward its lse rows
+                ex.epoch += 1
+                par = ex.epoch & 1
+                ex.in_flight[par] += 1
+                z, rinv, loss = kernels.fwd_peer(z, ex, par, inv_T)
+                ctx.save_for_backward(z, rinv)
+                ctx.meta = ("peer", inv_T, ex, ex.epoch, kernels)
+                return loss.reshape(())
         z, u, rinv = kernels.prep(z)
         u_all = _all_gather_rows(u, group) if distributed else u
         scratch = kernels.scratch(rows, u_all.shape[0], u_all.shape[1], z.device)
@@ -165,6 +207,12 @@ class _NTXent(torch.autograd.Function):
         if ctx.meta is None:
             (dz,) = ctx.saved_tensors
             return (dz * grad_out.to(dz.dtype)), None, None, None
+        if ctx.meta[0] == "peer":
+            z, rinv = ctx.saved_tensors
+            _, inv_T, ex, epoch, kernels = ctx.meta
+            dz = kernels.bwd_peer(z, rinv, ex, epoch, inv_T, grad_out)
+            ex.in_flight[epoch & 1] -= 1
+            return dz, None, None, None
         z, u_all, rinv, lse = ctx.saved_tensors
         inv_T, group, distributed, rank, kernels, scratch = ctx.meta
         lse_all = _all_gather_rows(lse, group) if distributed else lse

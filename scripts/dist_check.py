@@ -12,7 +12,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for (B, D, T) in ((64, 64, 0.1), (256, 128, 0.1), (128, 256, 0.2)):
+for (B, D, T) in ((64, 64, 0.1), (256, 128, 0.1), (128, 256, 0.2), (256, 128, 0.1), (256, 128, 0.1)):
     g = torch.Generator().manual_seed(11)
     z_locals = [torch.randn(2 * B, D, generator=g) for _ in range(world)]
     ref_losses, ref_grads = L.ntxent_rank_sharded(z_locals, T)
@@ -28,6 +28,12 @@ for (B, D, T) in ((64, 64, 0.1), (256, 128, 0.1), (128, 256, 0.2)):
     good = fro <= 1e-3 and lrel <= 1e-3
     ok &= good
     print(f"rank {rank}/{world} B={B} D={D} T={T}: loss rel {lrel:.2e} grad fro rel {fro:.2e} {'OK' if good else 'FAIL'}", flush=True)
+from medical_image_segmentation_b200 import peer
+print(f"rank {rank}: exchange mode {peer.mode()}, peer exchanges in use: {len(peer._cache)}, disabled: {peer._disabled_reason}", flush=True)
+for ex in peer._cache.values():
+    if ex.timed_out():
+        ok = False
+        print(f"rank {rank}: peer wait TIMED OUT", flush=True)
 flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
