@@ -11,6 +11,7 @@ Public surface (mirrors the reference's transform / loss call sites, see DESIGN.
 Importing this package loads libmis_b200.so; there is no CPU fallback.
 """
 from . import _lib  # noqa: F401  (fails loudly when the CUDA library is missing)
+from . import peer  # noqa: F401
 from .loss import byol_cosine_loss, nt_xent_loss, nt_xent_rows
 from .metrics import compute_mean_and_std
 from .params import draw_two_view_params, draw_two_view_params_torch
