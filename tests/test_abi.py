@@ -83,3 +83,26 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_peer_exchange_argument_errors_and_mode_switch(monkeypatch):
+    """The NVLink-exchange entry points validate their peer tables before any CUDA call; MIS_NTXENT_EXCHANGE=nccl
+    turns the peer path off without touching symmetric memory."""
+    from medical_image_segmentation_b200 import _lib, peer
+    lib = _lib.lib
+    buf = np.zeros(256, np.uint8)
+    p = buf.ctypes.data
+    tbl = (C.c_void_p * 8)(*([p] * 8))
+    null_tbl = (C.c_void_p * 8)(*([p] + [None] * 7))
+    assert lib.mis_ntxent_prep_gather(p, 1, 128, 64, 9, 0, tbl, p, tbl, 1, None) == _lib.MIS_ERR_INVALID_ARG      # > 8 ranks
+    assert lib.mis_ntxent_prep_gather(p, 1, 128, 64, 2, 2, tbl, p, tbl, 1, None) == _lib.MIS_ERR_INVALID_ARG      # rank >= world
+    assert lib.mis_ntxent_prep_gather(p, 1, 128, 64, 2, 0, null_tbl, p, tbl, 1, None) == _lib.MIS_ERR_INVALID_ARG  # null peer
+    assert b"rank 1" in lib.mis_last_error()
+    assert lib.mis_ntxent_fwd_gather(p, 256, 64, 100, 10.0, 2, 0, tbl, tbl, 1, p, p, 1 << 30, None) == _lib.MIS_ERR_INVALID_ARG
+    assert lib.mis_peer_wait(None, 0, 2, 1, None) == _lib.MIS_ERR_INVALID_ARG
+    assert lib.mis_peer_wait(p, 2, 2, 1, None) == _lib.MIS_ERR_INVALID_ARG
+    monkeypatch.setenv("MIS_NTXENT_EXCHANGE", "nccl")
+    assert peer.mode() == "nccl" and peer.get_exchange(None, 128, 64, None) is None
+    monkeypatch.delenv("MIS_NTXENT_EXCHANGE")
+    assert peer.mode() == "auto"
+    assert peer._FLAG_BYTES >= 4 * (2 * peer.MAX_PEERS + 3)       # flags [2][8] + 2 counters + timeout word (csrc/ntxent.cu)

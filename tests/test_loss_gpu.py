@@ -134,3 +134,17 @@ def test_mean_std_matches_reference_formula():
     assert abs(float(std[0]) - float(ref_std)) <= 1e-9 * float(ref_std)
     m01, s01 = compute_mean_and_std(batches, scale=1.0 / 65535.0)
     assert abs(float(m01[0]) - float(ref_mean) / 65535.0) < 1e-12
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one node")
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_two_rank_exchange_matches_sharded_oracle(exchange):
+    """NVLink peer-store exchange (and the NCCL fallback) on two real ranks: scripts/dist_check.py compares every
+    rank's loss and gradient with the rank-sharded oracle and fails on a peer-wait timeout."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MIS_NTXENT_EXCHANGE=exchange)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "scripts", "dist_check.py")],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
