@@ -198,6 +198,18 @@ int mis_ntxent_fwd_gather(const float* u_all, int cols, int D, int rows, float i
 
 int mis_peer_wait(const void* flags_local, int slot, int world, uint32_t epoch, void* stream);
 
+/* The same three / two steps as one call per autograd phase (what loss.py uses): forward = prep_gather, wait for the
+ * rows of all ranks, fwd_gather; backward = wait for the lse of all ranks, mis_ntxent_bwd over the local copies. */
+int mis_ntxent_fwd_peer(const void* z, int z_dtype, int rows, int D, float inv_T, int world, int rank,
+                        void* const* u_all_peers, void* const* lse_all_peers, void* const* flag_peers,
+                        uint32_t epoch, float* rinv, float* loss, void* scratch, int64_t scratch_bytes,
+                        void* stream);
+
+int mis_ntxent_bwd_peer(const float* u_all, const float* lse_all, const void* z_rows, int z_dtype,
+                        const float* rinv_rows, int D, int rows, float inv_T, float grad_scale,
+                        const float* grad_out, void* dz, int world, int rank, const void* flags_local,
+                        uint32_t epoch, void* scratch, int64_t scratch_bytes, void* stream);
+
 /* Single-rank NT-Xent (cols == rows, row0 == 0): prep, forward and backward with grad_out = 1 in ONE call --
  * the loss slot of byol_pytorch.py:217 when no cross-GPU gather is involved.  loss[0] and dz (z's dtype) are the
  * outputs; `workspace` (256-byte aligned, mis_ntxent_fwd_bwd_workspace_bytes(rows, D) bytes) holds u, rinv, lse

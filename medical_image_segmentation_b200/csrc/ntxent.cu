@@ -870,6 +870,28 @@ extern "C" int mis_ntxent_bwd(const float* u_all, const float* lse_all, const vo
   return MIS_OK;
 }
 
+// ---- one ABI call per autograd phase of the peer-exchange path (fewer host round trips per step) ------------------
+extern "C" int mis_ntxent_fwd_peer(const void* z, int z_dtype, int rows, int D, float inv_T, int world, int rank,
+                                   void* const* u_all_peers, void* const* lse_all_peers, void* const* flag_peers,
+                                   uint32_t epoch, float* rinv, float* loss, void* scratch, int64_t scratch_bytes,
+                                   void* stream) {
+  MIS_REQUIRE(u_all_peers && flag_peers && rank >= 0 && rank < world && world <= kMaxPeers, MIS_ERR_INVALID_ARG,
+              "mis_ntxent_fwd_peer: bad peer tables / rank %d of %d", rank, world);
+  if (int rc = mis_ntxent_prep_gather(z, z_dtype, rows, D, world, rank, u_all_peers, rinv, flag_peers, epoch, stream)) return rc;
+  if (int rc = mis_peer_wait(flag_peers[rank], 0, world, epoch, stream)) return rc;
+  return mis_ntxent_fwd_gather(static_cast<const float*>(u_all_peers[rank]), world * rows, D, rows, inv_T, world, rank,
+                               lse_all_peers, flag_peers, epoch, loss, scratch, scratch_bytes, stream);
+}
+
+extern "C" int mis_ntxent_bwd_peer(const float* u_all, const float* lse_all, const void* z_rows, int z_dtype,
+                                   const float* rinv_rows, int D, int rows, float inv_T, float grad_scale,
+                                   const float* grad_out, void* dz, int world, int rank, const void* flags_local,
+                                   uint32_t epoch, void* scratch, int64_t scratch_bytes, void* stream) {
+  if (int rc = mis_peer_wait(flags_local, 1, world, epoch, stream)) return rc;
+  return mis_ntxent_bwd(u_all, lse_all, z_rows, z_dtype, rinv_rows, world * rows, D, rank * rows, rows, inv_T, grad_scale,
+                        grad_out, dz, scratch, scratch_bytes, stream);
+}
+
 // ---- single-rank convenience: prep -> forward -> backward in one call (7 launches, one host round trip) ----------
 static inline size_t ws_u_bytes(int rows, int D) { return al256((size_t)rows * D * 4); }
 static inline size_t ws_row_bytes(int rows) { return al256((size_t)rows * 4); }

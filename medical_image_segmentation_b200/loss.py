@@ -98,34 +98,36 @@ class CudaKernels:
 
     @staticmethod
     def fwd_peer(z: torch.Tensor, ex, par: int, inv_T: float):
-        """Forward with the NVLink exchange fused into the producing kernels (mis_ntxent_prep_gather / _fwd_gather)."""
+        """Forward with the NVLink exchange fused into the producing kernels: one ABI call (mis_ntxent_fwd_peer =
+        prep_gather, wait for every rank's rows, fwd_gather)."""
         z = z.contiguous()
         rows, D = z.shape
-        rinv = torch.empty((rows,), dtype=torch.float32, device=z.device)
+        if ex.scratch is None:
+            ex.scratch = CudaKernels.scratch(rows, ex.cols, D, z.device)
+            ex.rinv = [torch.empty((rows,), dtype=torch.float32, device=z.device) for _ in range(2)]
         loss = torch.empty((1,), dtype=torch.float32, device=z.device)
-        scratch = CudaKernels.scratch(rows, ex.cols, D, z.device)
-        st = _stream(z)
         with _on_device(z.device):
-            rc = _lib.lib.mis_ntxent_prep_gather(z.data_ptr(), _dt(z), rows, D, ex.world, ex.rank, ex.u_peers[par],
-                                                 rinv.data_ptr(), ex.flag_peers, ex.epoch, st)
-            _lib.check(rc, "mis_ntxent_prep_gather")
-            _lib.check(_lib.lib.mis_peer_wait(ex.flags_ptr, 0, ex.world, ex.epoch, st), "mis_peer_wait")
-            rc = _lib.lib.mis_ntxent_fwd_gather(ex.u_all[par].data_ptr(), ex.cols, D, rows, inv_T, ex.world, ex.rank,
-                                                ex.l_peers[par], ex.flag_peers, ex.epoch, loss.data_ptr(),
-                                                scratch.data_ptr(), scratch.numel(), st)
-            _lib.check(rc, "mis_ntxent_fwd_gather")
-        ex.scratch = scratch
+            rc = _lib.lib.mis_ntxent_fwd_peer(z.data_ptr(), _dt(z), rows, D, inv_T, ex.world, ex.rank, ex.u_peers[par],
+                                              ex.l_peers[par], ex.flag_peers, ex.epoch, ex.rinv[par].data_ptr(),
+                                              loss.data_ptr(), ex.scratch.data_ptr(), ex.scratch.numel(), _stream(z))
+        _lib.check(rc, "mis_ntxent_fwd_peer")
         CudaKernels.launches += 4
-        return z, rinv, loss
+        return z, ex.rinv[par], loss
 
     @staticmethod
     def bwd_peer(z, rinv, ex, epoch: int, inv_T: float, grad_out: torch.Tensor):
         par = epoch & 1
-        st = _stream(z)
+        rows, D = z.shape
+        dz = torch.empty_like(z)
+        g = grad_out if (grad_out.dtype == torch.float32 and grad_out.is_contiguous()) else grad_out.to(torch.float32).contiguous()
         with _on_device(z.device):
-            _lib.check(_lib.lib.mis_peer_wait(ex.flags_ptr, 1, ex.world, epoch, st), "mis_peer_wait")
-        CudaKernels.launches += 1
-        return CudaKernels.bwd(ex.u_all[par], ex.lse_all[par], z, rinv, ex.rank * z.shape[0], inv_T, grad_out, ex.scratch)
+            rc = _lib.lib.mis_ntxent_bwd_peer(ex.u_all[par].data_ptr(), ex.lse_all[par].data_ptr(), z.data_ptr(), _dt(z),
+                                              rinv.data_ptr(), D, rows, inv_T, 1.0, g.data_ptr(), dz.data_ptr(), ex.world,
+                                              ex.rank, ex.flags_ptr, epoch, ex.scratch.data_ptr(), ex.scratch.numel(),
+                                              _stream(z))
+        _lib.check(rc, "mis_ntxent_bwd_peer")
+        CudaKernels.launches += 4
+        return dz
 
     @staticmethod
     def scratch(rows: int, cols: int, D: int, device) -> torch.Tensor:

@@ -58,6 +58,8 @@ class PeerExchange:
         self.u_all = [self.buf[o:o + self.cols * D * 4].view(torch.float32).view(self.cols, D) for o in self.off_u]
         self.lse_all = [self.buf[o:o + self.cols * 4].view(torch.float32) for o in self.off_l]
         self.epoch = 0
+        self.scratch = None                              # kernel scratch + rinv per parity (allocated by loss.py)
+        self.rinv = None
         self.in_flight = [0, 0]                          # forwards whose backward has not run yet, per parity
 
     def timed_out(self) -> bool:
