@@ -374,11 +374,9 @@ __global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __gri
     const uint8_t* base = reinterpret_cast<const uint8_t*>(a.src + e0);
     const int head = (int)(reinterpret_cast<uintptr_t>(base) & 127);
     const int lines = (head + 2 * P.w + 127) >> 7;               // 128-byte lines per crop row
-    const int total = (hi1 - lo0) * lines;
-    for (int i = tid; i < total; i += nthreads) {
-      const int r = lo0 + i / lines, l = i - (i / lines) * lines;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)r * a.W * 2 - head + l * 128));
-    }
+    if (lane < lines)                                            // one source row per warp and step, one line per lane
+      for (int r = lo0 + warp; r < hi1; r += (nthreads >> 5))
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)r * a.W * 2 - head + lane * 128));
   }
 
   // ---- this warp's strip: horizontal windows and class (independent of the tables above) --------------------
@@ -434,8 +432,22 @@ __global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __gri
       const int kcap = min(2 * (int)ceilf(vsup) + 1, kVK);
       size = hi - lo;
       size = size < 0 ? 0 : (size > kcap ? kcap : size);
-      float* w = sh.vw[tid];
-      {
+      float4* w4 = reinterpret_cast<float4*>(sh.vw[tid]);
+      if (size <= 8) {                                  // the usual case: taps in registers, no loops, two 16-byte stores
+        float wj[8];
+        float total = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          wj[j] = (j < size) ? aa_tri(j + lo, ctr, vinv) : 0.f;
+          total += wj[j];                               // same order as the reference (zeros beyond the window)
+        }
+        const float rtot = total != 0.f ? __frcp_rn(total) : 1.f;
+        w4[0] = make_float4(wj[0] * rtot, wj[1] * rtot, wj[2] * rtot, wj[3] * rtot);
+        w4[1] = make_float4(wj[4] * rtot, wj[5] * rtot, wj[6] * rtot, wj[7] * rtot);
+        w4[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w4[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        float* w = sh.vw[tid];
         float total = 0.f;
         for (int j = 0; j < size; ++j) {
           const float t0 = aa_tri(j + lo, ctr, vinv);
