@@ -197,8 +197,10 @@ __device__ __forceinline__ float run_tile(const Tile& t, const uint32_t (&p0)[8]
   const uint32_t op0 = smem_u32(ws.o) + 4u * (t.ocol + lane);
   uint32_t op = opaque(op0);
 
-  // the oldest open output row is complete in A: H pass over the intermediate row, park the results in the tile
-  auto hrow = [&]() {
+  // the oldest open output row is complete in A: H pass over the intermediate row (first half: park the row, read the
+  // windows, accumulate; second half: scale, clamp, sum, park the results in the tile)
+  uint64_t hacc[NO];
+  auto hrow_a = [&]() {
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
       float v0, v1;
@@ -215,8 +217,14 @@ __device__ __forceinline__ float run_tile(const Tile& t, const uint32_t (&p0)[8]
         acc = ffma2(pack2(v.x, v.y), hw[o][2 * j], acc);
         acc = ffma2(pack2(v.z, v.w), hw[o][2 * j + 1], acc);
       }
+      hacc[o] = acc;
+    }
+  };
+  auto hrow_b = [&]() {
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
       float lo, hi;
-      unpack2(acc, lo, hi);
+      unpack2(hacc[o], lo, hi);
       // 1/65535 (and a brightness factor that precedes contrast) in one saturating multiply; without brightness the
       // clamp only trims the one-ulp overshoot a normalised filter can produce
       const float val = __saturatef((lo + hi) * t.out_scale);
@@ -225,6 +233,10 @@ __device__ __forceinline__ float run_tile(const Tile& t, const uint32_t (&p0)[8]
     }
     op += kOPitch * 4;
     sel ^= (uint32_t)(kRowBuf * 4);
+  };
+  auto hrow = [&]() {
+    hrow_a();
+    hrow_b();
   };
 
   if (use_is) {
@@ -246,11 +258,13 @@ __device__ __forceinline__ float run_tile(const Tile& t, const uint32_t (&p0)[8]
           if (k < rem) p[k][i] = ldg_nc_u32(gq[i]);
           gq[i] = ptr_add(gq[i], rowb);
         }
-        // (the row's weights are fetched behind the H pass: six fewer live registers across it)
         if (m & (1u << k)) {                            // warp-uniform: the oldest open output row is complete
-          hrow();
+          // the row's weights are requested between the two halves of the H pass: not live across its window loads,
+          // yet their latency hides behind its tail
+          hrow_a();
           const float4 s0 = *reinterpret_cast<const float4*>(&sp[k].w[0][0]);
           const float2 s1 = *reinterpret_cast<const float2*>(&sp[k].w[2][0]);
+          hrow_b();
           const uint64_t w0 = pack2(s0.x, s0.y), w1 = pack2(s0.z, s0.w), w2 = pack2(s1.x, s1.y);
 #pragma unroll
           for (int i = 0; i < NL; ++i) {                // rotate the accumulators through the FMA operands
