@@ -112,7 +112,7 @@ __device__ __forceinline__ uint64_t ptr_add(uint64_t p, uint32_t bytes) {     //
 
 // One strip of one warp: NO x 32 output columns, all rows of the band.  Returns this lane's share of the pixel sum.
 template <int NL, int NS, int NO, bool kWindow>
-__device__ __forceinline__ float run_tile(const Tile& t, const uint32_t (&p0)[8], bool have_p0) {
+__device__ __forceinline__ float run_tile(const Tile& t) {
   Smem& sh = *t.sh;
   WarpSmem& ws = *t.ws;
   const int lane = t.lane;
@@ -174,13 +174,8 @@ __device__ __forceinline__ float run_tile(const Tile& t, const uint32_t (&p0)[8]
   if (t.down) {
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
-      if (i == 0 && have_p0) {                        // the first pair's rows were requested at kernel entry
 #pragma unroll
-        for (int k = 0; k < G; ++k) p[k][0] = p0[k];
-      } else {
-#pragma unroll
-        for (int k = 0; k < G; ++k) p[k][i] = ldg_nc_u32(gl[i] + (uint64_t)((uint32_t)min(k, nsrc - 1) * rowb));
-      }
+      for (int k = 0; k < G; ++k) p[k][i] = ldg_nc_u32(gl[i] + (uint64_t)((uint32_t)min(k, nsrc - 1) * rowb));
       gq[i] = gl[i] + (uint64_t)((uint32_t)G * rowb);
     }
   }
@@ -382,7 +377,6 @@ __global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __gri
     aa_window(y0, P.h, vscale, vsup, lo0, hi0, ctr);
     aa_window(y0 + nrows - 1, P.h, vscale, vsup, lo1, hi1, ctr);
   }
-  const uint32_t p0[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // (early request of the first rows: measured slower, the slots spill)
   // ---- pull the band's crop rows into L2 (every thread derives the row range itself) --------------------------
   if (!(a.debug_no_cluster & 2)) {
     const uint8_t* base = reinterpret_cast<const uint8_t*>(a.src + e0);
@@ -569,11 +563,11 @@ __global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __gri
     if constexpr (kStrip == 64) {
       if (two && span <= 128 && need <= 8) {
         fill(0, 2);
-        sum = run_tile<2, 2, 2, kWindow>(t, p0, false);
+        sum = run_tile<2, 2, 2, kWindow>(t);
         done = true;
       } else if (two && span <= 192 && need <= 12) {
         fill(0, 2);
-        sum = run_tile<3, 3, 2, kWindow>(t, p0, false);
+        sum = run_tile<3, 3, 2, kWindow>(t);
         done = true;
       }
     }
@@ -586,9 +580,9 @@ __global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __gri
         t.span = span;
         t.ocol = 32 * h;
         t.sync_sched = (h == 0);
-        if (span <= 64 && need <= 8) sum += run_tile<1, 2, 1, kWindow>(t, p0, false);
-        else if (span <= 128 && need <= 12) sum += run_tile<2, 3, 1, kWindow>(t, p0, false);
-        else sum += run_tile<3, 4, 1, kWindow>(t, p0, false);
+        if (span <= 64 && need <= 8) sum += run_tile<1, 2, 1, kWindow>(t);
+        else if (span <= 128 && need <= 12) sum += run_tile<2, 3, 1, kWindow>(t);
+        else sum += run_tile<3, 4, 1, kWindow>(t);
       }
     }
   }
@@ -605,11 +599,14 @@ __global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __gri
       float tot = 0.f;
       for (int i = 0; i < (nthreads >> 5); ++i) tot += sh.red[i];
       if (nocl) { for (int r = 0; r < a.nbands; ++r) sh.part[r] = tot; }
-      else for (int r = 0; r < a.nbands; ++r) st_cluster_f32(&sh.part[band], (uint32_t)r, tot);
+      else {
+        for (int r = 0; r < a.nbands; ++r) st_cluster_f32(&sh.part[band], (uint32_t)r, tot);
+        fence_acq_rel_cluster();          // the writer releases; everybody else arrives relaxed (no CTA-wide membar)
+      }
     }
     if (nocl) __syncthreads();
     else {
-      cluster_arrive_release();
+      cluster_arrive_relaxed();
       cluster_wait_acquire();
     }
     float tot = 0.f;
