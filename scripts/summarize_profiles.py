@@ -62,6 +62,16 @@ def main():
             for v, u in raw(rep):
                 f.write(f"## {v.get('Kernel Name', '')[:80]}\n\n")
                 table(f, v, u)
+    rep = os.path.join(G, f"ntxent_shard_{tag}.ncu-rep")
+    if os.path.exists(rep):
+        with open(os.path.join(OUT, f"{tag}_ntxent_shard_ncu.md"), "w") as f:
+            f.write(f"# K2/K3 ntxent_tile_kernel at the cfg3 shard shape, build of {tag}: `ncu --set full --clock-control none`\n\n"
+                    "Command: `python scripts/prof_loss_shard.py 1024 8192 128 3` (one rank's 1024 rows against the 8192 gathered rows of a\n"
+                    "global batch of 4096 on 8 GPUs, D = 128; forward = <0>, backward = <1>).  2.1 / 4.3 GFLOP per launch: the kernels\n"
+                    "last 11 / 18 us and are bound by pipeline fill and launch latency, not by the tensor pipe.\n\n")
+            for v, u in raw(rep):
+                f.write(f"## {v.get('Kernel Name', '')[:80]}\n\n")
+                table(f, v, u)
     lst = os.path.join(G, f"launches_{tag}.csv")
     if os.path.exists(lst):
         rows = [r for r in csv.reader(open(lst)) if len(r) > 10 and r[0].isdigit()]

@@ -205,3 +205,44 @@ def test_resize_jitter_flavour_matches_torchvision_chain(jitter):
     for i in range(3):
         ref = chain(A.u16_to_tv_image(imgs[i]))[0].numpy()
         _check(out[i, 0], ref, f"decathlon flavour img {i}")
+
+
+def test_full_size_properties_bench_workload():
+    """BASELINE.json cfg2 sizes (1024 slices 512x512 -> 2048 views 224x224), checked through properties that do not need
+    the (slow) oracle: a flipped view is the exact mirror image; jitter factors of 1 change nothing beyond the clamp; a
+    constant slice gives the constant (c/65535 - mean)/std; a window of the parameters' identity equals no window; and a
+    strided sample of views matches the oracle."""
+    B, H, W, crop = 1024, 512, 512, 224
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    x = torch.randint(0, 65536, (B, 1, H, W), dtype=torch.int32, device="cuda", generator=g).to(torch.uint16)
+    x[7] = 12345                                           # a constant slice
+    t = _mk(crop, out_dtype=torch.float32)
+    torch.manual_seed(2024)
+    params = t.draw_params(B, H, W)
+    vm = t.to_view_major(params)
+    base = t.apply(x, vm).clone()
+    assert torch.isfinite(base).all()
+    # (1) flip flag -> exact mirror
+    flipped = vm.copy()
+    flipped["flags"] ^= 1
+    out = t.apply(x, flipped)
+    assert torch.equal(out, base.flip(-1))
+    # (2) unit jitter factors on every view == no jitter (values are already inside [0, 1])
+    unit = vm.copy()
+    unit["flags"] |= 2
+    unit["brightness"] = 1.0
+    unit["contrast"] = 1.0
+    nojit = vm.copy()
+    nojit["flags"] &= ~np.uint32(2)
+    a, b = t.apply(x, unit).clone(), t.apply(x, nojit)
+    assert (a - b).abs().max().item() <= 2e-6
+    # (3) constant slice (views 7 and B + 7), jitter off: exact constant
+    const = (np.float32(12345) * np.float32(1.0 / 65535.0) - np.float32(MEAN)) / np.float32(STD)
+    for v in (7, B + 7):
+        assert (b[v] - float(const)).abs().max().item() <= 2e-6
+    # (4) strided sample of views against the oracle, every pixel
+    xh = x[:, 0].cpu().numpy()
+    for v in range(0, 2 * B, 257):
+        i, view = v % B, v // B
+        ref = A.apply_view(xh[i], _oracle_params(params[2 * i + view]), crop, MEAN, STD)
+        _check(base[v, 0].cpu().numpy(), ref, f"full-size view {v}")

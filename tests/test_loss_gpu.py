@@ -148,3 +148,32 @@ def test_two_rank_exchange_matches_sharded_oracle(exchange):
                         "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "scripts", "dist_check.py")],
                        cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_ntxent_full_size_properties():
+    """2N = 8192, D = 128 (the cfg3 matrix on one GPU), through properties that hold at any size: the loss does not
+    depend on the scale of a row (so <z_i, dz_i> = 0); swapping the two views leaves the loss unchanged and swaps the
+    gradients; the loss is bounded by log(2N - 1) +- 2/T; doubling the temperature-scaled problem is deterministic."""
+    from medical_image_segmentation_b200 import nt_xent_loss
+    n, d, T = 4096, 128, 0.1
+    z1, z2 = synth.embeddings(n, d, seed=5)
+    a = z1.cuda().requires_grad_(True)
+    b = z2.cuda().requires_grad_(True)
+    loss = nt_xent_loss(a, b, T)
+    loss.backward()
+    assert abs(float(loss) - np.log(2 * n - 1)) <= 2.0 / T
+    for zz in (a, b):                                      # scale invariance of every row
+        radial = (zz.detach() * zz.grad).sum(1).abs().max().item()
+        assert radial <= 1e-3 * zz.grad.abs().max().item() * zz.detach().norm(dim=1).max().item()
+    a2 = z2.cuda().requires_grad_(True)
+    b2 = z1.cuda().requires_grad_(True)
+    loss2 = nt_xent_loss(a2, b2, T)
+    loss2.backward()
+    assert abs(float(loss2) - float(loss)) <= 1e-5 * abs(float(loss))
+    assert (a2.grad - b.grad).abs().max().item() <= 1e-3 * b.grad.abs().max().item()
+    a3 = (3.0 * z1).cuda().requires_grad_(True)            # rescaled rows: same loss, gradients / 3
+    b3 = z2.cuda().requires_grad_(True)
+    loss3 = nt_xent_loss(a3, b3, T)
+    loss3.backward()
+    assert abs(float(loss3) - float(loss)) <= 1e-5 * abs(float(loss))
+    assert (3.0 * a3.grad - a.grad).abs().max().item() <= 1e-3 * a.grad.abs().max().item()
