@@ -223,6 +223,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MIS_NTXENT_GRAPH", "1")      # single-rank loss: the seven launches replayed as one CUDA graph
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
@@ -351,6 +352,8 @@ def run_b200(args):
                        "global_batch": B * world, "images_per_gpu": B, "crop": s, "proj_dim": D,
                        "l2": "inputs (512 MiB/GPU) larger than L2; no explicit flush",
                        "ntxent_operands": "tf32 (tcgen05 kind::tf32), fp32 accumulate",
+                       "ntxent_launch": ("CUDA graph replay (prep, fwd, bwd: 6 kernels + memset)"
+                                         if world == 1 and os.environ.get("MIS_NTXENT_GRAPH") == "1" else "eager"),
                        "exchange": ("none (single rank)" if world == 1 else
                                     ("NVLink peer stores fused into the producing kernels" if peer._cache else "NCCL all-gather"))},
             "aug_ms": ms_aug, "aug_views_per_s_per_gpu": 2 * B / (ms_aug * 1e-3),

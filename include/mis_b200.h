@@ -85,6 +85,10 @@ int mis_draw_two_view_params(uint8_t* rng_state, int64_t rng_state_len, int n_im
                              int H, int W, const float* blur_prob, const float* solarize_prob,
                              MisViewParams* out, int* n_done);
 
+/* Reorders the records of mis_draw_two_view_params from image-major [2*i + v] to view-major [v*n_images + i], the row
+ * order of torch.cat([view1, view2]) (byol_pytorch.py:207) that mis_aug_two_view's output planes follow.  Host only. */
+int mis_params_to_view_major(const MisViewParams* in, int n_images, MisViewParams* out);
+
 /* Single-view "Resize((s,s)) + ColorJitter(brightness, contrast)" records (the Decathlon flavour of the chain,
  * lightning_module.py:684-693): box = whole image, no flip, jitter always applied; consumes randperm(4) and one
  * uniform per non-zero magnitude per image exactly like torchvision's ColorJitter.make_params

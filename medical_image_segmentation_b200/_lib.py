@@ -31,6 +31,7 @@ EXPORTS = {
     "mis_last_error": (C.c_char_p, []),
     "mis_draw_two_view_params": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mis_params_to_view_major": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "mis_draw_resize_jitter_params": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                                 C.c_float, C.c_void_p]),
     "mis_aug_two_view": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int,

@@ -264,3 +264,14 @@ extern "C" int mis_draw_resize_jitter_params(uint8_t* rng_state, int64_t rng_sta
   store(rng_state, e);
   return MIS_OK;
 }
+
+// [2*i + v] (image-major, the draw order) -> [v*n_images + i] (view-major: the row order of cat([view1, view2]),
+// byol_pytorch.py:207).  Plain host copy of 48-byte records.
+extern "C" int mis_params_to_view_major(const MisViewParams* in, int n_images, MisViewParams* out) {
+  MIS_REQUIRE(in && out && n_images >= 0 && in != out, MIS_ERR_INVALID_ARG, "mis_params_to_view_major: bad arguments");
+  for (int i = 0; i < n_images; ++i) {
+    out[i] = in[2 * i];
+    out[n_images + i] = in[2 * i + 1];
+  }
+  return MIS_OK;
+}

@@ -17,6 +17,7 @@ reduce-scatter is needed because every rank can form both P_ij and P_ji for its 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -52,6 +53,28 @@ class _on_device:
             self.ctx.__exit__(*exc)
 
 
+class _LocalGraph:
+    """prep -> forward -> backward of one shape captured into a CUDA graph over static buffers."""
+
+    def __init__(self, z: torch.Tensor, inv_T: float, ws: torch.Tensor):
+        self.z = torch.empty_like(z)
+        self.loss = torch.empty((1,), dtype=torch.float32, device=z.device)
+        self.dz = torch.empty_like(z)
+        self.in_flight = 0
+        self.z.copy_(z)
+        CudaKernels._launch_local(self.z, inv_T, self.loss, self.dz, ws)          # warm-up outside the capture
+        torch.cuda.current_stream(z.device).synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            CudaKernels._launch_local(self.z, inv_T, self.loss, self.dz, ws)
+
+    def run(self, z: torch.Tensor):
+        self.z.copy_(z)
+        self.graph.replay()
+        self.in_flight += 1
+        return self.loss.clone(), self.dz, self
+
+
 class CudaKernels:
     """The three device steps of NT-Xent, bound to the C ABI (include/mis_b200.h)."""
 
@@ -72,29 +95,52 @@ class CudaKernels:
         return z, u, rinv
 
     _workspaces: dict = {}   # (device, rows, D) -> uint8 workspace of the single-rank fused path (stream-ordered reuse)
+    _graphs: dict = {}       # (device, rows, D, dtype, inv_T) -> captured single-rank step (MIS_NTXENT_GRAPH=1)
 
     @staticmethod
-    def fwd_bwd_local(z: torch.Tensor, inv_T: float):
-        """Single-rank loss and dL/dz in one call (mis_ntxent_fwd_bwd): 7 kernel launches, one host round trip."""
-        if not z.is_cuda:
-            raise RuntimeError("nt_xent_loss has no CPU path: embeddings must be CUDA tensors")
-        z = z.detach().contiguous()
-        rows, D = z.shape
-        key = (z.device, rows, D)
+    def _workspace(device, rows: int, D: int) -> torch.Tensor:
+        key = (device, rows, D)
         ws = CudaKernels._workspaces.get(key)
         if ws is None:
             n = int(_lib.lib.mis_ntxent_fwd_bwd_workspace_bytes(rows, D))
             if n <= 0:
                 raise ValueError(f"nt_xent_loss: unsupported shape {(rows, D)}")
-            ws = CudaKernels._workspaces[key] = torch.empty((n,), dtype=torch.uint8, device=z.device)
-        loss = torch.empty((1,), dtype=torch.float32, device=z.device)
-        dz = torch.empty_like(z)
+            ws = CudaKernels._workspaces[key] = torch.empty((n,), dtype=torch.uint8, device=device)
+        return ws
+
+    @staticmethod
+    def _launch_local(z, inv_T, loss, dz, ws):
+        rows, D = z.shape
         with _on_device(z.device):
             rc = _lib.lib.mis_ntxent_fwd_bwd(z.data_ptr(), _dt(z), rows, D, inv_T, loss.data_ptr(), dz.data_ptr(),
                                              ws.data_ptr(), ws.numel(), _stream(z))
         _lib.check(rc, "mis_ntxent_fwd_bwd")
+
+    @staticmethod
+    def fwd_bwd_local(z: torch.Tensor, inv_T: float):
+        """Single-rank loss and dL/dz in one call (mis_ntxent_fwd_bwd): 6 kernels + a memset, one host round trip.
+
+        With ``MIS_NTXENT_GRAPH=1`` the seven launches are captured once per (shape, dtype, T) into a CUDA graph over
+        static buffers and replayed (the step is launch-bound at SSL batch sizes: 6 kernels of 4-12 us).  The graph is
+        bypassed while a previous result of the same shape still waits for its backward."""
+        if not z.is_cuda:
+            raise RuntimeError("nt_xent_loss has no CPU path: embeddings must be CUDA tensors")
+        z = z.detach().contiguous()
+        rows, D = z.shape
+        ws = CudaKernels._workspace(z.device, rows, D)
+        if os.environ.get("MIS_NTXENT_GRAPH", "0") == "1":
+            key = (z.device, rows, D, z.dtype, float(inv_T))
+            g = CudaKernels._graphs.get(key)
+            if g is None:
+                g = CudaKernels._graphs[key] = _LocalGraph(z, inv_T, ws)
+            if g.in_flight == 0:
+                CudaKernels.launches += 6
+                return g.run(z)
+        loss = torch.empty((1,), dtype=torch.float32, device=z.device)
+        dz = torch.empty_like(z)
+        CudaKernels._launch_local(z, inv_T, loss, dz, ws)
         CudaKernels.launches += 6
-        return loss, dz
+        return loss, dz, None
 
     @staticmethod
     def fwd_peer(z: torch.Tensor, ex, par: int, inv_T: float):
@@ -181,9 +227,10 @@ class _NTXent(torch.autograd.Function):
         inv_T = 1.0 / float(temperature)
         if not distributed and kernels is CudaKernels and ctx.needs_input_grad[0]:
             # single rank: prep + forward + backward (grad_out = 1) in one ABI call; backward() only scales
-            loss, dz = kernels.fwd_bwd_local(z, inv_T)
+            loss, dz, holder = kernels.fwd_bwd_local(z, inv_T)
             ctx.save_for_backward(dz)
             ctx.meta = None
+            ctx.holder = holder                          # the captured graph whose static dz this result refers to
             return loss.reshape(())
         if distributed and kernels is CudaKernels:
             ex = peer.get_exchange(group, rows, z.shape[1], z.device)
@@ -208,7 +255,10 @@ class _NTXent(torch.autograd.Function):
     def backward(ctx, grad_out):
         if ctx.meta is None:
             (dz,) = ctx.saved_tensors
-            return (dz * grad_out.to(dz.dtype)), None, None, None
+            out = dz * grad_out.to(dz.dtype)
+            if ctx.holder is not None:
+                ctx.holder.in_flight -= 1
+            return out, None, None, None
         if ctx.meta[0] == "peer":
             z, rinv = ctx.saved_tensors
             _, inv_T, ex, epoch, kernels = ctx.meta

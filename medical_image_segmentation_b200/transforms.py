@@ -33,6 +33,21 @@ from . import _lib
 from ._lib import MIS_DTYPE_BF16, MIS_DTYPE_F32, VIEW_PARAMS_DTYPE
 from .params import draw_two_view_params
 
+
+class _on_device:
+    """`with torch.cuda.device(d)` costs ~10 us per entry; only switch when d is not already current."""
+
+    def __init__(self, device):
+        self.ctx = None if device.index is None or device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
 _U16_MAX = 65535.0
 
 
@@ -118,7 +133,10 @@ class FusedTwoViewTransforms:
     def to_view_major(params: np.ndarray) -> np.ndarray:
         """[2*i+v] -> [v*B+i]: row order of cat([view1, view2]) (byol_pytorch.py:207)."""
         B = params.shape[0] // 2
-        return np.ascontiguousarray(params.reshape(B, 2).T.reshape(-1))
+        src = np.ascontiguousarray(params)
+        out = np.empty_like(src)
+        _lib.check(_lib.lib.mis_params_to_view_major(src.ctypes.data, B, out.ctypes.data), "mis_params_to_view_major")
+        return out
 
     # -- device path --------------------------------------------------------------------------
     def apply(self, x: torch.Tensor, params_view_major: np.ndarray, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -146,8 +164,8 @@ class FusedTwoViewTransforms:
         dev = self._stage_params(params_view_major, x.device)
         mean_c = (C.c_float * Cc)(*mean)
         std_c = (C.c_float * Cc)(*std)
-        with torch.cuda.device(x.device):
-            stream = torch.cuda.current_stream().cuda_stream
+        with _on_device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
             rc = _lib.lib.mis_aug_two_view(
                 x.data_ptr(), B, Cc, H, W, Cc * H * W, dev.data_ptr(), n_views,
                 self.window[0], self.window[1], C.cast(mean_c, C.c_void_p), C.cast(std_c, C.c_void_p),
@@ -162,7 +180,7 @@ class FusedTwoViewTransforms:
         nbytes = params.nbytes
         if len(self._staging) < 3:
             host = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
-            self._staging.append([host, torch.empty_like(host, device=device), torch.cuda.Event()])
+            self._staging.append([host, torch.empty_like(host, device=device), torch.cuda.Event(), host.numpy()])
             slot = self._staging[-1]
         else:
             slot = self._staging[self._staging_idx % 3]
@@ -171,9 +189,13 @@ class FusedTwoViewTransforms:
             if slot[0].numel() < nbytes or slot[1].device != torch.device(device):
                 slot[0] = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
                 slot[1] = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        host, dev, ev = slot
-        host[:nbytes].numpy()[:] = params.view(np.uint8).reshape(-1)
-        dev[:nbytes].copy_(host[:nbytes], non_blocking=True)
+                slot[3] = slot[0].numpy()
+        host, dev, ev, host_np = slot
+        host_np[:nbytes] = params.view(np.uint8).reshape(-1)
+        if nbytes == host.numel():
+            dev.copy_(host, non_blocking=True)
+        else:
+            dev[:nbytes].copy_(host[:nbytes], non_blocking=True)
         ev.record(torch.cuda.current_stream(device))
         return dev
 
