@@ -1,7 +1,7 @@
 // K1 (tile variant) -- fused two-view augmentation for 16-bit slices, warp-autonomous tiles (sm_100a).
 //
 // One thread-block CLUSTER per output view plane, one CTA per band of 32 output rows, and inside the CTA one WARP per
-// 32-row x 64-column output tile.  After a short CTA prologue (vertical tap tables / schedule) a warp never
+// 32 x 32 output tile.  After a short CTA prologue (vertical tap tables / schedule) a warp never
 // synchronises with another warp until the contrast mean:
 //
 //   V pass   : lane = NL pairs of adjacent source columns (columns 2*lane + 64*i), read straight from global memory
@@ -11,19 +11,19 @@
 //              scattered with packed FFMA2 into the <= 3 output rows whose window contains it; the accumulators rotate
 //              through the FMA operands when an output row completes (a precomputed bit mask says when);
 //   H pass   : a completed intermediate row (<= 192 floats) goes to a warp-private double-buffered row in shared
-//              memory; lane = NO output columns (x0 + lane, x0 + 32 + lane), their tap weights live in REGISTERS for
-//              the whole tile, laid out against the 16-byte-aligned window start so an output costs NS 16-byte shared
-//              loads + 2*NS FFMA2; results are parked in a warp-private 32 x 64 fp32 tile (row pitch 68 floats);
+//              memory; lane = one output column, its tap weights live in REGISTERS for the whole tile, laid out
+//              against the 16-byte-aligned window start so an output costs NS 16-byte shared loads + 2*NS FFMA2;
+//              results are parked in a warp-private 32 x 32 fp32 tile (row pitch 36 floats);
 //   colour   : 1/65535 and a brightness that precedes contrast are one saturating multiply on the fly; the contrast
 //              mean over the whole view is reduced lane -> warp -> CTA -> cluster through distributed shared memory,
 //              so each view is written exactly once;
 //   store    : the tile is re-read 8 pixels per lane (conflict-free), contrast / brightness / normalise / flip,
 //              16-byte stores.
 //
-// Classes (warp-uniform, from the strip's source span): (NL, NS, NO) = (2,2,2) up to ~1.85x and (3,3,2) up to ~2.8x
-// downscaling for 64-column strips; (1,2,1), (2,3,1), (3,4,1) up to 5.5x for 32-column strips (the last strip of a
-// view, or both halves of a 64-column strip whose span is too wide).  Vertical upscaling (and any window that would
-// feed more than three output rows) uses an output-stationary V pass over the same H pass.
+// Classes (warp-uniform, from the strip's source span): (NL, NS) = (1,2) up to ~1.85x, (2,3) up to ~3x, (3,4) up to
+// 5.5x downscaling.  Vertical upscaling uses an output-stationary three-tap pass, any window that would feed more than
+// three output rows a generic output-stationary pass, both over the same H pass.  (A 64-column strip with two outputs
+// per lane executes 16 % fewer instructions but needs ~118 registers: 16 warps/SM, measured 0.79 ms vs 0.51 ms.)
 //
 // Arithmetic restated from torchvision 0.26 / ATen (see oracle/aug_oracle.py):
 //   taps   : _upsample_bilinear2d_aa (triangle filter, support = max(scale,1), weights normalised)
@@ -41,7 +41,7 @@ namespace augt {
 using namespace mis::aug;
 
 constexpr int kBand = 32;          // output rows per CTA
-constexpr int kStrip = 32;         // output columns per warp (64: two outputs per lane, measured slower: 16 warps/SM)
+constexpr int kStrip = 32;         // output columns per warp
 constexpr int kSchedCap = 200;     // source rows of one band (31*5.5 + window + group padding); <= 256 mask bits
 constexpr int kVK = 16;            // widest vertical window kept in the weight table (2*ceil(5.5)+1 = 13)
 constexpr int kRowBuf = 208;       // floats per intermediate-row buffer: 3*64 columns + slack for the aligned H reads
@@ -73,7 +73,7 @@ struct WarpSmem {
 };
 static_assert(sizeof(Smem) % 16 == 0 && sizeof(WarpSmem) % 16 == 0, "16-byte aligned shared-memory blocks");
 
-// what a warp needs to know about its strip of NO x 32 output columns
+// what a warp needs to know about its strip of 32 output columns
 struct Tile {
   float win_lo, win_scale;
   Smem* sh;
@@ -84,9 +84,8 @@ struct Tile {
   int lane, nthreads;
   int nrows;
   int span;                // source columns this warp stages, from `ca`
-  int ocol;                // first column of this strip inside the warp's output tile (0 or 32)
-  int hlo[2], hsize[2];    // per output: first source column, taps
-  float hctr[2];
+  int hlo, hsize;          // this lane's output: first source column, taps
+  float hctr;
   float hinv;
   float out_scale;         // 1/65535, times the brightness factor when brightness precedes contrast
   bool down;               // vertical downscaling and the schedule fits
@@ -110,34 +109,33 @@ __device__ __forceinline__ uint64_t ptr_add(uint64_t p, uint32_t bytes) {     //
   return r;
 }
 
-// One strip of one warp: NO x 32 output columns, all rows of the band.  Returns this lane's share of the pixel sum.
-template <int NL, int NS, int NO, bool kWindow>
+// One strip of one warp: 32 output columns, all rows of the band.  Returns this lane's share of the pixel sum.
+template <int NL, int NS, bool kWindow>
 __device__ __forceinline__ float run_tile(const Tile& t) {
   Smem& sh = *t.sh;
   WarpSmem& ws = *t.ws;
   const int lane = t.lane;
 
   // ---- this lane's horizontal taps, in registers, aligned to the 16-byte window start ------------------
-  uint64_t hw[NO][2 * NS];
-  uint32_t rbase[NO];
-#pragma unroll
-  for (int o = 0; o < NO; ++o) {
-    const int off = (t.hlo[o] - t.ca) & 3;
-    const int xa = t.hsize[o] > 0 ? ((t.hlo[o] - t.ca) & ~3) : 0;
+  uint64_t hw[2 * NS];
+  uint32_t rbase;
+  {
+    const int off = (t.hlo - t.ca) & 3;
+    const int xa = t.hsize > 0 ? ((t.hlo - t.ca) & ~3) : 0;
     float tot = 0.f;
-    for (int j = 0; j < t.hsize[o]; ++j) tot += aa_tri(j + t.hlo[o], t.hctr[o], t.hinv);
+    for (int j = 0; j < t.hsize; ++j) tot += aa_tri(j + t.hlo, t.hctr, t.hinv);
     // (one reciprocal instead of a division per tap: weights differ from w / total by at most one ulp)
     const float rtot = tot != 0.f ? __frcp_rn(tot) : 1.f;
     float w[4 * NS];
 #pragma unroll
     for (int jj = 0; jj < 4 * NS; ++jj) {
       const int j = jj - off;
-      const float wj = aa_tri(j + t.hlo[o], t.hctr[o], t.hinv);
-      w[jj] = (j >= 0 && j < t.hsize[o]) ? wj * rtot : 0.f;
+      const float wj = aa_tri(j + t.hlo, t.hctr, t.hinv);
+      w[jj] = (j >= 0 && j < t.hsize) ? wj * rtot : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 2 * NS; ++i) hw[o][i] = pack2(w[2 * i], w[2 * i + 1]);
-    rbase[o] = opaque(smem_u32(&ws.row[0][0]) + 4u * xa);          // aligned window start in buffer 0
+    for (int i = 0; i < 2 * NS; ++i) hw[i] = pack2(w[2 * i], w[2 * i + 1]);
+    rbase = opaque(smem_u32(&ws.row[0][0]) + 4u * xa);             // aligned window start in buffer 0
   }
   // zero-weight taps may read up to 15 columns behind the staged span: those must hold finite values
   if (lane < 24) {
@@ -168,7 +166,7 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
 
   // G register slots per lane hold the next G source rows of the input-stationary stream; issued before the
   // schedule barrier so their latency overlaps it
-  constexpr int G = (NL == 1 || (NL == 2 && NO == 2)) ? 8 : 4;
+  constexpr int G = NL == 1 ? 8 : 4;
   uint32_t p[G][NL];
   uint64_t gq[NL];                                  // next row to fetch, this lane's columns
   if (t.down) {
@@ -189,12 +187,12 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
   // running shared-memory cursors (32-bit shared addresses): the intermediate row alternates between two buffers,
   // the output tile advances one row per completed output row
   uint32_t sel = 0;                                                    // 0 / kRowBuf * 4: buffer in use
-  const uint32_t op0 = smem_u32(ws.o) + 4u * (t.ocol + lane);
+  const uint32_t op0 = smem_u32(ws.o) + 4u * lane;
   uint32_t op = opaque(op0);
 
   // the oldest open output row is complete in A: H pass over the intermediate row (first half: park the row, read the
   // windows, accumulate; second half: scale, clamp, sum, park the results in the tile)
-  uint64_t hacc[NO];
+  uint64_t hacc;
   auto hrow_a = [&]() {
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
@@ -203,29 +201,23 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
       sts64(wb[i] + sel, v0, v1);
     }
     __syncwarp();
+    uint64_t acc = 0ull;
 #pragma unroll
-    for (int o = 0; o < NO; ++o) {
-      uint64_t acc = 0ull;
-#pragma unroll
-      for (int j = 0; j < NS; ++j) {
-        const float4 v = lds128(rbase[o] + sel + 16u * j);
-        acc = ffma2(pack2(v.x, v.y), hw[o][2 * j], acc);
-        acc = ffma2(pack2(v.z, v.w), hw[o][2 * j + 1], acc);
-      }
-      hacc[o] = acc;
+    for (int j = 0; j < NS; ++j) {
+      const float4 v = lds128(rbase + sel + 16u * j);
+      acc = ffma2(pack2(v.x, v.y), hw[2 * j], acc);
+      acc = ffma2(pack2(v.z, v.w), hw[2 * j + 1], acc);
     }
+    hacc = acc;
   };
   auto hrow_b = [&]() {
-#pragma unroll
-    for (int o = 0; o < NO; ++o) {
-      float lo, hi;
-      unpack2(hacc[o], lo, hi);
-      // 1/65535 (and a brightness factor that precedes contrast) in one saturating multiply; without brightness the
-      // clamp only trims the one-ulp overshoot a normalised filter can produce
-      const float val = __saturatef((lo + hi) * t.out_scale);
-      sum += val;                                   // columns beyond the view's last column carry zero weights
-      sts32(op + 128u * o, val);
-    }
+    float lo, hi;
+    unpack2(hacc, lo, hi);
+    // 1/65535 (and a brightness factor that precedes contrast) in one saturating multiply; without brightness the
+    // clamp only trims the one-ulp overshoot a normalised filter can produce
+    const float val = __saturatef((lo + hi) * t.out_scale);
+    sum += val;                                   // lanes beyond the view's last column carry zero weights
+    sts32(op, val);
     op += kOPitch * 4;
     sel ^= (uint32_t)(kRowBuf * 4);
   };
@@ -343,7 +335,7 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
 }
 
 template <bool kWindow>
-__global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __grid_constant__ TileArgs a) {
+__global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   Smem& sh = *reinterpret_cast<Smem*>(smem);
   const int tid = threadIdx.x;
@@ -412,20 +404,17 @@ __global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __gri
   const bool has_post = jitter && pos_b > pos_c;
 
   const int x0 = warp * kStrip;
-  int wlo[2], wsize[2];
-  float wctr[2];
-#pragma unroll
-  for (int o = 0; o < 2; ++o) {
-    const int x = x0 + 32 * o + lane;
+  {
+    const int x = x0 + lane;
     int lo = 0, hi = 0;
     float ctr = 0.f;
-    if (o < kStrip / 32 && x < s) aa_window(x, P.w, hscale, hsup, lo, hi, ctr);
+    if (x < s) aa_window(x, P.w, hscale, hsup, lo, hi, ctr);
     const int kcap = 2 * (int)ceilf(hsup) + 1;
     int size = hi - lo;
     size = size < 0 ? 0 : (size > kcap ? kcap : size);
-    wlo[o] = lo;
-    wsize[o] = (o < kStrip / 32 && x < s) ? size : 0;
-    wctr[o] = ctr;
+    t.hlo = lo;
+    t.hsize = (x < s) ? size : 0;
+    t.hctr = ctr;
   }
   // ---- vertical tap tables of the band: warp 0, one lane per output row.  First thing after the parameters: every
   // other warp needs them at the first barrier and has the prefetch and its strip windows to do meanwhile ---------
@@ -473,20 +462,6 @@ __global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __gri
     size = __reduce_max_sync(0xffffffffu, size);
     if (lane == 0) sh.kv_max = size;
   }
-
-  // staged span of a strip of outputs [o_first, o_last]: from the 4-byte aligned column at or before the first window
-  auto strip = [&](int o_first, int o_last, int& ca, int& span, int& need) {
-    const int c_lo = __shfl_sync(0xffffffffu, wlo[o_first], 0);
-    ca = c_lo - (int)((e0 + c_lo) & 1);
-    int hi = 0, nd = 0;
-    for (int o = o_first; o <= o_last; ++o) {
-      hi = max(hi, wsize[o] > 0 ? wlo[o] + wsize[o] : 0);
-      nd = max(nd, wsize[o] > 0 ? ((wlo[o] - ca) & 3) + wsize[o] : 0);
-    }
-    span = __reduce_max_sync(0xffffffffu, hi) - ca;
-    need = __reduce_max_sync(0xffffffffu, nd);
-  };
-  const bool two = kStrip == 64 && x0 + 32 < s;      // this warp's strip has a second 32-column half
 
   __syncthreads();                                  // tables of the band are complete
   const int r_lo = sh.vinfo[0].x;
@@ -541,50 +516,18 @@ __global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __gri
     }
   }
 
-  // ---- the tile: class dispatch (the schedule barrier sits inside, behind the per-warp set-up) ---------------
-  float sum = 0.f;
+  // ---- the tile: staged span (from the 4-byte aligned column at or before the strip's first window), class dispatch
+  // (the schedule barrier sits inside, behind the per-warp set-up) ------------------------------------------------
+  float sum;
   {
-    int ca, span, need;
-    strip(0, two ? 1 : 0, ca, span, need);
-    auto fill = [&](int o_first, int n) {
-      for (int o = 0; o < 2; ++o) {
-        const int src = o_first + o;
-        const bool on = o < n;
-        t.hlo[o] = on ? wlo[src < 2 ? src : 1] : 0;
-        t.hsize[o] = on ? wsize[src < 2 ? src : 1] : 0;
-        t.hctr[o] = on ? wctr[src < 2 ? src : 1] : 0.f;
-      }
-    };
-    t.ca = ca;
-    t.span = span;
-    t.ocol = 0;
+    const int c_lo = __shfl_sync(0xffffffffu, t.hlo, 0);
+    t.ca = c_lo - (int)((e0 + c_lo) & 1);
+    t.span = __reduce_max_sync(0xffffffffu, t.hsize > 0 ? t.hlo + t.hsize : 0) - t.ca;
+    const int need = __reduce_max_sync(0xffffffffu, t.hsize > 0 ? ((t.hlo - t.ca) & 3) + t.hsize : 0);
     t.sync_sched = true;
-    bool done = false;
-    if constexpr (kStrip == 64) {
-      if (two && span <= 128 && need <= 8) {
-        fill(0, 2);
-        sum = run_tile<2, 2, 2, kWindow>(t);
-        done = true;
-      } else if (two && span <= 192 && need <= 12) {
-        fill(0, 2);
-        sum = run_tile<3, 3, 2, kWindow>(t);
-        done = true;
-      }
-    }
-    if (!done) {
-      // 32-column strips: the only half of the view's last strip, or both halves one after the other
-      for (int h = 0; h < (two ? 2 : 1); ++h) {
-        strip(h, h, ca, span, need);
-        fill(h, 1);
-        t.ca = ca;
-        t.span = span;
-        t.ocol = 32 * h;
-        t.sync_sched = (h == 0);
-        if (span <= 64 && need <= 8) sum += run_tile<1, 2, 1, kWindow>(t);
-        else if (span <= 128 && need <= 12) sum += run_tile<2, 3, 1, kWindow>(t);
-        else sum += run_tile<3, 4, 1, kWindow>(t);
-      }
-    }
+    if (t.span <= 64 && need <= 8) sum = run_tile<1, 2, kWindow>(t);
+    else if (t.span <= 128 && need <= 12) sum = run_tile<2, 3, kWindow>(t);
+    else sum = run_tile<3, 4, kWindow>(t);
   }
 
   // ================================ contrast mean over the view ===========================================
@@ -621,35 +564,32 @@ __global__ void __maxnreg__(kStrip == 64 ? 128 : 64) aug_tile_kernel(const __gri
   const float mean = a.mean[chan], inv_std = a.inv_std[chan];
   const bool flip = (P.flags & MIS_VIEW_FLIP) != 0;
   const float pb = P.brightness;
-#pragma unroll 1
-  for (int h = 0; h < (two ? 2 : 1); ++h) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int id = it * 32 + lane;
-      const int row = id >> 2, xs = x0 + 32 * h + 8 * (id & 3);
-      if (row < nrows && xs < s) {
-        const float* src = ws.o + row * kOPitch + 32 * h + 8 * (id & 3);
-        const float4 v0 = *reinterpret_cast<const float4*>(src);
-        const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
-        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        if (jitter) {
+  for (int it = 0; it < 4; ++it) {
+    const int id = it * 32 + lane;
+    const int row = id >> 2, xs = x0 + 8 * (id & 3);
+    if (row < nrows && xs < s) {
+      const float* src = ws.o + row * kOPitch + 8 * (id & 3);
+      const float4 v0 = *reinterpret_cast<const float4*>(src);
+      const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+      float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      if (jitter) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __saturatef(fmaf(v[i], cf, cadd));
-          if (has_post) {
+        for (int i = 0; i < 8; ++i) v[i] = __saturatef(fmaf(v[i], cf, cadd));
+        if (has_post) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __saturatef(v[i] * pb);
-          }
+          for (int i = 0; i < 8; ++i) v[i] = __saturatef(v[i] * pb);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * inv_std;
-        store_run<8>(v, a.out, ((size_t)plane * s + (y0 + row)) * s, xs, s, flip, a.out_f32 != 0);
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * inv_std;
+      store_run<8>(v, a.out, ((size_t)plane * s + (y0 + row)) * s, xs, s, flip, a.out_f32 != 0);
     }
   }
 }
 
 bool tile_supported(int C, int H, int W, int64_t img_stride, int s) {
-  // class (3,4,1) covers 5.5x downscaling per axis: 31*5.5 + 2*5.5 + 2 <= 192 staged columns, 3 + 13 <= 16 aligned
+  // class (3,4) covers 5.5x downscaling per axis: 31*5.5 + 2*5.5 + 2 <= 192 staged columns, 3 + 13 <= 16 aligned
   // taps, 31*5.5 + 13 + 8 <= kSchedCap schedule rows
   return C == 1 && s >= 8 && s <= kStrip * kMaxWarps && (W & 1) == 0 && (img_stride & 1) == 0 && 2 * W <= 11 * s &&
          2 * H <= 11 * s;
