@@ -344,6 +344,7 @@ def run_b200(args):
                          f"{r['cores']} worker processes + NT-Xent fwd+bwd fp32 CPU ({r['ntxent_ms']:.1f} ms)",
                "ntxent_fwd_bwd_ms": r["ntxent_ms"]}
 
+    peer.check_timeouts()                                # no consumer ever gave up waiting for a peer's flag
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,

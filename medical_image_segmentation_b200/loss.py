@@ -238,7 +238,8 @@ class _NTXent(torch.autograd.Function):
                 # NVLink peer stores: prep writes the rows into every rank's matrix, the forward its lse rows
                 ex.epoch += 1
                 par = ex.epoch & 1
-                ex.in_flight[par] += 1
+                if ctx.needs_input_grad[0]:
+                    ex.in_flight[par] += 1                # this parity's buffers are read again by the backward
                 z, rinv, loss = kernels.fwd_peer(z, ex, par, inv_T)
                 ctx.save_for_backward(z, rinv)
                 ctx.meta = ("peer", inv_T, ex, ex.epoch, kernels)

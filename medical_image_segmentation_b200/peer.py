@@ -93,3 +93,11 @@ def get_exchange(group, rows: int, D: int, device: torch.device):
             return None
         _cache[key] = ex
     return ex
+
+
+def check_timeouts() -> None:
+    """Raise if any consumer gave up waiting for a peer's flag (synchronises the device; call it off the hot path)."""
+    for ex in _cache.values():
+        if ex.timed_out():
+            raise RuntimeError(f"NT-Xent peer exchange: rank {ex.rank} timed out waiting for a peer's flag "
+                               "(a rank died or fell more than ~2 s behind); results of that step are invalid")

@@ -30,10 +30,11 @@ for (B, D, T) in ((64, 64, 0.1), (256, 128, 0.1), (128, 256, 0.2), (256, 128, 0.
     print(f"rank {rank}/{world} B={B} D={D} T={T}: loss rel {lrel:.2e} grad fro rel {fro:.2e} {'OK' if good else 'FAIL'}", flush=True)
 from medical_image_segmentation_b200 import peer
 print(f"rank {rank}: exchange mode {peer.mode()}, peer exchanges in use: {len(peer._cache)}, disabled: {peer._disabled_reason}", flush=True)
-for ex in peer._cache.values():
-    if ex.timed_out():
-        ok = False
-        print(f"rank {rank}: peer wait TIMED OUT", flush=True)
+try:
+    peer.check_timeouts()
+except RuntimeError as e:
+    ok = False
+    print(f"rank {rank}: {e}", flush=True)
 flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
