@@ -125,6 +125,15 @@ int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H, int W, int
                      const float* mean, const float* std, void* out, int s, int out_dtype,
                      int use_tma, void* stream);
 
+/* Host -> device staging for mis_aug_two_view: copies only the full-width rows [lo, hi) of each slice that the slice's
+ * records read, into the same offsets of `dst_dev` (the other rows keep whatever they held and are never read by K1
+ * for this table).  Neighbouring ranges whose gap is at most `min_gap_bytes` are merged into one cudaMemcpyAsync
+ * (a copy costs ~4 us of set-up = ~200 KB of PCIe time on B200; 0 = one copy per slice).  src_host should be pinned.
+ * params_host: HOST copy of the table (any order).  bytes_copied (may be NULL): bytes put on the wire. */
+int mis_h2d_needed_rows(const uint16_t* src_host, uint16_t* dst_dev, int n_images, int C, int H, int W,
+                        int64_t img_stride, const MisViewParams* params_host, int n_views,
+                        int64_t min_gap_bytes, void* stream, int64_t* bytes_copied);
+
 /* Profiling aid: when `buf` is a device array of [grid][8] int64, thread 0 of every K1 CTA writes clock64()
  * stamps at its phase boundaries (0 start, 1 tables, 2 V pass, 3 V barrier, 4 H pass, 5 colour, 6 end).
  * NULL (the default) disables it.  Not used by the product path. */

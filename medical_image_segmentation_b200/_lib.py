@@ -37,6 +37,8 @@ EXPORTS = {
     "mis_aug_two_view": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int,
                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p]),
+    "mis_h2d_needed_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p,
+                                      C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "mis_debug_set_stamp_buffer": (None, [C.c_void_p]),
     "mis_aug_algorithmic_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mis_ntxent_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),

@@ -89,6 +89,9 @@ class FusedTwoViewTransforms:
         self.prefetch_params = bool(prefetch_params)
         self._pool = None                     # one helper thread drawing the NEXT batch's parameters
         self._pending = None                  # ((B, H, W), future)
+        self._x_stage: torch.Tensor | None = None      # device staging buffer of host batches
+        self._x_host_keepalive = None
+        self.last_h2d_bytes = 0
         self.views_buffer: torch.Tensor | None = None
         self.last_params: np.ndarray | None = None
         self.launches = 0
@@ -199,6 +202,31 @@ class FusedTwoViewTransforms:
         ev.record(torch.cuda.current_stream(device))
         return dev
 
+    def stage_needed_rows(self, x_host: torch.Tensor, params: np.ndarray, device=None,
+                          min_gap_bytes: int = 256 << 10) -> torch.Tensor:
+        """Host batch -> device, copying only the rows the records read (mis_h2d_needed_rows); ranges closer than
+        ``min_gap_bytes`` are merged into one copy (a copy costs ~200 KB of PCIe time to set up).  Returns the full-size
+        device buffer K1 reads; rows no record touches are stale.  ``self.last_h2d_bytes`` = bytes put on the wire."""
+        if x_host.dtype != torch.uint16 or x_host.is_cuda or x_host.dim() != 4:
+            raise TypeError("stage_needed_rows expects a host torch.uint16 [B,C,H,W] batch")
+        x_host = x_host.contiguous()
+        if not x_host.is_pinned():
+            x_host = x_host.pin_memory()
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        B, Cc, H, W = x_host.shape
+        if self._x_stage is None or self._x_stage.shape != x_host.shape or self._x_stage.device != device:
+            self._x_stage = torch.empty(x_host.shape, dtype=torch.uint16, device=device)
+        p = np.ascontiguousarray(params)
+        nbytes = C.c_int64(0)
+        with _on_device(device):
+            rc = _lib.lib.mis_h2d_needed_rows(x_host.data_ptr(), self._x_stage.data_ptr(), B, Cc, H, W, Cc * H * W,
+                                              p.ctypes.data, p.shape[0], int(min_gap_bytes),
+                                              C.c_void_p(torch.cuda.current_stream(device).cuda_stream), C.byref(nbytes))
+        _lib.check(rc, "mis_h2d_needed_rows")
+        self._x_host_keepalive = x_host                 # the async copies read it until the stream gets there
+        self.last_h2d_bytes = int(nbytes.value)
+        return self._x_stage
+
     def __call__(self, x) -> list[torch.Tensor]:
         if isinstance(x, np.ndarray):
             x = torch.from_numpy(x)
@@ -206,13 +234,13 @@ class FusedTwoViewTransforms:
             x = x[None, None]
         elif x.dim() == 3:
             x = x[:, None]
-        if not x.is_cuda:
-            if not torch.cuda.is_available():
-                raise RuntimeError("FusedTwoViewTransforms has no CPU path: a CUDA device is required")
-            x = (x if x.is_pinned() else x.pin_memory()).cuda(non_blocking=True)
+        if not x.is_cuda and not torch.cuda.is_available():
+            raise RuntimeError("FusedTwoViewTransforms has no CPU path: a CUDA device is required")
         B, _, H, W = x.shape
         params = self.next_params(B, H, W)
         self.last_params = params
+        if not x.is_cuda:
+            x = self.stage_needed_rows(x, params)       # host batch: only the rows the crops read cross PCIe
         out = self.apply(x, self.to_view_major(params))
         self.views_buffer = out
         return [out[:B], out[B:]]

@@ -246,3 +246,33 @@ def test_full_size_properties_bench_workload():
         i, view = v % B, v // B
         ref = A.apply_view(xh[i], _oracle_params(params[2 * i + view]), crop, MEAN, STD)
         _check(base[v, 0].cpu().numpy(), ref, f"full-size view {v}")
+
+
+def test_host_batch_stages_only_the_rows_the_crops_read():
+    """A host batch goes through mis_h2d_needed_rows (per slice one copy of the rows its two crops read): same views as
+    the device-resident batch, fewer bytes on the wire, and a poisoned staging buffer shows no stale row is ever read."""
+    imgs = synth.batch_512(12, seed=17, H=320, W=288)
+    xh = torch.from_numpy(imgs)[:, None].contiguous().pin_memory()
+    ta = _mk(96, out_dtype=torch.float32)
+    tb = _mk(96, out_dtype=torch.float32)
+    tb._x_stage = torch.full((12, 1, 320, 288), 65535, dtype=torch.int32).to(torch.uint16).cuda()   # poison
+    torch.manual_seed(404)
+    ta(xh.cuda())
+    torch.manual_seed(404)
+    rec = tb.draw_params(12, 320, 288)
+    xs = tb.stage_needed_rows(xh, rec, min_gap_bytes=0)             # one copy per slice: exactly the union of its crops' rows
+    tb.apply(xs, tb.to_view_major(rec))
+    out_b = tb.apply(xs, tb.to_view_major(rec)).clone()
+    assert torch.equal(ta.views_buffer, out_b)
+    full = xh.numel() * 2
+    want = 0
+    for i in range(12):
+        lo = min(int(rec[2 * i]["top"]), int(rec[2 * i + 1]["top"]))
+        hi = max(int(rec[2 * i]["top"] + rec[2 * i]["h"]), int(rec[2 * i + 1]["top"] + rec[2 * i + 1]["h"]))
+        want += (hi - lo) * 288 * 2
+    assert tb.last_h2d_bytes == want and 0 < want < full
+    # default gap threshold: neighbouring ranges merge, the views do not change, never more than the whole batch
+    torch.manual_seed(404)
+    tb(xh)
+    assert torch.equal(ta.views_buffer, tb.views_buffer)
+    assert want <= tb.last_h2d_bytes <= full
