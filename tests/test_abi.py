@@ -106,3 +106,22 @@ def test_peer_exchange_argument_errors_and_mode_switch(monkeypatch):
     monkeypatch.delenv("MIS_NTXENT_EXCHANGE")
     assert peer.mode() == "auto"
     assert peer._FLAG_BYTES >= 4 * (2 * peer.MAX_PEERS + 3)       # flags [2][8] + 2 counters + timeout word (csrc/ntxent.cu)
+
+
+def test_h2d_staging_argument_errors_without_gpu():
+    """mis_h2d_needed_rows validates sizes and every record before the first copy is enqueued."""
+    from medical_image_segmentation_b200 import _lib
+    lib = _lib.lib
+    buf = np.zeros(2 * 8 * 8, np.uint16)
+    rec = np.zeros(2, _lib.VIEW_PARAMS_DTYPE)
+    rec["img"] = (0, 1)
+    rec["h"] = rec["w"] = 4
+    p, r = buf.ctypes.data, rec.ctypes.data
+    assert lib.mis_h2d_needed_rows(None, p, 2, 1, 8, 8, 64, r, 2, 0, None, None) == _lib.MIS_ERR_INVALID_ARG
+    assert lib.mis_h2d_needed_rows(p, p, 2, 1, 8, 8, 32, r, 2, 0, None, None) == _lib.MIS_ERR_INVALID_ARG        # stride < C*H*W
+    rec["top"] = (0, 6)                                                                                          # rows [6, 10) of 8
+    assert lib.mis_h2d_needed_rows(p, p, 2, 1, 8, 8, 64, r, 2, 0, None, None) == _lib.MIS_ERR_INVALID_ARG
+    assert b"record 1" in lib.mis_last_error()
+    rec["top"] = 0
+    rec["img"] = (0, 2)                                                                                          # slice 2 of 2
+    assert lib.mis_h2d_needed_rows(p, p, 2, 1, 8, 8, 64, r, 2, 0, None, None) == _lib.MIS_ERR_INVALID_ARG
