@@ -122,19 +122,19 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
   {
     const int off = (t.hlo - t.ca) & 3;
     const int xa = t.hsize > 0 ? ((t.hlo - t.ca) & ~3) : 0;
-    float tot = 0.f;
-    for (int j = 0; j < t.hsize; ++j) tot += aa_tri(j + t.hlo, t.hctr, t.hinv);
-    // (one reciprocal instead of a division per tap: weights differ from w / total by at most one ulp)
-    const float rtot = tot != 0.f ? __frcp_rn(tot) : 1.f;
+    // taps at their aligned positions (zero outside the window); their sum in ascending order is the reference's total
     float w[4 * NS];
+    float tot = 0.f;
 #pragma unroll
     for (int jj = 0; jj < 4 * NS; ++jj) {
       const int j = jj - off;
-      const float wj = aa_tri(j + t.hlo, t.hctr, t.hinv);
-      w[jj] = (j >= 0 && j < t.hsize) ? wj * rtot : 0.f;
+      w[jj] = (j >= 0 && j < t.hsize) ? aa_tri(j + t.hlo, t.hctr, t.hinv) : 0.f;
+      tot += w[jj];
     }
+    // (one reciprocal instead of a division per tap: weights differ from w / total by at most one ulp)
+    const float rtot = tot != 0.f ? __frcp_rn(tot) : 1.f;
 #pragma unroll
-    for (int i = 0; i < 2 * NS; ++i) hw[i] = pack2(w[2 * i], w[2 * i + 1]);
+    for (int i = 0; i < 2 * NS; ++i) hw[i] = pack2(w[2 * i] * rtot, w[2 * i + 1] * rtot);
     rbase = opaque(smem_u32(&ws.row[0][0]) + 4u * xa);             // aligned window start in buffer 0
   }
   // zero-weight taps may read up to 15 columns behind the staged span: those must hold finite values
@@ -343,9 +343,9 @@ __global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs
   const int lane = tid & 31;
   const int nthreads = blockDim.x;
   WarpSmem& ws = *reinterpret_cast<WarpSmem*>(smem + sizeof(Smem) + (size_t)warp * sizeof(WarpSmem));
-  const int band = blockIdx.x % a.nbands;       // == rank in cluster
-  const int plane = blockIdx.x / a.nbands;      // view * C + c
-  const int view = plane / a.C;
+  const int band = blockIdx.x;                  // grid = (bands, planes): band == rank in cluster, no integer divisions
+  const int plane = blockIdx.y;                 // view * C + c
+  const int view = a.C == 1 ? plane : plane / a.C;
   const int chan = plane - view * a.C;
   const int s = a.s;
 
@@ -600,19 +600,28 @@ int launch_tile(const TileArgs& a, int n_views, bool window, cudaStream_t stream
   const size_t smem = sizeof(Smem) + (size_t)nxw * sizeof(WarpSmem);
   auto* fn = window ? &aug_tile_kernel<true> : &aug_tile_kernel<false>;
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(a.nbands * n_views * a.C));
-  cfg.blockDim = dim3((unsigned)(32 * nxw));
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (a.debug_no_cluster & 1) ? 1u : (unsigned)a.nbands;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  MIS_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, a));
+  // grid = (bands, planes): gridDim.y holds at most 65535 planes, larger batches go out in several launches
+  const int max_views = 65535 / a.C;
+  const size_t esize = a.out_f32 ? 4 : 2;
+  for (int v0 = 0; v0 < n_views; v0 += max_views) {
+    const int nv = n_views - v0 < max_views ? n_views - v0 : max_views;
+    TileArgs b = a;
+    b.params = a.params + v0;
+    b.out = static_cast<uint8_t*>(a.out) + (size_t)v0 * a.C * a.s * a.s * esize;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)a.nbands, (unsigned)(nv * a.C));
+    cfg.blockDim = dim3((unsigned)(32 * nxw));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (a.debug_no_cluster & 1) ? 1u : (unsigned)a.nbands;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MIS_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, b));
+  }
   return MIS_OK;
 }
 
