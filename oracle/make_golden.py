@@ -15,7 +15,7 @@ aug_small.npz   6 synthetic uint16 slices 96x128 (stored), crops 32 and 48: full
 aug_real.npz    128x128 windows cut from the 5 real 16-bit slices shipped under
                 data/visualizations/example_images/, crop 64: full outputs + params.
 aug_512.npz     4 synthetic 512x512 slices (regenerated from seed by tests/synth.py),
-                crops 224 and 96: params, strided output samples out[::7, ::7], sums.
+                crops 224, 96 and 256: params, strided output samples out[::7, ::7], sums.
 params_stream.npz  crop boxes / flags for 400 images (800 views) at 512x512, 256x768 and
                 448x448 + the generator state after, pinning the RNG replay.
 byol_loss.npz   inputs and outputs of the reference BYOL loss.
@@ -152,7 +152,7 @@ def main():
     big = synth.batch_512(4)
     seeds = 1000 + np.arange(4)
     blob = dict(seeds=seeds, mean=MEAN, std=STD, stride=7)
-    for crop in (224, 96):
+    for crop in (224, 96, 256):
         out, (ints, order, fac) = run_reference(Ref, big, crop, seeds)
         blob[f"sample_{crop}"] = out[:, :, ::7, ::7].copy()
         blob[f"sum_{crop}"] = out.astype(np.float64).sum(axis=(2, 3))

@@ -67,7 +67,7 @@ def test_matches_reference_golden_real_slices():
         _check(v2[0, 0].cpu().numpy(), g["out_64"][k, 1], f"real {k} v2")
 
 
-@pytest.mark.parametrize("crop", [224, 96])
+@pytest.mark.parametrize("crop", [224, 96, 256])
 def test_matches_reference_golden_512(crop):
     """Full-size slices: strided samples + sums of the reference's outputs (goldens), batched call."""
     g = np.load(os.path.join(GOLD, "aug_512.npz"))

@@ -56,7 +56,7 @@ def test_restatement_matches_reference_real_slices():
             assert np.abs(views[v] - g["out_64"][k, v]).max() < 5e-6
 
 
-@pytest.mark.parametrize("crop", [224, 96])
+@pytest.mark.parametrize("crop", [224, 96, 256])
 def test_restatement_matches_reference_512(crop):
     g = np.load(os.path.join(GOLD, "aug_512.npz"))
     mean, std = float(g["mean"]), float(g["std"])
