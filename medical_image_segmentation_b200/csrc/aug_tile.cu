@@ -89,7 +89,6 @@ struct Tile {
   float hinv;
   float out_scale;         // 1/65535, times the brightness factor when brightness precedes contrast
   bool down;               // vertical downscaling and the schedule fits
-  bool sync_sched;         // this call waits for the schedule barrier
 };
 
 template <bool kWindow>
@@ -177,7 +176,7 @@ __device__ __forceinline__ float run_tile(const Tile& t) {
       gq[i] = gl[i] + (uint64_t)((uint32_t)G * rowb);
     }
   }
-  if (t.sync_sched) bar_sync(1, t.nthreads);        // the schedule (built by the CTA's first threads) is complete
+  bar_sync(1, t.nthreads);                                  // the schedule (built by the CTA's first threads) is complete
   const bool use_is = t.down && sh.m_max <= 3;
 
   uint64_t A[NL], B[NL], Cc[NL];    // the three open output rows of this lane's column pair(s)
@@ -524,7 +523,6 @@ __global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs
     t.ca = c_lo - (int)((e0 + c_lo) & 1);
     t.span = __reduce_max_sync(0xffffffffu, t.hsize > 0 ? t.hlo + t.hsize : 0) - t.ca;
     const int need = __reduce_max_sync(0xffffffffu, t.hsize > 0 ? ((t.hlo - t.ca) & 3) + t.hsize : 0);
-    t.sync_sched = true;
     if (t.span <= 64 && need <= 8) sum = run_tile<1, 2, kWindow>(t);
     else if (t.span <= 128 && need <= 12) sum = run_tile<2, 3, kWindow>(t);
     else sum = run_tile<3, 4, kWindow>(t);
