@@ -115,10 +115,15 @@ int mis_draw_resize_jitter_params(uint8_t* rng_state, int64_t rng_state_len, int
  *   mean,std   host float[C]
  *   out        [n_views, C, s, s] in out_dtype (MIS_DTYPE_BF16 or MIS_DTYPE_F32), NCHW
  *   s          output crop size, 8 <= s <= 256
- *   use_tma    1: a producer warp stages crop rows with 2-D TMA tensor-map boxes (cp.async.bulk.tensor) into a
- *                 shared-memory ring (needs W % 8 == 0 and dense images, otherwise falls back to 0)
- *              0: every thread stages its own columns with cp.async into a private ring, two 16-row sub-bands
- *                 per band (fastest measured on B200: 3 CTAs/SM)
+ *   use_tma    kernel variant (the name is historical):
+ *              0: warp-tile kernel (csrc/aug_tile.cu; default, fastest measured on B200: one warp per 32x32 output
+ *                 tile, rows straight from global memory through refill-on-consume register slots, taps in
+ *                 registers) for C == 1, s <= 256 and at most 5.5x downscaling of the whole slice per axis; other
+ *                 shapes fall through to variant 2
+ *              1: band kernel, a producer warp stages crop rows with 2-D TMA tensor-map boxes (cp.async.bulk.tensor)
+ *                 into a shared-memory ring (needs W % 8 == 0 and dense images, otherwise variant 2)
+ *              2: band kernel, every thread stages its own columns with cp.async into a private ring, two 16-row
+ *                 sub-bands per band
  * ------------------------------------------------------------------------------------------ */
 int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H, int W, int64_t img_stride,
                      const MisViewParams* params, int n_views, float win_lo, float win_hi,
