@@ -139,11 +139,6 @@ int mis_h2d_needed_rows(const uint16_t* src_host, uint16_t* dst_dev, int n_image
                         int64_t img_stride, const MisViewParams* params_host, int n_views,
                         int64_t min_gap_bytes, void* stream, int64_t* bytes_copied);
 
-/* Profiling aid: when `buf` is a device array of [grid][8] int64, thread 0 of every K1 CTA writes clock64()
- * stamps at its phase boundaries (0 start, 1 tables, 2 V pass, 3 V barrier, 4 H pass, 5 colour, 6 end).
- * NULL (the default) disables it.  Not used by the product path. */
-void mis_debug_set_stamp_buffer(void* buf);
-
 /* Algorithmic bytes K1 moves for a host copy of the params table (crop window read + output
  * write).  Pure host arithmetic. */
 int64_t mis_aug_algorithmic_bytes(const MisViewParams* params_host, int n_views, int C, int s,

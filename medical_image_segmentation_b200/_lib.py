@@ -39,7 +39,6 @@ EXPORTS = {
                                    C.c_int, C.c_void_p]),
     "mis_h2d_needed_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p,
                                       C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
-    "mis_debug_set_stamp_buffer": (None, [C.c_void_p]),
     "mis_aug_algorithmic_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mis_ntxent_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "mis_ntxent_prep": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

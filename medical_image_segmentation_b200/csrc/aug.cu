@@ -33,6 +33,7 @@
 #include <mutex>
 
 #include "aug_math.cuh"
+#include "aug_strip.cuh"
 #include "aug_tile.cuh"
 #include "common.cuh"
 
@@ -622,7 +623,11 @@ aug_kernel(const __grid_constant__ CUtensorMap map64, const __grid_constant__ CU
   const int s = a.s;
 
   cluster_arrive_relaxed();   // phase 1: "every CTA of the cluster is running" (waited before DSMEM use)
+#ifdef MIS_DEBUG
 #define MIS_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[(size_t)blockIdx.x * 8 + (i)] = clock64(); } while (0)
+#else
+#define MIS_STAMP(i) do { } while (0)
+#endif
   MIS_STAMP(0);
 
   const MisViewParams P = a.params[view];
@@ -1033,9 +1038,11 @@ static int launch(const Args& a, const CUtensorMap* maps, int grid, size_t smem,
 
 using namespace mis;
 
+#ifdef MIS_DEBUG
+// profiling aid of -DMIS_DEBUG builds only (not part of the ABI): device buffer of [grid][8] int64 clock stamps, or NULL
 static long long* g_dbg = nullptr;
-// profiling aid (not part of the public ABI contract): device buffer of [grid][8] int64 clock stamps, or NULL
 extern "C" void mis_debug_set_stamp_buffer(void* p) { g_dbg = static_cast<long long*>(p); }
+#endif
 
 extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H, int W, int64_t img_stride,
                                 const MisViewParams* params, int n_views, float win_lo, float win_hi,
@@ -1061,8 +1068,29 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
     MIS_REQUIRE(std[c] != 0.f, MIS_ERR_INVALID_ARG, "mis_aug_two_view: std[%d] == 0", c);
   if (n_views == 0) return MIS_OK;
 
-  // staging 0 (default): warp-tile kernel (aug_tile.cu) wherever it applies; 1: TMA band kernel; 2: cp.async band kernel
-  if (use_tma == 0 && mis::augt::tile_supported(C, H, W, img_stride, s)) {
+  // variant 0 (default): strip kernel (aug_strip.cu) wherever it applies, else the round-1 warp-tile kernel (3), else
+  // the cp.async band kernel (2); 1: TMA band kernel
+  const bool window = !(win_lo == 0.f && win_hi == 65535.f);
+  if (use_tma == 0 && mis::augs::strip_supported(C, H, W, img_stride, s)) {
+    mis::augs::StripArgs t = {};
+    t.src = src;
+    t.img_stride = img_stride;
+    t.C = C;
+    t.H = H;
+    t.W = W;
+    t.params = params;
+    t.win_lo = win_lo;
+    t.win_scale = 1.0f / (win_hi - win_lo);
+    for (int c = 0; c < C; ++c) {
+      t.mean[c] = mean[c];
+      t.inv_std[c] = 1.0f / std[c];
+    }
+    t.out = out;
+    t.s = s;
+    t.out_f32 = out_dtype == MIS_DTYPE_F32 ? 1 : 0;
+    return mis::augs::launch_strip(t, n_views, window, reinterpret_cast<cudaStream_t>(stream));
+  }
+  if ((use_tma == 0 || use_tma == 3) && mis::augt::tile_supported(C, H, W, img_stride, s)) {
     mis::augt::TileArgs t = {};
     t.src = src;
     t.img_stride = img_stride;
@@ -1080,8 +1108,7 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
     t.s = s;
     t.out_f32 = out_dtype == MIS_DTYPE_F32 ? 1 : 0;
     t.nbands = (s + kBandRows - 1) / kBandRows;
-    t.debug_no_cluster = std::getenv("MIS_DEBUG_FLAGS") ? std::atoi(std::getenv("MIS_DEBUG_FLAGS")) : 0;
-    return mis::augt::launch_tile(t, n_views, !(win_lo == 0.f && win_hi == 65535.f), reinterpret_cast<cudaStream_t>(stream));
+    return mis::augt::launch_tile(t, n_views, window, reinterpret_cast<cudaStream_t>(stream));
   }
   use_tma = (use_tma == 1) ? 1 : 0;
 
@@ -1146,8 +1173,9 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
   MIS_REQUIRE(smem <= 227 * 1024, MIS_ERR_UNSUPPORTED,
               "mis_aug_two_view: needs %zu B of shared memory per CTA (H=%d W=%d s=%d)", smem, H, W, s);
 
+#ifdef MIS_DEBUG
   a.dbg = g_dbg;
-  const bool window = !(win_lo == 0.f && win_hi == 65535.f);
+#endif
   const int grid = a.nbands * n_views * C;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap maps[4] = {};

@@ -1,0 +1,663 @@
+// K1 (strip variant, the default) -- fused two-view augmentation for 16-bit slices (sm_100a).
+//
+// One CTA per output view plane.  The plane is cut into strips of 32 output columns and nsy vertical parts; every
+// (strip, part) is one WARP that streams its own source rows and never synchronises with another warp between the
+// CTA-wide table build and the contrast mean:
+//
+//   tables   : all threads build the vertical tap table (one output row per thread) and from it the
+//              input-stationary schedule of the WHOLE crop (one 16-byte entry per source row: the weights of the
+//              three output rows it feeds, plus a bit mask "this row completes an output row") -- once per view
+//              instead of once per 32-row band as in the round-1 tile kernel;
+//   V pass   : lane = NL pairs of adjacent source columns, read straight from global memory with 4-byte loads
+//              through G register slots refilled on consumption; every pixel is converted once (exact
+//              magic-number u16 -> f32) and scattered with FFMA2 (scalar-broadcast weight operand) into the three
+//              open output rows, which rotate through the FMA operands;
+//   H pass   : a completed row goes through a warp-private row buffer; lane = one output column with its taps in
+//              registers (pre-scaled so the result is in uint16 units); the result is PARKED AS UINT16 (round to
+//              nearest of x*65535, |error| <= 7.7e-6 of full scale) in a warp-private tile -- 2*s*s bytes per view
+//              instead of 4*s*s, which is what lets a whole 224x224 view (and two CTAs) live on one SM;
+//   colour   : the contrast mean is a CTA reduction (no cluster, no DSMEM); views without jitter skip the barrier;
+//   store    : 8 pixels per lane from the parked tile: contrast / brightness / normalise / flip, 16-byte stores.
+//
+// Vertical upscaling uses an output-stationary three-tap pass, windows the stream cannot express (a source row
+// feeding more than three output rows -- never seen for downscaling) a generic output-stationary pass.
+//
+// Arithmetic restated from torchvision 0.26 / ATen (see oracle/aug_oracle.py):
+//   taps   : _upsample_bilinear2d_aa (triangle filter, support = max(scale,1), weights normalised)
+//   colour : functional/_color.py:114-125 (brightness), :190-205 + _blend :92-97 (contrast)
+//   output : (x - mean) / std, functional/_misc.py:37-67
+#include <cuda_bf16.h>
+
+#include "aug_math.cuh"
+#include "aug_strip.cuh"
+#include "common.cuh"
+
+namespace mis {
+namespace augs {
+
+using namespace mis::aug;
+
+constexpr int kStrip = 32;         // output columns per warp
+constexpr int kVK = 16;            // widest vertical window kept in the weight table (2*ceil(5.5)+1 = 13)
+constexpr int kTilePitch = 64;     // bytes per parked row of a warp tile (32 x uint16)
+constexpr int kMaxParts = 8;
+constexpr float kMagic = 8388608.f;   // 2^23: float(2^23 + q) carries the integer q in its low mantissa bits
+
+struct Misc {
+  float red[32];
+  int part_lo[kMaxParts];    // first source row of a part's stream (crop coordinates)
+  int part_end[kMaxParts];   // one past its last source row
+  int m_max;                 // most output rows a single source row feeds (4 = the schedule cannot express the view)
+  int pad[3];
+};
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void sts64u(uint32_t addr, uint64_t v) {
+  asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t ptr_add(uint64_t p, uint32_t bytes) {     // one IMAD.WIDE instead of an add pair
+  uint64_t r;
+  asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(bytes), "l"(p));
+  return r;
+}
+
+template <bool kWindow>
+__device__ __forceinline__ uint64_t conv_px(uint32_t p, uint64_t wsc, uint64_t wof) {
+  uint64_t f = u16x2_to_f32x2(p);
+  if (kWindow) {
+    f = ffma2(f, wsc, wof);
+    float f0, f1;
+    unpack2(f, f0, f1);
+    f = pack2(fminf(fmaxf(f0, 0.f), 1.f), fminf(fmaxf(f1, 0.f), 1.f));
+  }
+  return f;
+}
+
+// what a warp needs to know about its (strip, part)
+struct Part {
+  float win_lo, win_scale;
+  uint32_t sched;          // shared address of the schedule / upscaling table
+  uint32_t fmask;          // shared address of the completion bit mask
+  uint32_t row;            // shared address of this warp's row buffer(s)
+  uint32_t toggle;         // bytes between the two row buffers (0: one buffer, extra warp barrier per row)
+  uint32_t tile;           // shared address of this warp's parked tile
+  int rowbuf;              // floats per row buffer
+  const uint16_t* crop;    // crop (0, 0) of this plane in global memory
+  int W;                   // source row pitch in elements
+  int h;                   // crop height
+  int ca;                  // first staged source column (crop coordinates, 4-byte aligned address)
+  int lane;
+  int y0, nrows;           // output rows of this part
+  int span;                // source columns this warp stages, from `ca`
+  int hlo, hsize;          // this lane's output: first source column, taps
+  float hctr, hinv;
+  float out_k;             // folded into the horizontal taps: result in uint16 units (times an early brightness)
+  int mode;                // 0 input-stationary stream, 1 three-tap upscaling, 2 generic
+  int r_lo, r_end;         // mode 0: source rows [r_lo, r_end) of the stream
+  float vscale, vsup, vinv;
+};
+
+// One (strip, part) of one warp: 32 output columns, nrows output rows.  Returns this lane's share of the pixel sum
+// (uint16 units).
+template <int NL, int NS, bool kWindow>
+__device__ __forceinline__ float run_part(const Part& t) {
+  const int lane = t.lane;
+
+  // ---- this lane's horizontal taps, in registers, aligned to the 16-byte window start ------------------
+  uint64_t hw[2 * NS];
+  uint32_t rbase;
+  {
+    const int off = (t.hlo - t.ca) & 3;
+    const int xa = t.hsize > 0 ? ((t.hlo - t.ca) & ~3) : 0;
+    // taps at their aligned positions (zero outside the window); their sum in ascending order is the reference's total
+    float w[4 * NS];
+    float tot = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 4 * NS; ++jj) {
+      const int j = jj - off;
+      w[jj] = (j >= 0 && j < t.hsize) ? aa_tri(j + t.hlo, t.hctr, t.hinv) : 0.f;
+      tot += w[jj];
+    }
+    // (one reciprocal instead of a division per tap: weights differ from w / total by at most one ulp)
+    const float rtot = (tot != 0.f ? __frcp_rn(tot) : 1.f);
+#pragma unroll
+    for (int i = 0; i < 2 * NS; ++i) hw[i] = pack2(w[2 * i] * rtot * t.out_k, w[2 * i + 1] * rtot * t.out_k);
+    rbase = opaque(t.row + 4u * xa);             // aligned window start in buffer 0
+  }
+  // zero-weight taps may read up to 15 columns behind the staged span: those must hold finite values
+  if (lane < 24) {
+    const int c = (t.span & ~1) + lane;
+    if (c < t.rowbuf) {
+      sts32(t.row + 4u * c, 0.f);
+      sts32(t.row + t.toggle + 4u * c, 0.f);
+    }
+  }
+  __syncwarp();
+
+  bool act[NL];
+  uint32_t wb[NL];
+  uint64_t gl[NL];
+  // (idle lanes read a valid address and park their finite garbage in the last two floats of the buffer)
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    act[i] = (2 * lane + 64 * i) < t.span;
+    wb[i] = opaque(t.row + (act[i] ? 8u * lane + 256u * i : 4u * (t.rowbuf - 2)));
+  }
+  const uint64_t wsc = pack2(t.win_scale, t.win_scale);
+  const uint64_t wof = pack2(-t.win_lo * t.win_scale, -t.win_lo * t.win_scale);
+  const uint32_t rowb = 2u * (uint32_t)t.W;                          // source row pitch in bytes
+#pragma unroll
+  for (int i = 0; i < NL; ++i)
+    gl[i] = reinterpret_cast<uint64_t>(t.crop + t.ca + (act[i] ? 2 * lane + 64 * i : 0));
+
+  uint64_t A[NL], B[NL], Cc[NL];    // the three open output rows of this lane's column pair(s)
+#pragma unroll
+  for (int i = 0; i < NL; ++i) A[i] = B[i] = Cc[i] = 0ull;
+  float sum = 0.f;
+  uint32_t sel = 0;                                  // 0 / toggle: row buffer in use
+  uint32_t op = opaque(t.tile + 2u * lane);          // where this lane parks its next result
+
+  // the oldest open output row is complete in A: H pass over the intermediate row, result parked as uint16
+  auto hrow = [&]() {
+    if (t.toggle == 0) __syncwarp();                 // single buffer: the previous row's window reads are done
+#pragma unroll
+    for (int i = 0; i < NL; ++i) sts64u(wb[i] + sel, A[i]);
+    __syncwarp();
+    uint64_t acc = 0ull;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const float4 v = lds128(rbase + sel + 16u * j);
+      acc = ffma2(pack2(v.x, v.y), hw[2 * j], acc);
+      acc = ffma2(pack2(v.z, v.w), hw[2 * j + 1], acc);
+    }
+    float lo, hi;
+    unpack2(acc, lo, hi);
+    // uint16 units; the clamp is the upper half of clamp(x * brightness, 0, 1) (everything here is >= 0) and trims
+    // the one-ulp overshoot a normalised filter can produce
+    const float val = fminf(lo + hi, 65535.f);
+    sum += val;                                   // lanes beyond the view's last column carry zero weights
+    sts_u16(op, __float_as_uint(val + kMagic));   // low 16 mantissa bits of 2^23 + val = round-to-nearest(val)
+    op += kTilePitch;
+    sel ^= t.toggle;
+  };
+
+  if (t.mode == 0) {
+    // ---- input-stationary stream over the part's source rows --------------------------------------------
+    // The stream starts at the group-aligned row at or before the part's first row: the rows in front of it only
+    // feed output rows of the previous part, whose (partial) results are dropped: `cur` counts completed output
+    // rows relative to y0 and only 0 <= cur < nrows is emitted.
+    constexpr int G = NL == 1 ? 8 : 4;
+    const int r_start = t.r_lo & ~(G - 1);
+    const int r_end = t.r_end;
+    int cur;
+    {
+      const uint32_t info = lds32(t.sched + 16u * r_start + 12u);
+      cur = (int)(info & 0xffffu) - (int)(info >> 16) - t.y0;     // first open row (minus one if this row flushes)
+    }
+    uint32_t p[G][NL];
+    uint64_t gq[NL];                                  // next row to fetch, this lane's columns
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const uint64_t g0 = gl[i] + (uint64_t)((uint32_t)r_start * rowb);
+#pragma unroll
+      for (int k = 0; k < G; ++k) p[k][i] = ldg_nc_u32(g0 + (uint64_t)((uint32_t)min(k, r_end - 1 - r_start) * rowb));
+      gq[i] = g0 + (uint64_t)((uint32_t)G * rowb);
+    }
+    uint32_t sp = t.sched + 16u * r_start;
+    const uint32_t nrows = (uint32_t)t.nrows;
+#pragma unroll 1
+    for (int rr0 = r_start; rr0 < r_end; rr0 += G) {
+      const uint32_t m = lds32(t.fmask + 4u * (rr0 >> 5)) >> (rr0 & 31);
+      const int rem = r_end - G - rr0;                 // slot k is refilled while k < rem
+#pragma unroll
+      for (int k = 0; k < G; ++k) {
+        uint64_t f[NL];
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+          f[i] = conv_px<kWindow>(p[k][i], wsc, wof);
+          if (k < rem) p[k][i] = ldg_nc_u32(gq[i]);
+          gq[i] = ptr_add(gq[i], rowb);
+        }
+        const float4 s0 = lds128(sp + 16u * k);        // {w0, w1, w2, info}: weights of the three open rows
+        const uint64_t w0 = pack2(s0.x, s0.x), w1 = pack2(s0.y, s0.y), w2 = pack2(s0.z, s0.z);
+        if (m & (1u << k)) {                            // warp-uniform: the oldest open output row is complete
+          if ((uint32_t)cur < nrows) hrow();
+          ++cur;
+#pragma unroll
+          for (int i = 0; i < NL; ++i) {                // rotate the accumulators through the FMA operands
+            A[i] = ffma2(f[i], w0, B[i]);
+            B[i] = ffma2(f[i], w1, Cc[i]);
+            Cc[i] = ffma2(f[i], w2, 0ull);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NL; ++i) {
+            A[i] = ffma2(f[i], w0, A[i]);
+            B[i] = ffma2(f[i], w1, B[i]);
+            Cc[i] = ffma2(f[i], w2, Cc[i]);
+          }
+        }
+      }
+      sp += 16u * G;
+    }
+#pragma unroll 1
+    while (cur < t.nrows) {
+      if (cur >= 0) hrow();
+      ++cur;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        A[i] = B[i];
+        B[i] = Cc[i];
+        Cc[i] = 0ull;
+      }
+    }
+  } else if (t.mode == 1) {
+    // ---- output-stationary, three taps (vertical upscaling): table entry y = {w0, w1, w2, first source row}; the taps
+    // of the next output row are fetched while the current one is accumulated
+    uint32_t q[3][NL];
+    float4 e = lds128(t.sched + 16u * t.y0);
+    auto fetch = [&](const float4& en) {
+      const int lo = __float_as_int(en.w);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const uint32_t rr = (uint32_t)min(lo + k, t.h - 1);
+#pragma unroll
+        for (int i = 0; i < NL; ++i) q[k][i] = ldg_nc_u32(gl[i] + (uint64_t)(rr * rowb));
+      }
+    };
+    fetch(e);
+#pragma unroll 1
+    for (int y = 0; y < t.nrows; ++y) {
+      uint64_t f[3][NL];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int i = 0; i < NL; ++i) f[k][i] = conv_px<kWindow>(q[k][i], wsc, wof);
+      const uint64_t w0 = pack2(e.x, e.x), w1 = pack2(e.y, e.y), w2 = pack2(e.z, e.z);
+      if (y + 1 < t.nrows) {
+        e = lds128(t.sched + 16u * (t.y0 + y + 1));
+        fetch(e);
+      }
+#pragma unroll
+      for (int i = 0; i < NL; ++i) A[i] = ffma2(f[2][i], w2, ffma2(f[1][i], w1, ffma2(f[0][i], w0, 0ull)));
+      hrow();
+    }
+  } else {
+    // ---- output-stationary, any window: the taps are recomputed per output row (warp-uniform arithmetic) --------
+#pragma unroll 1
+    for (int y = 0; y < t.nrows; ++y) {
+      int lo, hi;
+      float ctr;
+      aa_window(t.y0 + y, t.h, t.vscale, t.vsup, lo, hi, ctr);
+      const int kcap = min(2 * (int)ceilf(t.vsup) + 1, kVK);
+      int size = hi - lo;
+      size = size < 0 ? 0 : (size > kcap ? kcap : size);
+      float total = 0.f;
+      for (int k = 0; k < size; ++k) total += aa_tri(lo + k, ctr, t.vinv);
+      const float rtot = total != 0.f ? __frcp_rn(total) : 1.f;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) A[i] = 0ull;
+#pragma unroll 1
+      for (int k = 0; k < size; ++k) {
+        const float w = aa_tri(lo + k, ctr, t.vinv) * rtot;
+        const uint64_t wp = pack2(w, w);
+        const uint64_t ro = (uint64_t)((uint32_t)(lo + k) * rowb);
+#pragma unroll
+        for (int i = 0; i < NL; ++i) A[i] = ffma2(conv_px<kWindow>(ldg_nc_u32(gl[i] + ro), wsc, wof), wp, A[i]);
+      }
+      hrow();
+    }
+  }
+  return sum;
+}
+
+template <bool kWindow, int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) aug_strip_kernel(const __grid_constant__ StripArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int nthreads = blockDim.x;
+  const int nwarps = nthreads >> 5;
+  const int sy = warp / a.nsx;
+  const int sx = warp - sy * a.nsx;
+  const int plane = blockIdx.x;                 // view * C + c
+  const int view = a.C == 1 ? plane : plane / a.C;
+  const int chan = plane - view * a.C;
+  const int s = a.s;
+  Misc& misc = *reinterpret_cast<Misc*>(smem + a.off_misc);
+  float4* const sched = reinterpret_cast<float4*>(smem + a.off_sched);
+  uint32_t* const fmask = reinterpret_cast<uint32_t*>(smem + a.off_fmask);
+  // vertical tap table of the view: lives in the (not yet used) parked-tile area until the schedule is built
+  float* const vw = reinterpret_cast<float*>(smem);                       // [s][kVK]
+  int2* const vinfo = reinterpret_cast<int2*>(smem + (size_t)s * kVK * 4);  // [s] {first source row, taps}
+
+  const MisViewParams P = a.params[view];
+  const int64_t plane_base = (int64_t)P.img * a.img_stride + (int64_t)chan * a.H * a.W;
+  const int64_t e0 = plane_base + (int64_t)P.top * a.W + P.left;   // element index of crop (0,0)
+  const float vscale = (float)P.h / (float)s;
+  const float hscale = (float)P.w / (float)s;
+  const float vsup = vscale >= 1.f ? vscale : 1.f, vinv = vscale >= 1.f ? 1.f / vscale : 1.f;
+  const float hsup = hscale >= 1.f ? hscale : 1.f, hinv = hscale >= 1.f ? 1.f / hscale : 1.f;
+  const bool vdown = vscale >= 1.f;
+  const int y0 = sy * a.rp;
+  const int nrows = max(0, min(a.rp, s - y0));
+
+  // ---- vertical taps: one output row per thread -------------------------------------------------------------
+  const int hpad = (P.h + 7) & ~7;
+  if (tid == 0) misc.m_max = 0;
+  for (int i = tid; i < (hpad >> 5) + 1; i += nthreads) fmask[i] = 0u;
+  if (tid < s) {
+    int lo, hi;
+    float ctr;
+    aa_window(tid, P.h, vscale, vsup, lo, hi, ctr);
+    const int kcap = min(2 * (int)ceilf(vsup) + 1, kVK);
+    int size = hi - lo;
+    size = size < 0 ? 0 : (size > kcap ? kcap : size);
+    float wj[kVK];
+    float total = 0.f;
+    if (size <= 8) {                                  // the usual case: no loops
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        wj[j] = (j < size) ? aa_tri(j + lo, ctr, vinv) : 0.f;
+        total += wj[j];                               // same order as the reference (zeros beyond the window)
+      }
+#pragma unroll
+      for (int j = 8; j < kVK; ++j) wj[j] = 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < kVK; ++j) {
+        wj[j] = (j < size) ? aa_tri(j + lo, ctr, vinv) : 0.f;
+        total += wj[j];
+      }
+    }
+    const float rtot = total != 0.f ? __frcp_rn(total) : 1.f;
+    if (vdown) {
+      float4* w4 = reinterpret_cast<float4*>(vw + (size_t)tid * kVK);
+#pragma unroll
+      for (int j = 0; j < kVK / 4; ++j)
+        w4[j] = make_float4(wj[4 * j] * rtot, wj[4 * j + 1] * rtot, wj[4 * j + 2] * rtot, wj[4 * j + 3] * rtot);
+      vinfo[tid] = make_int2(lo, size);
+    } else {
+      // upscaling: at most three taps; the table entry IS the pass's working set
+      sched[tid] = make_float4(wj[0] * rtot, wj[1] * rtot, wj[2] * rtot, __int_as_float(lo));
+    }
+    // stream bounds of the parts (the table above is recycled as tile storage once the first warp parks a row)
+    const int py = tid / a.rp;
+    if (tid == py * a.rp) misc.part_lo[py] = lo;
+    if (tid == min(s, (py + 1) * a.rp) - 1) misc.part_end[py] = lo + size;
+  }
+
+  // ---- this warp's strip: horizontal windows (independent of the tables above) -----------------------------
+  Part t;
+  t.win_lo = a.win_lo;
+  t.win_scale = a.win_scale;
+  t.sched = smem_u32(sched);
+  t.fmask = smem_u32(fmask);
+  t.rowbuf = a.rowbuf;
+  t.toggle = a.dbl ? 4u * (uint32_t)a.rowbuf : 0u;
+  t.row = smem_u32(smem + a.off_row) + (uint32_t)warp * (a.dbl ? 8u : 4u) * (uint32_t)a.rowbuf;
+  t.tile = smem_u32(smem) + (uint32_t)warp * (uint32_t)(a.rp * kTilePitch);
+  t.crop = a.src + e0;
+  t.W = a.W;
+  t.h = P.h;
+  t.lane = lane;
+  t.y0 = y0;
+  t.nrows = nrows;
+  t.hinv = hinv;
+  t.vscale = vscale;
+  t.vsup = vsup;
+  t.vinv = vinv;
+  const bool jitter = (P.flags & MIS_VIEW_JITTER) != 0;
+  // brightness (op 0) before contrast (op 1) is applied while the tile is produced: the contrast mean needs it
+  int pos_b = 0, pos_c = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (P.order[k] == 0) pos_b = k;
+    if (P.order[k] == 1) pos_c = k;
+  }
+  const float unit = kWindow ? 65535.f : 1.f;          // the windowed pixel is already in [0, 1]
+  t.out_k = (jitter && pos_b < pos_c) ? unit * P.brightness : unit;
+  const bool has_post = jitter && pos_b > pos_c;
+
+  const int x0 = sx * kStrip;
+  {
+    const int x = x0 + lane;
+    int lo = 0, hi = 0;
+    float ctr = 0.f;
+    if (x < s) aa_window(x, P.w, hscale, hsup, lo, hi, ctr);
+    const int kcap = 2 * (int)ceilf(hsup) + 1;
+    int size = hi - lo;
+    size = size < 0 ? 0 : (size > kcap ? kcap : size);
+    t.hlo = lo;
+    t.hsize = (x < s) ? size : 0;
+    t.hctr = ctr;
+  }
+
+  __syncthreads();                                  // tap table complete
+  if (vdown) {
+    // input-stationary schedule (windows are monotone in y): one entry per source row of the crop.
+    // Source row r can only lie in the windows of the output rows around (r + 0.5) / vscale - 0.5.
+    const float inv_vs = 1.f / vscale;
+    for (int r = tid; r < hpad; r += nthreads) {
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+      int first = s;
+      uint32_t flush = 0;
+      if (r < P.h) {
+        const int yc = (int)floorf(((float)r + 0.5f) * inv_vs - 0.5f);
+        int last = -1, prev = s;
+#pragma unroll
+        for (int d = -3; d <= 3; ++d) {
+          const int yy = yc + d;
+          if (yy >= 0 && yy < s) {
+            const int2 info = vinfo[yy];
+            if (info.x <= r && r < info.x + info.y) {
+              first = min(first, yy);
+              last = max(last, yy);
+            }
+            if (info.x <= r - 1 && r - 1 < info.x + info.y) prev = min(prev, yy);
+          }
+        }
+        // the stream handles at most three open output rows and completes at most ONE output row per source row;
+        // anything else (never seen for downscaling windows) sends the view to the generic pass
+        int m = last - first + 1;
+        if (last < 0 || (r == 0 ? (first != 0) : (prev >= s || first - prev > 1 || first < prev))) {
+          m = 4;
+          first = 0;
+          last = -1;
+        }
+        if (first <= last) w0 = vw[(size_t)first * kVK + (r - vinfo[first].x)];
+        if (first + 1 <= last) w1 = vw[(size_t)(first + 1) * kVK + (r - vinfo[first + 1].x)];
+        if (first + 2 <= last) w2 = vw[(size_t)(first + 2) * kVK + (r - vinfo[first + 2].x)];
+        if (m > 3) atomicMax(&misc.m_max, m);
+        if (r > 0 && first > prev) {
+          flush = 1;
+          atomicOr(&fmask[r >> 5], 1u << (r & 31));
+        }
+      }
+      sched[r] = make_float4(w0, w1, w2, __uint_as_float((uint32_t)first | (flush << 16)));
+    }
+  }
+
+  // ---- the strip's staged span (from the 4-byte aligned column at or before its first window) and class ---------
+  const int c_lo = __shfl_sync(0xffffffffu, t.hlo, 0);
+  t.ca = c_lo - (int)((e0 + c_lo) & 1);
+  t.span = __reduce_max_sync(0xffffffffu, t.hsize > 0 ? t.hlo + t.hsize : 0) - t.ca;
+  const int need = __reduce_max_sync(0xffffffffu, t.hsize > 0 ? ((t.hlo - t.ca) & 3) + t.hsize : 0);
+
+  __syncthreads();                                  // schedule complete; vw / vinfo are dead from here on
+  t.mode = !vdown ? 1 : (misc.m_max <= 3 ? 0 : 2);
+  t.r_lo = misc.part_lo[sy];
+  t.r_end = misc.part_end[sy];
+
+  float sum = 0.f;
+  if (nrows > 0) {
+    if (t.span <= 64 && need <= 8) sum = run_part<1, 2, kWindow>(t);
+    else if (t.span <= 128 && need <= 12) sum = run_part<2, 3, kWindow>(t);
+    else sum = run_part<3, 4, kWindow>(t);
+  }
+
+  // ================================ contrast mean over the view ===========================================
+  float cadd = 0.f;
+  const float cf = P.contrast;
+  if (jitter) {
+    sum = warp_sum(sum);
+    if (lane == 0) misc.red[warp] = sum;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < nwarps; ++i) tot += misc.red[i];
+    const float mu = tot / (float)(s * s) * (1.f / 65535.f);
+    cadd = mu * (1.f - cf);
+  } else {
+    __syncwarp();
+  }
+
+  // ================================ colour, normalise, store ==============================================
+  const float mean = a.mean[chan], inv_std = a.inv_std[chan];
+  const bool flip = (P.flags & MIS_VIEW_FLIP) != 0;
+  const float pb = P.brightness;
+  const float cs = cf * (1.f / 65535.f);
+  const uint64_t nmagic = pack2(-kMagic, -kMagic);
+  const int iters = (nrows + 7) >> 3;
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    const int id = it * 32 + lane;
+    const int row = id >> 2, xs = x0 + 8 * (id & 3);
+    if (row < nrows && xs < s) {
+      const uint4 q = lds128u(t.tile + (uint32_t)(row * kTilePitch + 16 * (id & 3)));
+      const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t lo = __byte_perm(qq[i], 0x4B000000u, 0x7610);
+        const uint32_t hi = __byte_perm(qq[i], 0x4B000000u, 0x7632);
+        unpack2(fadd2(pack2(__uint_as_float(lo), __uint_as_float(hi)), nmagic), v[2 * i], v[2 * i + 1]);
+      }
+      if (jitter) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __saturatef(fmaf(v[i], cs, cadd));
+        if (has_post) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __saturatef(v[i] * pb);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = v[i] * (1.f / 65535.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * inv_std;
+      store_run<8>(v, a.out, ((size_t)plane * s + (y0 + row)) * s, xs, s, flip, a.out_f32 != 0);
+    }
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+struct Plan {
+  int nsx, nsy, rp, rowbuf, dbl, threads, big;
+  uint32_t off_sched, off_fmask, off_row, off_misc;
+  size_t smem;
+  int ctas;
+};
+
+static inline size_t al16(size_t v) { return (v + 15) & ~size_t(15); }
+
+static bool make_plan(int H, int W, int s, Plan* best) {
+  const int nsx = (s + kStrip - 1) / kStrip;
+  // widest staged span of a strip: 31 output steps + one window + alignment
+  const double sm = (double)W / s > 1.0 ? (double)W / s : 1.0;
+  const int span_max = (int)(33.0 * sm + 3.0) + 2;
+  if (span_max > 192) return false;
+  const int rowbuf = (span_max + 18 + 7) & ~7;
+  const int sched_cap = (((H > s ? H : s) + 7) & ~7) + 8;
+  const size_t kSmPerSm = 233472, kSmPerBlock = 232448;
+  bool found = false;
+  int best_warps = 0;
+  for (int nsy = 1; nsy <= kMaxParts; ++nsy) {
+    const int threads = 32 * nsx * nsy;
+    if (threads > 1024) break;
+    const int rp = (s + nsy - 1) / nsy;
+    if (rp < 8 && nsy > 1) break;
+    if ((s + rp - 1) / rp != nsy) continue;            // an empty trailing part: skip this split
+    const int nwarps = nsx * nsy;
+    size_t park = (size_t)nwarps * rp * kTilePitch;
+    const size_t vtab = (size_t)s * (kVK * 4 + 8);
+    if (park < vtab) park = vtab;
+    for (int dbl = 1; dbl >= 0; --dbl) {
+      Plan p = {};
+      p.nsx = nsx; p.nsy = nsy; p.rp = rp; p.rowbuf = rowbuf; p.dbl = dbl; p.threads = threads;
+      p.big = threads > 448;
+      size_t off = al16(park);
+      p.off_sched = (uint32_t)off; off += (size_t)sched_cap * 16;
+      p.off_fmask = (uint32_t)off; off += al16((size_t)(sched_cap / 32 + 2) * 4);
+      p.off_row = (uint32_t)off; off += (size_t)nwarps * (dbl ? 2 : 1) * rowbuf * 4;
+      p.off_misc = (uint32_t)off; off += sizeof(Misc);
+      p.smem = off;
+      if (p.smem > kSmPerBlock) continue;
+      const int regs = p.big ? 64 : 72;
+      int ctas = (int)(kSmPerSm / (p.smem + 1024));
+      const int by_threads = 2048 / threads, by_regs = 65536 / (regs * threads);
+      ctas = ctas < by_threads ? ctas : by_threads;
+      ctas = ctas < by_regs ? ctas : by_regs;
+      if (ctas > 32) ctas = 32;
+      if (ctas < 1) continue;
+      p.ctas = ctas;
+      const int warps = ctas * nwarps;
+      // more resident warps win; on a tie fewer parts (less halo, fewer redundant set-ups), then two row buffers
+      if (!found || warps > best_warps) {
+        *best = p;
+        best_warps = warps;
+        found = true;
+      }
+    }
+  }
+  return found;
+}
+
+bool strip_supported(int C, int H, int W, int64_t img_stride, int s) {
+  // class (3,4) covers 5.5x downscaling per axis: 31*5.5 + 2*5.5 + 2 <= 192 staged columns, 3 + 13 <= 16 aligned taps
+  if (!(C == 1 && s >= 8 && s <= 256 && (W & 1) == 0 && (img_stride & 1) == 0 && 2 * W <= 11 * s && 2 * H <= 11 * s))
+    return false;
+  Plan p;
+  return make_plan(H, W, s, &p);
+}
+
+template <bool kWindow, int kMaxThreads, int kMinBlocks>
+static int launch_one(const StripArgs& a, int n_planes, const Plan& p, cudaStream_t stream) {
+  auto* fn = &aug_strip_kernel<kWindow, kMaxThreads, kMinBlocks>;
+  MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  fn<<<dim3((unsigned)n_planes), dim3((unsigned)p.threads), p.smem, stream>>>(a);
+  MIS_CUDA_TRY(cudaGetLastError());
+  return MIS_OK;
+}
+
+int launch_strip(StripArgs a, int n_views, bool window, cudaStream_t stream) {
+  Plan p;
+  MIS_REQUIRE(make_plan(a.H, a.W, a.s, &p), MIS_ERR_UNSUPPORTED, "mis_aug_two_view: no strip plan for H=%d W=%d s=%d",
+              a.H, a.W, a.s);
+  a.nsx = p.nsx; a.nsy = p.nsy; a.rp = p.rp; a.rowbuf = p.rowbuf; a.dbl = p.dbl;
+  a.off_sched = p.off_sched; a.off_fmask = p.off_fmask; a.off_row = p.off_row; a.off_misc = p.off_misc;
+  const int n_planes = n_views * a.C;
+  if (p.big) return window ? launch_one<true, 1024, 1>(a, n_planes, p, stream) : launch_one<false, 1024, 1>(a, n_planes, p, stream);
+  return window ? launch_one<true, 448, 2>(a, n_planes, p, stream) : launch_one<false, 448, 2>(a, n_planes, p, stream);
+}
+
+}  // namespace augs
+}  // namespace mis

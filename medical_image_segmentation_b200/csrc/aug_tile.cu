@@ -348,8 +348,7 @@ __global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs
   const int chan = plane - view * a.C;
   const int s = a.s;
 
-  const bool nocl = (a.debug_no_cluster & 1) != 0;
-  if (!nocl) cluster_arrive_relaxed();   // phase 1: "every CTA of the cluster is running" (waited before DSMEM use)
+  cluster_arrive_relaxed();   // phase 1: "every CTA of the cluster is running" (waited before DSMEM use)
 
   const MisViewParams P = a.params[view];
   const int y0 = band * kBand;
@@ -369,7 +368,7 @@ __global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs
     aa_window(y0 + nrows - 1, P.h, vscale, vsup, lo1, hi1, ctr);
   }
   // ---- pull the band's crop rows into L2 (every thread derives the row range itself) --------------------------
-  if (!(a.debug_no_cluster & 2)) {
+  {
     const uint8_t* base = reinterpret_cast<const uint8_t*>(a.src + e0);
     const int head = (int)(reinterpret_cast<uintptr_t>(base) & 127);
     const int lines = (head + 2 * P.w + 127) >> 7;               // 128-byte lines per crop row
@@ -529,7 +528,7 @@ __global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs
   }
 
   // ================================ contrast mean over the view ===========================================
-  if (!nocl) cluster_wait_acquire();   // phase 1 done: all CTAs of the cluster are resident
+  cluster_wait_acquire();   // phase 1 done: all CTAs of the cluster are resident
   float cadd = 0.f;
   const float cf = P.contrast;
   if (jitter) {
@@ -539,17 +538,11 @@ __global__ void __maxnreg__(64) aug_tile_kernel(const __grid_constant__ TileArgs
     if (tid == 0) {
       float tot = 0.f;
       for (int i = 0; i < (nthreads >> 5); ++i) tot += sh.red[i];
-      if (nocl) { for (int r = 0; r < a.nbands; ++r) sh.part[r] = tot; }
-      else {
-        for (int r = 0; r < a.nbands; ++r) st_cluster_f32(&sh.part[band], (uint32_t)r, tot);
-        fence_acq_rel_cluster();          // the writer releases; everybody else arrives relaxed (no CTA-wide membar)
-      }
+      for (int r = 0; r < a.nbands; ++r) st_cluster_f32(&sh.part[band], (uint32_t)r, tot);
+      fence_acq_rel_cluster();          // the writer releases; everybody else arrives relaxed (no CTA-wide membar)
     }
-    if (nocl) __syncthreads();
-    else {
-      cluster_arrive_relaxed();
-      cluster_wait_acquire();
-    }
+    cluster_arrive_relaxed();
+    cluster_wait_acquire();
     float tot = 0.f;
     for (int r = 0; r < a.nbands; ++r) tot += sh.part[r];
     const float mu = tot / (float)(s * s);
@@ -613,7 +606,7 @@ int launch_tile(const TileArgs& a, int n_views, bool window, cudaStream_t stream
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (a.debug_no_cluster & 1) ? 1u : (unsigned)a.nbands;
+    attr[0].val.clusterDim.x = (unsigned)a.nbands;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;

@@ -20,7 +20,6 @@ struct TileArgs {
   int s;
   int out_f32;
   int nbands;
-  int debug_no_cluster;   // timing experiments only: no cluster launch, the contrast mean is per band (WRONG results)
 };
 
 // shapes the tile kernel covers (single channel, s <= 256, at most 5.5x downscaling of the whole slice per axis)

@@ -81,6 +81,13 @@ class CudaKernels:
     launches = 0   # kernels launched through this class (bench.py's gpu_launches claim)
 
     @staticmethod
+    def launch_mode(world: int) -> str:
+        """How the loss's kernels reach the GPU (reported by bench.py)."""
+        if world == 1 and os.environ.get("MIS_NTXENT_GRAPH") == "1":
+            return "CUDA graph replay (prep, fwd, bwd: 6 kernels + memset)"
+        return "eager"
+
+    @staticmethod
     def prep(z: torch.Tensor):
         if not z.is_cuda:
             raise RuntimeError("nt_xent_loss has no CPU path: embeddings must be CUDA tensors")

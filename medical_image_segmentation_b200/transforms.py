@@ -12,9 +12,10 @@ per-sample CPU callable to a per-batch GPU kernel:
   train/model/byol_pytorch.py:207 is free.
 * random parameters are drawn from torch's global CPU generator in exactly the reference's order
   (params.py), so ``torch.manual_seed(k)`` gives the same crops / flips / jitter as the reference.
-* ``use_tma`` selects the K1 variant: ``False``/``0`` (default: the warp-tile kernel, csrc/aug_tile.cu, wherever it
-  applies), ``True``/``1`` (band kernel, 2-D TMA tensor-map boxes fed by a producer warp) or ``2`` (band kernel,
-  per-thread cp.async rings, 16-row sub-bands).  All three are parity-tested against the same oracle.
+* ``use_tma`` selects the K1 variant: ``False``/``0`` (default: the strip kernel, csrc/aug_strip.cu, wherever it
+  applies), ``True``/``1`` (band kernel, 2-D TMA tensor-map boxes fed by a producer warp), ``2`` (band kernel,
+  per-thread cp.async rings, 16-row sub-bands) or ``3`` (round-1 warp-tile kernel, csrc/aug_tile.cu).  All four are
+  parity-tested against the same oracle.
 * ``prefetch_params=True`` draws the next batch's parameters on a helper thread while the GPU works on the current
   one (same records in the same order; see ``next_params``).
 * GaussianBlur and Solarize (lightning_module.py:53-54) are not implemented on the device yet:
@@ -84,8 +85,9 @@ class FusedTwoViewTransforms:
         self.out_dtype = out_dtype
         self.window = (0.0, _U16_MAX) if window is None else (float(window[0]), float(window[1]))
         self.use_tma = int(use_tma)
-        if self.use_tma not in (0, 1, 2):
-            raise ValueError("use_tma must be 0 (tile kernel), 1 (TMA band kernel) or 2 (cp.async band kernel)")
+        if self.use_tma not in (0, 1, 2, 3):
+            raise ValueError("use_tma must be 0 (strip kernel), 1 (TMA band kernel), 2 (cp.async band kernel) or "
+                             "3 (warp-tile kernel)")
         self.prefetch_params = bool(prefetch_params)
         self._pool = None                     # one helper thread drawing the NEXT batch's parameters
         self._pending = None                  # ((B, H, W), future)

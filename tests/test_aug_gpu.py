@@ -36,7 +36,7 @@ def _check(got, ref, what):
     return float(err.max())
 
 
-@pytest.mark.parametrize("use_tma", [0, 1, 2])      # tile kernel, TMA band kernel, cp.async band kernel
+@pytest.mark.parametrize("use_tma", [0, 1, 2, 3])   # strip kernel, TMA band kernel, cp.async band kernel, warp-tile kernel
 @pytest.mark.parametrize("crop", [32, 48])
 def test_matches_reference_golden_small(crop, use_tma):
     g = np.load(os.path.join(GOLD, "aug_small.npz"))
@@ -53,7 +53,9 @@ def test_matches_reference_golden_small(crop, use_tma):
         assert [(int(p[i]["flags"]) >> 1) & 1 for i in range(2)] == [int(r[5]) for r in ints]
         for v, out in enumerate((v1, v2)):
             worst = max(worst, _check(out[0, 0].cpu().numpy(), g[f"out_{crop}"][k, v], f"img {k} view {v}"))
-    assert worst < 2e-5      # expected ~1e-6: fp32 separable filter, only the pass order differs
+    # fp32 separable filter, only the pass order differs: ~1e-6.  The strip kernel parks the pre-colour tile as uint16
+    # (|dx| <= 7.7e-6 of full scale, times contrast * brightness / std <= 8.3): ~6e-5 worst case.
+    assert worst < (1e-4 if use_tma == 0 else 2e-5)
 
 
 def test_matches_reference_golden_real_slices():
@@ -85,10 +87,10 @@ def test_matches_reference_golden_512(crop):
 @pytest.mark.parametrize("shape,crop", [((512, 512), 224), ((512, 512), 96), ((512, 512), 256), ((256, 768), 112),
                                         ((448, 448), 56), ((130, 70), 40), ((64, 64), 8), ((512, 512), 100),
                                         ((200, 360), 72), ((96, 96), 224)])
-@pytest.mark.parametrize("use_tma", [0, 2])
+@pytest.mark.parametrize("use_tma", [0, 2, 3])
 def test_batch_matches_oracle(shape, crop, use_tma):
-    """A whole batch in one launch vs the numpy restatement, every pixel (0: tile kernel where it applies -- the
-    8x downscaling shapes fall back to the band kernel; 2: cp.async band kernel)."""
+    """A whole batch in one launch vs the numpy restatement, every pixel (0: strip kernel where it applies -- the
+    8x downscaling shapes fall back to the band kernel; 2: cp.async band kernel; 3: warp-tile kernel)."""
     H, W = shape
     B = 6
     imgs = synth.batch_512(B, seed=77, H=H, W=W)
@@ -106,24 +108,27 @@ def test_batch_matches_oracle(shape, crop, use_tma):
 
 @pytest.mark.parametrize("shape,crop", [((512, 512), 224), ((512, 512), 96), ((300, 500), 64)])
 def test_kernel_variants_agree_and_match_oracle(shape, crop):
-    """The three K1 variants (0 tile kernel, 1 TMA band kernel, 2 cp.async band kernel) against each other and the oracle."""
+    """The K1 variants (0 strip kernel, 1 TMA band kernel, 2 cp.async band kernel, 3 warp-tile kernel) against each
+    other and the oracle."""
     H, W = shape
     imgs = synth.batch_512(4, seed=13, H=H, W=W)
     x = torch.from_numpy(imgs).cuda()
     outs = []
-    for variant in (1, 2, 0):
+    for variant in (1, 2, 3, 0):
         tb = _mk(crop, out_dtype=torch.float32, use_tma=variant)
         torch.manual_seed(77)
         tb(x)
         outs.append(tb.views_buffer.cpu().numpy())
-    a, c, b = outs
+    a, c, b, d = outs
     assert np.abs(a - c).max() <= 2e-6
     assert np.abs(a - b).max() <= 4e-6
+    assert np.abs(a - d).max() <= 1e-4          # the strip kernel's uint16 parking: <= 7.7e-6 * gain (<= 8.3)
     p = tb.last_params
     for i in range(4):
         for v in range(2):
             ref = A.apply_view(imgs[i], _oracle_params(p[2 * i + v]), crop, MEAN, STD)
             _check(b[v * 4 + i, 0], ref, f"tile kernel {shape} img {i} view {v}")
+            _check(d[v * 4 + i, 0], ref, f"strip kernel {shape} img {i} view {v}")
 
 
 def test_bf16_output_is_rounded_fp32_output():
