@@ -47,6 +47,7 @@ struct Misc {
   float red[32];
   int part_lo[kMaxParts];    // first source row of a part's stream (crop coordinates)
   int part_end[kMaxParts];   // one past its last source row
+  int part_e0[kMaxParts];    // source row whose flush completes the part's first output row
   int m_max;                 // most output rows a single source row feeds (4 = the schedule cannot express the view)
   int pad[3];
 };
@@ -96,7 +97,6 @@ struct Part {
   uint32_t sched;          // shared address of the schedule / upscaling table
   uint32_t fmask;          // shared address of the completion bit mask
   uint32_t row;            // shared address of this warp's row buffer(s)
-  uint32_t toggle;         // bytes between the two row buffers (0: one buffer, extra warp barrier per row)
   uint32_t tile;           // shared address of this warp's parked tile
   int rowbuf;              // floats per row buffer
   const uint16_t* crop;    // crop (0, 0) of this plane in global memory
@@ -105,20 +105,23 @@ struct Part {
   int ca;                  // first staged source column (crop coordinates, 4-byte aligned address)
   int lane;
   int y0, nrows;           // output rows of this part
+  int rp;                  // output rows of a full part (kernel argument)
   int span;                // source columns this warp stages, from `ca`
   int hlo, hsize;          // this lane's output: first source column, taps
   float hctr, hinv;
   float out_k;             // folded into the horizontal taps: result in uint16 units (times an early brightness)
   int mode;                // 0 input-stationary stream, 1 three-tap upscaling, 2 generic
   int r_lo, r_end;         // mode 0: source rows [r_lo, r_end) of the stream
+  int r_e0;                // mode 0: source row whose flush completes the part's first output row
   float vscale, vsup, vinv;
 };
 
 // One (strip, part) of one warp: 32 output columns, nrows output rows.  Returns this lane's share of the pixel sum
 // (uint16 units).
-template <int NL, int NS, bool kWindow>
+template <int NL, int NS, bool kWindow, bool kDbl, int kW>
 __device__ __forceinline__ float run_part(const Part& t) {
   const int lane = t.lane;
+  const uint32_t toggle = kDbl ? 4u * (uint32_t)t.rowbuf : 0u;
 
   // ---- this lane's horizontal taps, in registers, aligned to the 16-byte window start ------------------
   uint64_t hw[2 * NS];
@@ -146,7 +149,7 @@ __device__ __forceinline__ float run_part(const Part& t) {
     const int c = (t.span & ~1) + lane;
     if (c < t.rowbuf) {
       sts32(t.row + 4u * c, 0.f);
-      sts32(t.row + t.toggle + 4u * c, 0.f);
+      sts32(t.row + toggle + 4u * c, 0.f);
     }
   }
   __syncwarp();
@@ -162,7 +165,7 @@ __device__ __forceinline__ float run_part(const Part& t) {
   }
   const uint64_t wsc = pack2(t.win_scale, t.win_scale);
   const uint64_t wof = pack2(-t.win_lo * t.win_scale, -t.win_lo * t.win_scale);
-  const uint32_t rowb = 2u * (uint32_t)t.W;                          // source row pitch in bytes
+  const uint32_t rowb = kW > 0 ? 2u * (uint32_t)kW : 2u * (uint32_t)t.W;   // source row pitch in bytes
 #pragma unroll
   for (int i = 0; i < NL; ++i)
     gl[i] = reinterpret_cast<uint64_t>(t.crop + t.ca + (act[i] ? 2 * lane + 64 * i : 0));
@@ -175,17 +178,23 @@ __device__ __forceinline__ float run_part(const Part& t) {
   uint32_t op = opaque(t.tile + 2u * lane);          // where this lane parks its next result
 
   // the oldest open output row is complete in A: H pass over the intermediate row, result parked as uint16
-  auto hrow = [&]() {
-    if (t.toggle == 0) __syncwarp();                 // single buffer: the previous row's window reads are done
+  // first half: park the intermediate row, read this lane's aligned window
+  float4 hv[NS];
+  auto hrow_a = [&]() {
+    if (!kDbl) __syncwarp();                         // single buffer: the previous row's window reads are done
 #pragma unroll
     for (int i = 0; i < NL; ++i) sts64u(wb[i] + sel, A[i]);
     __syncwarp();
+#pragma unroll
+    for (int j = 0; j < NS; ++j) hv[j] = lds128(rbase + sel + 16u * j);
+  };
+  // second half: taps, clamp, sum, park the result as uint16
+  auto hrow_b = [&]() {
     uint64_t acc = 0ull;
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-      const float4 v = lds128(rbase + sel + 16u * j);
-      acc = ffma2(pack2(v.x, v.y), hw[2 * j], acc);
-      acc = ffma2(pack2(v.z, v.w), hw[2 * j + 1], acc);
+      acc = ffma2(pack2(hv[j].x, hv[j].y), hw[2 * j], acc);
+      acc = ffma2(pack2(hv[j].z, hv[j].w), hw[2 * j + 1], acc);
     }
     float lo, hi;
     unpack2(acc, lo, hi);
@@ -195,51 +204,91 @@ __device__ __forceinline__ float run_part(const Part& t) {
     sum += val;                                   // lanes beyond the view's last column carry zero weights
     sts_u16(op, __float_as_uint(val + kMagic));   // low 16 mantissa bits of 2^23 + val = round-to-nearest(val)
     op += kTilePitch;
-    sel ^= t.toggle;
+    if (kDbl) sel ^= toggle;
+  };
+  auto hrow = [&]() {
+    hrow_a();
+    hrow_b();
   };
 
   if (t.mode == 0) {
     // ---- input-stationary stream over the part's source rows --------------------------------------------
     // The stream starts at the group-aligned row at or before the part's first row: the rows in front of it only
-    // feed output rows of the previous part, whose (partial) results are dropped: `cur` counts completed output
-    // rows relative to y0 and only 0 <= cur < nrows is emitted.
+    // feed output rows of the previous part, whose (partial) results are dropped: output row y is complete when the
+    // stream reaches source row e(y) = one past its window, so this part emits exactly at the flushing rows in
+    // [e(y0), r_end].
     constexpr int G = NL == 1 ? 8 : 4;
-    const int r_start = t.r_lo & ~(G - 1);
-    const int r_end = t.r_end;
-    int cur;
-    {
-      const uint32_t info = lds32(t.sched + 16u * r_start + 12u);
-      cur = (int)(info & 0xffffu) - (int)(info >> 16) - t.y0;     // first open row (minus one if this row flushes)
-    }
+    // (warp-uniform by construction; the reductions tell the compiler so: uniform registers and plain branches
+    // instead of convergence barriers around every per-row decision)
+    const int r_start = __reduce_max_sync(0xffffffffu, t.r_lo & ~(G - 1));
+    const int r_end = __reduce_max_sync(0xffffffffu, t.r_end);
+    const int r_e0 = __reduce_max_sync(0xffffffffu, t.r_e0);
+    int cur = 0;                                      // output rows emitted so far
     uint32_t p[G][NL];
-    uint64_t gq[NL];                                  // next row to fetch, this lane's columns
+    uint64_t gq[NL];                                  // kW == 0: next row to fetch; kW > 0: first row of the current group
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
       const uint64_t g0 = gl[i] + (uint64_t)((uint32_t)r_start * rowb);
 #pragma unroll
       for (int k = 0; k < G; ++k) p[k][i] = ldg_nc_u32(g0 + (uint64_t)((uint32_t)min(k, r_end - 1 - r_start) * rowb));
-      gq[i] = g0 + (uint64_t)((uint32_t)G * rowb);
+      gq[i] = kW > 0 ? g0 : g0 + (uint64_t)((uint32_t)G * rowb);
+    }
+    // L2 prefetch kPF rows ahead of the register slots: one instruction per group, lane = (row of the group, 128-byte
+    // line of the strip's staged span).  The slots alone keep G rows (< 1 us of work) in flight, less than the DRAM
+    // latency under load.
+    constexpr int kPF = 4 * G;
+    constexpr int kLinesLog2 = G == 8 ? 2 : 3;
+    uint64_t pfa;
+    int pf_row;                                      // crop row this lane prefetches next
+    bool pf_lane;
+    {
+      const uint64_t first = reinterpret_cast<uint64_t>(t.crop + t.ca);
+      const uint32_t head = (uint32_t)(first & 127u);
+      const int line = lane & ((1 << kLinesLog2) - 1);
+      pf_lane = (uint32_t)(line * 128) < head + 2u * (uint32_t)t.span;
+      pf_row = r_start + G + (lane >> kLinesLog2);
+      pfa = first - head + (uint64_t)((uint32_t)pf_row * rowb) + (uint64_t)(line * 128);
+#pragma unroll 1
+      for (int j = 0; j < kPF / G - 1; ++j) {
+        if (pf_lane && pf_row < r_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(pfa));
+        pf_row += G;
+        pfa += (uint64_t)((uint32_t)G * rowb);
+      }
     }
     uint32_t sp = t.sched + 16u * r_start;
-    const uint32_t nrows = (uint32_t)t.nrows;
+    // schedule entries and mask words are requested one row / one group ahead of their use
+    float4 sn = lds128(sp);
+    uint32_t mw = lds32(t.fmask + 4u * (r_start >> 5));
 #pragma unroll 1
     for (int rr0 = r_start; rr0 < r_end; rr0 += G) {
-      const uint32_t m = lds32(t.fmask + 4u * (rr0 >> 5)) >> (rr0 & 31);
+      const uint32_t m = __reduce_or_sync(0xffffffffu, mw >> (rr0 & 31));
+      // rows rr0 + k of this group that emit: flushing rows with e(y0) <= row <= r_end
+      const int lo_c = min(max(r_e0 - rr0, 0), G), hi_c = min(max(r_end + 1 - rr0, 0), G);
+      const uint32_t me = m & ((1u << hi_c) - 1u) & ~((1u << lo_c) - 1u);
+      cur += __popc(me);
+      mw = lds32(t.fmask + 4u * ((rr0 + G) >> 5));
       const int rem = r_end - G - rr0;                 // slot k is refilled while k < rem
+      if (pf_lane && pf_row < r_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(pfa));
+      pf_row += G;
+      pfa += (uint64_t)((uint32_t)G * rowb);
 #pragma unroll
       for (int k = 0; k < G; ++k) {
         uint64_t f[NL];
 #pragma unroll
         for (int i = 0; i < NL; ++i) {
           f[i] = conv_px<kWindow>(p[k][i], wsc, wof);
-          if (k < rem) p[k][i] = ldg_nc_u32(gq[i]);
-          gq[i] = ptr_add(gq[i], rowb);
+          if (kW > 0) {
+            if (k < rem) p[k][i] = ldg_nc_u32(gq[i] + (uint64_t)((uint32_t)(G + k) * rowb));
+          } else {
+            if (k < rem) p[k][i] = ldg_nc_u32(gq[i]);
+            gq[i] = ptr_add(gq[i], rowb);
+          }
         }
-        const float4 s0 = lds128(sp + 16u * k);        // {w0, w1, w2, info}: weights of the three open rows
+        const float4 s0 = sn;                          // {w0, w1, w2, info}: weights of the three open rows
+        sn = lds128(sp + 16u * (k + 1));               // (the schedule is padded by a whole group)
         const uint64_t w0 = pack2(s0.x, s0.x), w1 = pack2(s0.y, s0.y), w2 = pack2(s0.z, s0.z);
         if (m & (1u << k)) {                            // warp-uniform: the oldest open output row is complete
-          if ((uint32_t)cur < nrows) hrow();
-          ++cur;
+          if (me & (1u << k)) hrow();
 #pragma unroll
           for (int i = 0; i < NL; ++i) {                // rotate the accumulators through the FMA operands
             A[i] = ffma2(f[i], w0, B[i]);
@@ -255,11 +304,15 @@ __device__ __forceinline__ float run_part(const Part& t) {
           }
         }
       }
+      if (kW > 0) {
+#pragma unroll
+        for (int i = 0; i < NL; ++i) gq[i] += (uint64_t)((uint32_t)G * rowb);
+      }
       sp += 16u * G;
     }
 #pragma unroll 1
     while (cur < t.nrows) {
-      if (cur >= 0) hrow();
+      hrow();
       ++cur;
 #pragma unroll
       for (int i = 0; i < NL; ++i) {
@@ -269,35 +322,63 @@ __device__ __forceinline__ float run_part(const Part& t) {
       }
     }
   } else if (t.mode == 1) {
-    // ---- output-stationary, three taps (vertical upscaling): table entry y = {w0, w1, w2, first source row}; the taps
-    // of the next output row are fetched while the current one is accumulated
-    uint32_t q[3][NL];
+    // ---- three taps (vertical upscaling): table entry y = {w0, w1, w2, first source row}.  The loop runs over the
+    // window position (one source row per step, unrolled over a ring of four raw rows in flight, so the ring index
+    // is a compile-time constant); the output rows whose window starts there -- one or two when upscaling -- are
+    // produced before the window slides.  The L2 prefetch runs 16 rows ahead of the ring.
+    uint64_t f0[NL], f1[NL], f2[NL];
+    uint32_t q[4][NL];
     float4 e = lds128(t.sched + 16u * t.y0);
-    auto fetch = [&](const float4& en) {
-      const int lo = __float_as_int(en.w);
+    const int base0 = __reduce_max_sync(0xffffffffu, __float_as_int(e.w));     // (warp-uniform, see mode 0)
+    const int hm1 = t.h - 1;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const uint32_t rr = (uint32_t)min(lo + k, t.h - 1);
+    for (int i = 0; i < NL; ++i) {
+      auto at = [&](int r) { return ldg_nc_u32(gl[i] + (uint64_t)((uint32_t)min(r, hm1) * rowb)); };
+      const uint32_t r0 = at(base0), r1 = at(base0 + 1), r2 = at(base0 + 2);
 #pragma unroll
-        for (int i = 0; i < NL; ++i) q[k][i] = ldg_nc_u32(gl[i] + (uint64_t)(rr * rowb));
-      }
-    };
-    fetch(e);
+      for (int k = 0; k < 4; ++k) q[k][i] = at(base0 + 3 + k);
+      f0[i] = conv_px<kWindow>(r0, wsc, wof);
+      f1[i] = conv_px<kWindow>(r1, wsc, wof);
+      f2[i] = conv_px<kWindow>(r2, wsc, wof);
+    }
+    uint64_t pfb;
+    bool pf_lane;
+    {
+      const uint64_t first = reinterpret_cast<uint64_t>(t.crop + t.ca);
+      const uint32_t head = (uint32_t)(first & 127u);
+      pf_lane = (uint32_t)(lane * 128) < head + 2u * (uint32_t)t.span;
+      pfb = first - head + (uint64_t)(lane * 128);
 #pragma unroll 1
-    for (int y = 0; y < t.nrows; ++y) {
-      uint64_t f[3][NL];
+      for (int r = base0 + 7; r < base0 + 23; ++r)
+        if (pf_lane && r <= hm1) asm volatile("prefetch.global.L2 [%0];" ::"l"(pfb + (uint64_t)((uint32_t)r * rowb)));
+    }
+    int y = 0;
+    int lo_e = base0;                                 // first source row of the pending output row
+    const int nrows = t.nrows;
+#pragma unroll 1
+    for (int b0 = base0; y < nrows; b0 += 4) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll 1
+        while (y < nrows && lo_e <= b0 + k) {          // (== by monotonicity; <= so that nothing can make the loop spin)
+          const uint64_t w0 = pack2(e.x, e.x), w1 = pack2(e.y, e.y), w2 = pack2(e.z, e.z);
+          ++y;
+          e = lds128(t.sched + 16u * (t.y0 + y));     // (the table is padded: reading one entry past the part is harmless)
 #pragma unroll
-        for (int i = 0; i < NL; ++i) f[k][i] = conv_px<kWindow>(q[k][i], wsc, wof);
-      const uint64_t w0 = pack2(e.x, e.x), w1 = pack2(e.y, e.y), w2 = pack2(e.z, e.z);
-      if (y + 1 < t.nrows) {
-        e = lds128(t.sched + 16u * (t.y0 + y + 1));
-        fetch(e);
+          for (int i = 0; i < NL; ++i) A[i] = ffma2(f2[i], w2, ffma2(f1[i], w1, ffma2(f0[i], w0, 0ull)));
+          hrow();
+          lo_e = __reduce_max_sync(0xffffffffu, __float_as_int(e.w));
+        }
+        const int rn = b0 + k + 7;                    // the ring slot is re-armed with the row four behind the newest
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+          f0[i] = f1[i];
+          f1[i] = f2[i];
+          f2[i] = conv_px<kWindow>(q[k][i], wsc, wof);
+          q[k][i] = ldg_nc_u32(gl[i] + (uint64_t)((uint32_t)min(rn, hm1) * rowb));
+        }
+        if (pf_lane && rn + 16 <= hm1) asm volatile("prefetch.global.L2 [%0];" ::"l"(pfb + (uint64_t)((uint32_t)(rn + 16) * rowb)));
       }
-#pragma unroll
-      for (int i = 0; i < NL; ++i) A[i] = ffma2(f[2][i], w2, ffma2(f[1][i], w1, ffma2(f[0][i], w0, 0ull)));
-      hrow();
     }
   } else {
     // ---- output-stationary, any window: the taps are recomputed per output row (warp-uniform arithmetic) --------
@@ -328,7 +409,78 @@ __device__ __forceinline__ float run_part(const Part& t) {
   return sum;
 }
 
-template <bool kWindow, int kMaxThreads, int kMinBlocks>
+// 8 pixels per lane from the parked tile: contrast / late brightness / normalise / flip, one 16-byte store (bf16)
+template <bool kFlip, bool kF32>
+__device__ __forceinline__ void store_tile(uint32_t tile, int nrows, int lane, int x0, int s, void* out_base,
+                                           size_t plane_row0, bool jitter, bool has_post, float cs, float cadd, float pb,
+                                           float mean, float inv_std) {
+  const int chunk = lane & 3, r0 = lane >> 2;
+  const int xs = x0 + 8 * chunk;
+  if (xs >= s) return;
+  const int col = kFlip ? (s - xs - 8) : xs;
+  uint32_t ta = tile + (uint32_t)(r0 * kTilePitch + 16 * chunk);
+  constexpr size_t esz = kF32 ? 4 : 2;
+  uint8_t* op = static_cast<uint8_t*>(out_base) + ((plane_row0 + r0) * (size_t)s + col) * esz;
+  const size_t step = (size_t)8 * s * esz;
+  const uint64_t nmagic = pack2(-kMagic, -kMagic);
+  const uint64_t nmean = pack2(-mean, -mean), istd = pack2(inv_std, inv_std);
+  const uint64_t unit = pack2(1.f / 65535.f, 1.f / 65535.f);
+#pragma unroll 1
+  for (int row = r0; row < nrows; row += 8, ta += 8 * kTilePitch, op += step) {
+    const uint4 q = lds128u(ta);
+    const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+    uint64_t u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t lo = __byte_perm(qq[i], 0x4B000000u, 0x7610);
+      const uint32_t hi = __byte_perm(qq[i], 0x4B000000u, 0x7632);
+      u[i] = fadd2(pack2(__uint_as_float(lo), __uint_as_float(hi)), nmagic);
+    }
+    if (jitter) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a, b;
+        unpack2(u[i], a, b);
+        a = __saturatef(fmaf(a, cs, cadd));
+        b = __saturatef(fmaf(b, cs, cadd));
+        if (has_post) {
+          a = __saturatef(a * pb);
+          b = __saturatef(b * pb);
+        }
+        u[i] = pack2(a, b);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) u[i] = fmul2(u[i], unit);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = fmul2(fadd2(u[i], nmean), istd);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) unpack2(u[i], v[2 * i], v[2 * i + 1]);
+    if (kF32) {
+      float4* dst = reinterpret_cast<float4*>(op);
+      if (!kFlip) {
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+        dst[0] = make_float4(v[7], v[6], v[5], v[4]);
+        dst[1] = make_float4(v[3], v[2], v[1], v[0]);
+      }
+    } else {
+      uint32_t pk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = kFlip ? __floats2bfloat162_rn(v[7 - 2 * i], v[6 - 2 * i])
+                                       : __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+template <bool kWindow, int kMaxThreads, int kMinBlocks, bool kDbl, int kW>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) aug_strip_kernel(const __grid_constant__ StripArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -401,7 +553,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) aug_strip_kernel(cons
     }
     // stream bounds of the parts (the table above is recycled as tile storage once the first warp parks a row)
     const int py = tid / a.rp;
-    if (tid == py * a.rp) misc.part_lo[py] = lo;
+    if (tid == py * a.rp) {
+      misc.part_lo[py] = lo;
+      misc.part_e0[py] = lo + size;
+    }
     if (tid == min(s, (py + 1) * a.rp) - 1) misc.part_end[py] = lo + size;
   }
 
@@ -412,8 +567,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) aug_strip_kernel(cons
   t.sched = smem_u32(sched);
   t.fmask = smem_u32(fmask);
   t.rowbuf = a.rowbuf;
-  t.toggle = a.dbl ? 4u * (uint32_t)a.rowbuf : 0u;
-  t.row = smem_u32(smem + a.off_row) + (uint32_t)warp * (a.dbl ? 8u : 4u) * (uint32_t)a.rowbuf;
+  t.row = smem_u32(smem + a.off_row) + (uint32_t)warp * (kDbl ? 8u : 4u) * (uint32_t)a.rowbuf;
   t.tile = smem_u32(smem) + (uint32_t)warp * (uint32_t)(a.rp * kTilePitch);
   t.crop = a.src + e0;
   t.W = a.W;
@@ -421,6 +575,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) aug_strip_kernel(cons
   t.lane = lane;
   t.y0 = y0;
   t.nrows = nrows;
+  t.rp = a.rp;
   t.hinv = hinv;
   t.vscale = vscale;
   t.vsup = vsup;
@@ -449,6 +604,28 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) aug_strip_kernel(cons
     t.hlo = lo;
     t.hsize = (x < s) ? size : 0;
     t.hctr = ctr;
+  }
+
+  // ---- the strip's staged span (from the 4-byte aligned column at or before its first window) and class ---------
+  const int c_lo = __shfl_sync(0xffffffffu, t.hlo, 0);
+  t.ca = c_lo - (int)((e0 + c_lo) & 1);
+  t.span = __reduce_max_sync(0xffffffffu, t.hsize > 0 ? t.hlo + t.hsize : 0) - t.ca;
+  const int need = __reduce_max_sync(0xffffffffu, t.hsize > 0 ? ((t.hlo - t.ca) & 3) + t.hsize : 0);
+  // pull the first 16 rows of this warp's stream towards L2 while the tables are built (lane = row, 128-byte line)
+  if (nrows > 0) {
+    int lo, hi;
+    float ctr;
+    aa_window(y0, P.h, vscale, vsup, lo, hi, ctr);
+    const uint64_t first = reinterpret_cast<uint64_t>(t.crop + t.ca);
+    const uint32_t head = (uint32_t)(first & 127u);
+    const int line = lane & 3;
+    if ((uint32_t)(line * 128) < head + 2u * (uint32_t)t.span) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int r = (vdown ? (lo & ~7) : lo) + (lane >> 2) + 8 * j;
+        if (r < P.h) asm volatile("prefetch.global.L2 [%0];" ::"l"(first - head + (uint64_t)((uint32_t)r * 2u * (uint32_t)a.W) + (uint64_t)(line * 128)));
+      }
+    }
   }
 
   __syncthreads();                                  // tap table complete
@@ -496,22 +673,17 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) aug_strip_kernel(cons
     }
   }
 
-  // ---- the strip's staged span (from the 4-byte aligned column at or before its first window) and class ---------
-  const int c_lo = __shfl_sync(0xffffffffu, t.hlo, 0);
-  t.ca = c_lo - (int)((e0 + c_lo) & 1);
-  t.span = __reduce_max_sync(0xffffffffu, t.hsize > 0 ? t.hlo + t.hsize : 0) - t.ca;
-  const int need = __reduce_max_sync(0xffffffffu, t.hsize > 0 ? ((t.hlo - t.ca) & 3) + t.hsize : 0);
-
   __syncthreads();                                  // schedule complete; vw / vinfo are dead from here on
   t.mode = !vdown ? 1 : (misc.m_max <= 3 ? 0 : 2);
   t.r_lo = misc.part_lo[sy];
   t.r_end = misc.part_end[sy];
+  t.r_e0 = misc.part_e0[sy];
 
   float sum = 0.f;
   if (nrows > 0) {
-    if (t.span <= 64 && need <= 8) sum = run_part<1, 2, kWindow>(t);
-    else if (t.span <= 128 && need <= 12) sum = run_part<2, 3, kWindow>(t);
-    else sum = run_part<3, 4, kWindow>(t);
+    if (t.span <= 64 && need <= 8) sum = run_part<1, 2, kWindow, kDbl, kW>(t);
+    else if (t.span <= 128 && need <= 12) sum = run_part<2, 3, kWindow, kDbl, kW>(t);
+    else sum = run_part<3, 4, kWindow, kDbl, kW>(t);
   }
 
   // ================================ contrast mean over the view ===========================================
@@ -534,6 +706,19 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) aug_strip_kernel(cons
   const bool flip = (P.flags & MIS_VIEW_FLIP) != 0;
   const float pb = P.brightness;
   const float cs = cf * (1.f / 65535.f);
+  if ((s & 7) == 0) {
+    const size_t prow0 = (size_t)plane * s + y0;
+    const bool f32 = a.out_f32 != 0;
+    if (!f32) {
+      if (flip) store_tile<true, false>(t.tile, nrows, lane, x0, s, a.out, prow0, jitter, has_post, cs, cadd, pb, mean, inv_std);
+      else store_tile<false, false>(t.tile, nrows, lane, x0, s, a.out, prow0, jitter, has_post, cs, cadd, pb, mean, inv_std);
+    } else {
+      if (flip) store_tile<true, true>(t.tile, nrows, lane, x0, s, a.out, prow0, jitter, has_post, cs, cadd, pb, mean, inv_std);
+      else store_tile<false, true>(t.tile, nrows, lane, x0, s, a.out, prow0, jitter, has_post, cs, cadd, pb, mean, inv_std);
+    }
+    return;
+  }
+  // crop sizes that are not a multiple of 8: element-wise stores
   const uint64_t nmagic = pack2(-kMagic, -kMagic);
   const int iters = (nrows + 7) >> 3;
 #pragma unroll 1
@@ -638,14 +823,24 @@ bool strip_supported(int C, int H, int W, int64_t img_stride, int s) {
   return make_plan(H, W, s, &p);
 }
 
-template <bool kWindow, int kMaxThreads, int kMinBlocks>
+template <bool kWindow, int kMaxThreads, int kMinBlocks, bool kDbl, int kW>
 static int launch_one(const StripArgs& a, int n_planes, const Plan& p, cudaStream_t stream) {
-  auto* fn = &aug_strip_kernel<kWindow, kMaxThreads, kMinBlocks>;
+  auto* fn = &aug_strip_kernel<kWindow, kMaxThreads, kMinBlocks, kDbl, kW>;
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   fn<<<dim3((unsigned)n_planes), dim3((unsigned)p.threads), p.smem, stream>>>(a);
   MIS_CUDA_TRY(cudaGetLastError());
   return MIS_OK;
+}
+template <bool kWindow, int kMaxThreads, int kMinBlocks>
+static int launch_shape(const StripArgs& a, int n_planes, const Plan& p, cudaStream_t stream) {
+  // the row pitch of the common 512-wide slice is a compile-time constant of the hot loop (load offsets become
+  // immediates); any other width takes the generic instantiation
+  if (a.W == 512)
+    return p.dbl ? launch_one<kWindow, kMaxThreads, kMinBlocks, true, 512>(a, n_planes, p, stream)
+                 : launch_one<kWindow, kMaxThreads, kMinBlocks, false, 512>(a, n_planes, p, stream);
+  return p.dbl ? launch_one<kWindow, kMaxThreads, kMinBlocks, true, 0>(a, n_planes, p, stream)
+               : launch_one<kWindow, kMaxThreads, kMinBlocks, false, 0>(a, n_planes, p, stream);
 }
 
 int launch_strip(StripArgs a, int n_views, bool window, cudaStream_t stream) {
@@ -655,8 +850,8 @@ int launch_strip(StripArgs a, int n_views, bool window, cudaStream_t stream) {
   a.nsx = p.nsx; a.nsy = p.nsy; a.rp = p.rp; a.rowbuf = p.rowbuf; a.dbl = p.dbl;
   a.off_sched = p.off_sched; a.off_fmask = p.off_fmask; a.off_row = p.off_row; a.off_misc = p.off_misc;
   const int n_planes = n_views * a.C;
-  if (p.big) return window ? launch_one<true, 1024, 1>(a, n_planes, p, stream) : launch_one<false, 1024, 1>(a, n_planes, p, stream);
-  return window ? launch_one<true, 448, 2>(a, n_planes, p, stream) : launch_one<false, 448, 2>(a, n_planes, p, stream);
+  if (p.big) return window ? launch_shape<true, 1024, 1>(a, n_planes, p, stream) : launch_shape<false, 1024, 1>(a, n_planes, p, stream);
+  return window ? launch_shape<true, 448, 2>(a, n_planes, p, stream) : launch_shape<false, 448, 2>(a, n_planes, p, stream);
 }
 
 }  // namespace augs
