@@ -158,7 +158,8 @@ int64_t mis_aug_algorithmic_bytes(const MisViewParams* params_host, int n_views,
  *                     container) and rinv = 1/max(|z|,1e-12).  u is what gets all-gathered.
  *   mis_ntxent_fwd    lse_i = log sum_{j != g(i)} exp(<u_i,u_j>/T) over all `cols` columns (tcgen05
  *                     kind::tf32, accumulators in TMEM; S never leaves the SM);
- *                     loss[0] = mean_i (lse_i - <u_i,u_p(i)>/T) over the local rows.
+ *                     loss[0] = mean_i (lse_i - <u_i,u_p(i)>/T) over the local rows.  One kernel launch: the
+ *                     last CTA of every row tile finishes its rows, the last CTA of the launch the mean.
  *   mis_ntxent_bwd    dz_local = grad_out[0] * grad_scale * sum_r' dL_r'/dz_local  (SURVEY A.5,
  *                     option L: uses the all-gathered lse instead of a D-wide gradient exchange).
  *                     S is recomputed tile by tile; W = P + P^T is rounded to TF32 and stays in
@@ -182,46 +183,41 @@ int mis_ntxent_bwd(const float* u_all, const float* lse_all, const void* z_rows,
                    int64_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * NT-Xent exchange over NVLink peer memory (one node, world <= 8): the two all-gathers of the loss
- * (normalised rows in the forward, log-sum-exp scalars for the backward; reference template:
- * concat_all_gather, train/callback/knn.py:143-144) fused into the kernels that PRODUCE the data.
+ * NT-Xent over NVLink peer memory (one node, 2 <= world <= 8): the two all-gathers of the loss (normalised rows in the
+ * forward, log-sum-exp scalars for the backward; reference template: concat_all_gather, train/callback/knn.py:143-144)
+ * are fused into the kernels that PRODUCE the data, and the kernels that CONSUME it wait for it themselves.
  * Every rank passes the same-shaped buffers of all ranks (peer pointers of one symmetric allocation):
  *
- *   u_all_peers[r]   rank r's gathered matrix [world*rows, D] f32  (this epoch's buffer)
- *   lse_all_peers[r] rank r's gathered lse [world*rows] f32        (this epoch's buffer)
- *   flag_peers[r]    rank r's flag block: uint32 [2][8] flags (slot 0: rows, slot 1: lse; entry = source
- *                    rank, value = epoch), then 2 producer counters and 1 timeout word; zeroed once
+ *   u_peers0/1[r]    rank r's gathered matrix [world*rows, D] f32, buffer parity 0 / 1
+ *   lse_peers0/1[r]  rank r's gathered lse [world*rows] f32, buffer parity 0 / 1
+ *   ctl_peers[r]     rank r's control block (256 bytes, zeroed once): uint32 flag[2][8] (slot 0: rows, slot 1: lse;
+ *                    entry = source rank, value = epoch), producer counter, EPOCH (forwards completed on that rank),
+ *                    abort word
  *
- * mis_ntxent_prep_gather   prep + store of the local rows into every rank's matrix at row rank*rows, then
- *                          flag[0][rank] = epoch on every rank (st.release.sys by the last CTA)
- * mis_ntxent_fwd_gather    forward over the local copy of the gathered matrix; lse rows are stored into every
- *                          rank's lse vector, then flag[1][rank] = epoch
- * mis_peer_wait            enqueue a one-warp kernel that returns once flag[slot][r] >= epoch for all r < world
- *                          (acquire loads; gives up after ~2 s and sets the timeout word instead of hanging)
- * `epoch` increases by one per loss evaluation on every rank; buffers alternate with its parity, which is
- * enough to make reuse safe (a rank reaches epoch k+1 only after every peer finished epoch k-1).
+ * forward  = prep kernel (normalise, round to TF32, store the local rows into every rank's matrix, raise
+ *            flag[0][rank] on every rank) + ONE tile kernel: its TMA producers wait per column tile for the flag of the
+ *            rank that owns those rows (tiles are walked starting at the local rows), the last CTA of every row tile
+ *            forms lse / positives / row losses and stores the lse rows into every rank's vector, the last CTA of the
+ *            launch forms the mean loss, raises flag[1][rank] on every rank and publishes the epoch.
+ * backward = transpose + ONE tile kernel (D <= 256): its epilogue warps wait once for the lse flags of all ranks (S tiles
+ *            are already being computed meanwhile); the last CTA of every row tile applies the normalisation Jacobian.
+ * Epoch and buffer parity are read from the DEVICE-side counter, so both calls can be captured into CUDA graphs and
+ * replayed.  Buffers alternate with the epoch's parity; that is sufficient for safe reuse as long as a rank's backward of
+ * epoch k is enqueued before its forward of epoch k+1 (one evaluation outstanding -- loss.py enforces it).
+ * A consumer waits `timeout_s` seconds for a peer's flag; after that the kernel sets the abort word and TRAPS (the step
+ * fails with a CUDA error instead of continuing on stale rows).  Use a time-out of the order of the NCCL watchdog's.
+ * rows a multiple of 128 (at most 414 * 128 per rank), D as for mis_ntxent_fwd / mis_ntxent_bwd.
  * ------------------------------------------------------------------------------------------ */
-int mis_ntxent_prep_gather(const void* z, int z_dtype, int rows, int D, int world, int rank,
-                           void* const* u_all_peers, float* rinv, void* const* flag_peers, uint32_t epoch,
-                           void* stream);
-
-int mis_ntxent_fwd_gather(const float* u_all, int cols, int D, int rows, float inv_T, int world, int rank,
-                          void* const* lse_all_peers, void* const* flag_peers, uint32_t epoch, float* loss,
-                          void* scratch, int64_t scratch_bytes, void* stream);
-
-int mis_peer_wait(const void* flags_local, int slot, int world, uint32_t epoch, void* stream);
-
-/* The same three / two steps as one call per autograd phase (what loss.py uses): forward = prep_gather, wait for the
- * rows of all ranks, fwd_gather; backward = wait for the lse of all ranks, mis_ntxent_bwd over the local copies. */
 int mis_ntxent_fwd_peer(const void* z, int z_dtype, int rows, int D, float inv_T, int world, int rank,
-                        void* const* u_all_peers, void* const* lse_all_peers, void* const* flag_peers,
-                        uint32_t epoch, float* rinv, float* loss, void* scratch, int64_t scratch_bytes,
-                        void* stream);
+                        void* const* u_peers0, void* const* u_peers1, void* const* lse_peers0,
+                        void* const* lse_peers1, void* const* ctl_peers, double timeout_s, float* rinv,
+                        float* loss, void* scratch, int64_t scratch_bytes, void* stream);
 
-int mis_ntxent_bwd_peer(const float* u_all, const float* lse_all, const void* z_rows, int z_dtype,
-                        const float* rinv_rows, int D, int rows, float inv_T, float grad_scale,
-                        const float* grad_out, void* dz, int world, int rank, const void* flags_local,
-                        uint32_t epoch, void* scratch, int64_t scratch_bytes, void* stream);
+int mis_ntxent_bwd_peer(const void* z_rows, int z_dtype, const float* rinv_rows, int rows, int D, float inv_T,
+                        float grad_scale, const float* grad_out, void* dz, int world, int rank,
+                        void* const* u_peers0, void* const* u_peers1, void* const* lse_peers0,
+                        void* const* lse_peers1, void* const* ctl_peers, double timeout_s, void* scratch,
+                        int64_t scratch_bytes, void* stream);
 
 /* Single-rank NT-Xent (cols == rows, row0 == 0): prep, forward and backward with grad_out = 1 in ONE call --
  * the loss slot of byol_pytorch.py:217 when no cross-GPU gather is involved.  loss[0] and dz (z's dtype) are the

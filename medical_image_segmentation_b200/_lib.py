@@ -47,17 +47,12 @@ EXPORTS = {
     "mis_ntxent_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                  C.c_void_p]),
-    "mis_ntxent_prep_gather": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                         C.c_void_p, C.c_uint32, C.c_void_p]),
-    "mis_ntxent_fwd_gather": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p,
-                                        C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    "mis_peer_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p]),
     "mis_ntxent_fwd_peer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p,
-                                      C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                      C.c_void_p]),
-    "mis_ntxent_bwd_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
-                                      C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int64, C.c_void_p]),
+    "mis_ntxent_bwd_peer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_double, C.c_void_p, C.c_int64, C.c_void_p]),
     "mis_ntxent_fwd_bwd_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "mis_ntxent_fwd_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p]),

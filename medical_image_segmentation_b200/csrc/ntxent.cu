@@ -46,14 +46,53 @@ constexpr int kTmemCols = 512;
 constexpr int kDuCol = 256;            // TMEM column where the dU accumulator starts
 constexpr float kLog2e = 1.4426950408889634f;
 
+constexpr int kMaxPeers = 8;
+
+// Control block at the start of every rank's symmetric (peer-mapped) buffer.  flag[slot][r] = epoch is raised by
+// rank r (st.release.sys) when its rows (slot 0) / log-sum-exp scalars (slot 1) of that epoch have landed here.
+struct PeerCtl {
+  uint32_t flag[2][kMaxPeers];
+  uint32_t prep_counter;     // CTAs of the prep kernel that have finished (self-resetting)
+  uint32_t epoch;            // forwards completed on this rank: kernels derive epoch and buffer parity from it, so
+                             // a captured CUDA graph needs no host-side value
+  uint32_t abort;            // set before a kernel traps on a peer time-out
+  uint32_t pad;
+};
+
+// what the last CTA of a row tile needs to finish the rows (the former fwd_rows / bwd_finalize kernels)
+struct Finish {
+  unsigned int* counters;    // [row_tiles] arrivals per row tile, then [1] finished row tiles; zero on entry, left zero
+  int fold;                  // 0: partials only (backward of D > 256: a separate finalize kernel follows)
+  // forward
+  const float* u_all[2];     // per parity: gathered matrix (positives)
+  float* lse_dst[2][kMaxPeers];  // per parity, per rank: gathered lse vector (dst[.][rank] is the local copy)
+  int lse_off;               // row offset of this rank inside the gathered vectors
+  float* row_loss;           // [rows] scratch
+  float* loss;               // [1]
+  // backward
+  const void* z_rows;
+  const float* rinv;
+  void* dz;
+  int z_bf16;
+  float scale;               // grad_scale / (T * rows)
+  const float* grad_out;     // may be null (= 1)
+};
+
 struct TileArgs {
   int rows, cols, D, row0;
   int col_tiles, tiles_per_split;
   float k1;                // log2(e) / T
   int d0, ds;              // backward: columns [d0, d0 + ds) of dU are produced by this launch (ds <= 256)
-  const float* lse;        // [cols] all-gathered log-sum-exp (backward): c_j = exp(1/T - lse_j) is formed on the fly
+  const float* lse[2];     // per parity: [cols] all-gathered log-sum-exp (backward): c_j = exp(1/T - lse_j) on the fly
   float inv_T;
   float* partial;          // fwd: [nsplit][rows]   bwd: [nsplit][rows][D]
+  // multi-rank exchange (world == 1: ctl == nullptr, parity 0)
+  PeerCtl* ctl;            // local control block
+  PeerCtl* ctl_peers[kMaxPeers];
+  int world, rank, rows_per_rank;
+  int epoch_add;           // forward: 1 (the epoch being produced), backward: 0 (the epoch completed last)
+  long long timeout_clk;   // SM clocks a consumer waits for a peer before it traps
+  Finish fin;
 };
 
 struct Bars {
@@ -152,10 +191,35 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   return y;
 }
 
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Wait until a peer has raised `*f` to `epoch`.  A peer that is merely late (checkpointing, a data-loader stall) is
+// waited for like NCCL would; after `timeout_clk` SM clocks the rank is declared dead: the kernel records it in
+// ctl->abort and TRAPS, so the step fails with a CUDA error instead of continuing on stale rows.
+__device__ __forceinline__ void wait_peer_flag(const uint32_t* f, uint32_t epoch, long long timeout_clk, uint32_t* abort) {
+  if ((int32_t)(ld_acquire_sys(f) - epoch) >= 0) return;
+  const long long t0 = clock64();
+  while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+    __nanosleep(100);
+    if (clock64() - t0 > timeout_clk) {
+      *abort = 1u;
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ float ldcg_f32(const float* p) { return __ldcg(p); }
+
 template <bool kBwd>
 __global__ void __launch_bounds__(kThreads, 1)
-ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_ut,
-                   const TileArgs a) {
+ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_constant__ CUtensorMap map_u1,
+                   const __grid_constant__ CUtensorMap map_ut, const __grid_constant__ TileArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Bars& bars = *reinterpret_cast<Bars*>(smem + kRingBytes);
@@ -178,9 +242,19 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
   const int T = min(a.tiles_per_split, a.col_tiles - t_begin);
   const int KB = a.D / kKBlock;
   const int g_row_tile0 = a.row0 + row_tile * kTile;   // global row index of this tile's first row
+  // epoch / buffer parity of this evaluation (single rank: one buffer, nothing to wait for)
+  const uint32_t epoch = a.ctl ? a.ctl->epoch + (uint32_t)a.epoch_add : 0u;
+  const int par = (int)(epoch & 1u);
+  const CUtensorMap* const map_u = par ? &map_u1 : &map_u0;
+  // column tiles are walked starting at this rank's own rows, so the tiles of late peers come last
+  const int rot = a.world > 1 ? (a.rank * a.rows_per_rank) / kTile : 0;
+  auto col_tile = [&](int t) {
+    int c = t_begin + t + rot;
+    return c >= a.col_tiles ? c - a.col_tiles : c;
+  };
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&map_u);
+    prefetch_tmap(map_u);
     if (kBwd) prefetch_tmap(&map_ut);
   }
   if (warp == 1) {
@@ -226,22 +300,34 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
       if (res_a) {    // resident row tile, loaded once
         if (pidx == 0) mbar_arrive_expect_tx(&bars.a_full, (uint32_t)KB * kTile * 128);
         for (int kb = pidx; kb < KB; kb += kProducers)
-          tma_load_2d(smem_a + kb * kTile * 128, &map_u, kb * kKBlock, g_row_tile0, &bars.a_full);
+          tma_load_2d(smem_a + kb * kTile * 128, map_u, kb * kKBlock, g_row_tile0, &bars.a_full);
       }
+      // forward of a multi-rank evaluation: the rows of rank r are complete once flag[0][r] carries this epoch
+      // (written by r's prep kernel over NVLink); every producer thread checks before its first box of that rank
+      uint32_t ready = (!kBwd && a.world > 1) ? (1u << a.rank) : 0xffffffffu;
       auto push_s = [&](int t) {   // operands of S = U_I . U_J^T
+        const int ct = col_tile(t);
+        if (!kBwd && a.world > 1) {
+          const int r = (ct * kTile) / a.rows_per_rank;
+          if (!((ready >> r) & 1u)) {
+            wait_peer_flag(&a.ctl->flag[0][r], epoch, a.timeout_clk, &a.ctl->abort);
+            asm volatile("fence.proxy.async.global;" ::: "memory");   // peer stores (generic proxy) before TMA reads
+            ready |= 1u << r;
+          }
+        }
         for (int kb = 0; kb < KB; kb += kps_s) {
           mbar_wait(&bars.empty[stage], phase ^ 1);
           uint8_t* sa = ring + stage * kStageBytes;
           if (res_a) {             // the whole U_J tile in one stage, one box per producer
             if (pidx == 0) mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)KB * kTile * 128);
             for (int k2 = pidx; k2 < KB; k2 += kProducers)
-              tma_load_2d(sa + k2 * kTile * 128, &map_u, k2 * kKBlock, (t_begin + t) * kTile, &bars.full[stage]);
+              tma_load_2d(sa + k2 * kTile * 128, map_u, k2 * kKBlock, ct * kTile, &bars.full[stage]);
           } else {
             if (pidx == 0) {
               mbar_arrive_expect_tx(&bars.full[stage], 2 * kTile * 128);
-              tma_load_2d(sa, &map_u, kb * kKBlock, g_row_tile0, &bars.full[stage]);
+              tma_load_2d(sa, map_u, kb * kKBlock, g_row_tile0, &bars.full[stage]);
             } else if (pidx == 1) {
-              tma_load_2d(sa + kTile * 128, &map_u, kb * kKBlock, (t_begin + t) * kTile, &bars.full[stage]);
+              tma_load_2d(sa + kTile * 128, map_u, kb * kKBlock, ct * kTile, &bars.full[stage]);
             }
           }
           advance();
@@ -253,7 +339,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
           uint8_t* sa = ring + stage * kStageBytes;
           if (pidx == 0) mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)kps_g * a.ds * 128);
           for (int k2 = pidx; k2 < kps_g; k2 += kProducers)
-            tma_load_2d(sa + k2 * a.ds * 128, &map_ut, (t_begin + t) * kTile + (kb + k2) * kKBlock, a.d0, &bars.full[stage]);
+            tma_load_2d(sa + k2 * a.ds * 128, &map_ut, col_tile(t) * kTile + (kb + k2) * kKBlock, a.d0, &bars.full[stage]);
           advance();
         }
       };
@@ -335,17 +421,24 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
     const int r_in = quad * 32 + lane;               // row inside the tile == TMEM lane
     const int etid = (tid - 64) & 127;
     const uint32_t tlane = (uint32_t)(quad * 32) << 16;
-    const float ci = kBwd ? __expf(a.inv_T - a.lse[g_row_tile0 + r_in]) : 0.f;
+    const float* const lse_all = a.lse[par];
+    if (kBwd && a.world > 1) {
+      // the log-sum-exp scalars of rank r are complete once flag[1][r] carries this epoch (stored over NVLink by the
+      // last CTAs of r's forward); S tiles are already being computed while this group waits
+      if (etid < a.world && etid != a.rank) wait_peer_flag(&a.ctl->flag[1][etid], epoch, a.timeout_clk, &a.ctl->abort);
+      bar_sync(2 + grp, kEpiThreads);
+    }
+    const float ci = kBwd ? __expf(a.inv_T - lse_all[g_row_tile0 + r_in]) : 0.f;
     const float k1 = a.k1;
     const int il = row_tile * kTile + r_in;                       // local row index
     const int pos_col = a.row0 + (il + (a.rows >> 1)) % a.rows;   // global column of this row's positive
     float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;         // independent partial sums: no serial FADD chain
     for (int t = grp; t < T; t += 2) {
       const int buf = grp;
-      const int col0 = (t_begin + t) * kTile;
+      const int col0 = col_tile(t) * kTile;
       if (kBwd) {
         bar_sync(2 + grp, kEpiThreads);                         // previous tile's readers of cj[buf] are done
-        bars.cj[buf][etid] = __expf(a.inv_T - a.lse[col0 + etid]);
+        bars.cj[buf][etid] = __expf(a.inv_T - lse_all[col0 + etid]);
         bar_sync(2 + grp, kEpiThreads);
       }
       mbar_wait(&bars.tmem_full[buf], (t >> 1) & 1);
@@ -397,6 +490,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
     if (!kBwd) {
       // each group writes its own partial row sums: partial[(2*split + grp)][row]
       a.partial[(size_t)(2 * split + grp) * a.rows + row_tile * kTile + r_in] = (rs0 + rs1) + (rs2 + rs3);
+      __threadfence();
     } else {
       mbar_wait(&bars.du_full, 0);
       tc_fence_after();
@@ -409,6 +503,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
         for (int j = 0; j < 8; ++j)
           reinterpret_cast<uint4*>(dst + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
+      __threadfence();
     }
   }
 
@@ -416,6 +511,93 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_const
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+
+  // ===================== the last CTA of a row tile finishes its rows (no separate kernel) =====================
+  const Finish& fin = a.fin;
+  if (!fin.fold) return;
+  __shared__ int s_flag;
+  __shared__ float s_red[kThreads / 32];
+  if (tid == 0) {
+    __threadfence();
+    s_flag = atomicAdd(&fin.counters[row_tile], 1u) == gridDim.y - 1;
+  }
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  const int nsplit = (int)gridDim.y;
+  const int row_tiles = (int)gridDim.x;
+  if (!kBwd) {
+    // lse_i = 1/T + log(sum of the split partials); pos_i = <u_i, u_p(i)> / T; row loss = lse_i - pos_i (warp per row)
+    const float* u_all = fin.u_all[par];
+    for (int r = warp; r < kTile; r += kThreads / 32) {
+      const int i = row_tile * kTile + r;
+      float sacc = 0.f;
+      for (int k = lane; k < 2 * nsplit; k += 32) sacc += ldcg_f32(a.partial + (size_t)k * a.rows + i);
+      sacc = warp_sum(sacc);
+      const float lse = a.inv_T + logf(sacc);
+      const float* ui = u_all + (size_t)(a.row0 + i) * a.D;
+      const float* up = u_all + (size_t)(a.row0 + (i + (a.rows >> 1)) % a.rows) * a.D;
+      float dot = 0.f;
+      for (int d = lane; d < a.D; d += 32) dot = fmaf(ui[d], up[d], dot);
+      dot = warp_sum(dot);
+      if (lane == 0) {
+        for (int q = 0; q < a.world; ++q) fin.lse_dst[par][q][fin.lse_off + i] = lse;    // every rank's gathered lse
+        fin.row_loss[i] = lse - dot * a.inv_T;
+      }
+    }
+  } else {
+    // dz_i = (dU_i - u_i <u_i,dU_i>) * rinv_i with dU_i = scale * sum of the split partials (the -2 u_p(i) one-hot term
+    // is already inside W); warp per row
+    const float g = fin.scale * (fin.grad_out ? fin.grad_out[0] : 1.f);
+    for (int r = warp; r < kTile; r += kThreads / 32) {
+      const int i = row_tile * kTile + r;
+      const float rv = fin.rinv[i];
+      auto z_at = [&](int d) {
+        return fin.z_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(fin.z_rows)[(size_t)i * a.D + d])
+                          : static_cast<const float*>(fin.z_rows)[(size_t)i * a.D + d];
+      };
+      auto du_at = [&](int d) {
+        float sacc = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp) sacc += ldcg_f32(a.partial + ((size_t)sp * a.rows + i) * a.D + d);
+        return g * sacc;
+      };
+      float dot = 0.f;
+      for (int d = lane; d < a.D; d += 32) dot = fmaf(z_at(d) * rv, du_at(d), dot);
+      dot = warp_sum(dot);
+      for (int d = lane; d < a.D; d += 32) {
+        const float v = (du_at(d) - z_at(d) * rv * dot) * rv;
+        if (fin.z_bf16) static_cast<__nv_bfloat16*>(fin.dz)[(size_t)i * a.D + d] = __float2bfloat16_rn(v);
+        else static_cast<float*>(fin.dz)[(size_t)i * a.D + d] = v;
+      }
+    }
+  }
+  // ---- the CTA that finishes the last row tile: mean loss, lse flags to every rank, epoch, counters back to zero ----
+  if (a.world > 1 && !kBwd) __threadfence_system();
+  else __threadfence();
+  __syncthreads();
+  if (tid == 0) s_flag = atomicAdd(&fin.counters[row_tiles], 1u) == (unsigned)row_tiles - 1;
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  if (!kBwd) {
+    float acc = 0.f;
+    for (int r = tid; r < a.rows; r += kThreads) acc += ldcg_f32(fin.row_loss + r);   // fixed order: deterministic
+    acc = warp_sum(acc);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < kThreads / 32; ++w) tot += s_red[w];
+      fin.loss[0] = tot / (float)a.rows;
+    }
+  }
+  if (tid <= row_tiles) fin.counters[tid] = 0u;          // (row_tiles < kThreads is checked on the host)
+  if (tid == 0 && a.ctl && !kBwd) {
+    __threadfence_system();
+    for (int q = 0; q < a.world; ++q)
+      if (a.world > 1) st_release_sys(&a.ctl_peers[q]->flag[1][a.rank], epoch);
+    a.ctl->epoch = epoch;                                // this forward is complete: the backward reads it back
   }
 }
 
@@ -428,61 +610,25 @@ template <>
 __device__ __forceinline__ float load_as_f32<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) { return __bfloat162float(p[i]); }
 
 // ---- peer-memory exchange (NVLink stores, no NCCL call on the data path) --------------------------------------------
-// A producer kernel writes its rows straight into the same buffer of EVERY rank of the node (peer pointers from CUDA
-// IPC / symmetric memory; dst[rank] is the local copy) and its last CTA raises flag[slot][rank] = epoch in every
-// rank's flag array with a system-scope release; consumers wait for all `world` flags with acquire loads
-// (peer_wait_kernel).  world == 1 degenerates to a plain local store with no signalling.
-constexpr int kMaxPeers = 8;
-struct Peers {
-  float* dst[kMaxPeers];        // per rank: destination buffer (all-gathered layout)
-  uint32_t* flag[kMaxPeers];    // per rank: flag array [2][kMaxPeers]; null when world == 1
-  int world, rank, slot;
-  uint32_t epoch;
-  unsigned int* counter;        // local: CTAs of the producer kernel that have finished (self-resetting)
+// A producer writes its rows straight into the same buffer of EVERY rank of the node (peer pointers of one symmetric
+// allocation; dst[rank] is the local copy) and its last CTA raises flag[slot][rank] = epoch in every rank's control
+// block with a system-scope release; the CONSUMING tile kernels wait for the flags themselves (wait_peer_flag: the
+// forward's TMA producers per column tile, the backward's epilogue warps once).  Epoch and buffer parity come from the
+// device-side counter PeerCtl::epoch.  world == 1 degenerates to a plain local store with no signalling.
+struct PrepPeers {
+  float* dst[2][kMaxPeers];     // per parity, per rank: gathered matrix
+  PeerCtl* ctl[kMaxPeers];      // per rank: control block; ctl[rank] is local; null when world == 1
+  int world, rank;
 };
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// called by every thread of every CTA after its peer stores; the last CTA to arrive signals all ranks
-__device__ __forceinline__ void peers_signal(const Peers& pe) {
-  if (pe.world <= 1) return;
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int total = gridDim.x * gridDim.y;
-    if (atomicAdd(pe.counter, 1u) == total - 1) {
-      __threadfence_system();
-      *pe.counter = 0u;
-      for (int r = 0; r < pe.world; ++r) st_release_sys(pe.flag[r] + pe.slot * kMaxPeers + pe.rank, pe.epoch);
-    }
-  }
-}
-// one warp: lane r < world waits until rank r has raised flag[slot][r] to `epoch` (bounded: ~2 s, then *timeout = 1)
-__global__ void peer_wait_kernel(const uint32_t* flags, int slot, int world, uint32_t epoch, uint32_t* timeout) {
-  const int r = threadIdx.x;
-  if (r < world) {
-    const uint32_t* f = flags + slot * kMaxPeers + r;
-    long long spins = 0;
-    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-      __nanosleep(200);
-      if (++spins > 10000000ll) {
-        *timeout = 1u;
-        break;
-      }
-    }
-  }
-}
 
 // one warp per row: rinv = 1/max(|z|,1e-12), u = tf32(z * rinv), written to every rank's gathered matrix at row row0 + i
 template <typename T>
-__global__ void prep_kernel(const T* __restrict__ z, int rows, int D, int row0, float* __restrict__ rinv, const Peers pe) {
+__global__ void prep_kernel(const T* __restrict__ z, int rows, int D, int row0, float* __restrict__ rinv, const PrepPeers pe) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  PeerCtl* const ctl = pe.world > 1 ? pe.ctl[pe.rank] : nullptr;
+  const uint32_t epoch = ctl ? ctl->epoch + 1u : 0u;
+  const int par = (int)(epoch & 1u);
   if (row < rows) {
     float ss = 0.f;
     for (int d = lane; d < D; d += 32) {
@@ -493,71 +639,40 @@ __global__ void prep_kernel(const T* __restrict__ z, int rows, int D, int row0, 
     const float r = 1.f / fmaxf(sqrtf(ss), 1e-12f);
     for (int d = lane; d < D; d += 32) {
       const float v = __uint_as_float(to_tf32(load_as_f32(z, (size_t)row * D + d) * r));
-      for (int q = 0; q < pe.world; ++q) pe.dst[q][(size_t)(row0 + row) * D + d] = v;
+      for (int q = 0; q < pe.world; ++q) pe.dst[par][q][(size_t)(row0 + row) * D + d] = v;
     }
     if (lane == 0) rinv[row] = r;
   }
-  peers_signal(pe);
+  if (!ctl) return;
+  // the last CTA to arrive signals all ranks: flag[0][rank] = epoch
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&ctl->prep_counter, 1u) == gridDim.x - 1) {
+      __threadfence_system();
+      ctl->prep_counter = 0u;
+      for (int q = 0; q < pe.world; ++q) st_release_sys(&pe.ctl[q]->flag[0][pe.rank], epoch);
+    }
+  }
 }
 
-// U [cols, D] -> U^T [D, cols]
-__global__ void transpose_kernel(const float* __restrict__ u, float* __restrict__ ut, int cols, int D) {
+// U [cols, D] -> U^T [D, cols] (the gathered matrix of the current parity when a control block is given)
+__global__ void transpose_kernel(const float* __restrict__ u0, const float* __restrict__ u1, const PeerCtl* ctl,
+                                 float* __restrict__ ut, int cols, int D) {
   __shared__ float tile[32][33];
+  const float* u = (ctl && (ctl->epoch & 1u)) ? u1 : u0;
   const int c0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) tile[i][threadIdx.x] = u[(size_t)(c0 + i) * D + d0 + threadIdx.x];
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) ut[(size_t)(d0 + i) * cols + c0 + threadIdx.x] = tile[threadIdx.x][i];
 }
 
-// lse_i = 1/T + log(sum of split partials); pos_i = <u_i,u_p(i)>/T; per-row loss term lse_i - pos_i.  One warp per row.
-__global__ void fwd_rows_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ u_all, int D,
-                                int row0, int rows, float inv_T, const Peers lse_pe, int lse_off,
-                                float* __restrict__ row_loss, unsigned int* __restrict__ counter, float* __restrict__ loss) {
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (i < rows) {
-    float s = 0.f;
-    for (int k = 0; k < nsplit; ++k) s += partial[(size_t)k * rows + i];
-    const float lse = inv_T + logf(s);
-    const float* ui = u_all + (size_t)(row0 + i) * D;
-    const float* up = u_all + (size_t)(row0 + (i + (rows >> 1)) % rows) * D;
-    float dot = 0.f;
-    for (int d = lane; d < D; d += 32) dot = fmaf(ui[d], up[d], dot);
-    dot = warp_sum(dot);
-    if (lane == 0) {
-      for (int q = 0; q < lse_pe.world; ++q) lse_pe.dst[q][lse_off + i] = lse;     // every rank's gathered lse
-      row_loss[i] = lse - dot * inv_T;
-    }
-  }
-  peers_signal(lse_pe);
-  // loss = mean(row_loss): the last block to finish sums all rows in a fixed order (deterministic, no extra launch)
-  __shared__ bool last;
-  __shared__ float red[32];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  float acc = 0.f;
-  for (int r = threadIdx.x; r < rows; r += blockDim.x) acc += __ldcg(row_loss + r);
-  acc = warp_sum(acc);
-  if (lane == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float tot = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
-    loss[0] = tot / (float)rows;
-    *counter = 0u;                                   // ready for the next call on this scratch buffer
-  }
-}
-
-// dz_i = (dU_i - u_i <u_i,dU_i>) * rinv_i with dU_i = scale * sum_splits partial (the -2 u_p(i) one-hot term is
-// already inside W); one warp per row
+// dz_i = (dU_i - u_i <u_i,dU_i>) * rinv_i with dU_i = scale * sum_splits partial; one warp per row.  Only for D > 256,
+// where the backward runs one tile-kernel launch per 256-column slice of dU (smaller D: folded into the tile kernel).
 template <typename T>
-__global__ void bwd_finalize_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ u_all,
-                                    const T* __restrict__ z_rows, const float* __restrict__ rinv, int D, int row0,
-                                    int rows, float scale, const float* __restrict__ grad_out, T* __restrict__ dz) {
+__global__ void bwd_finalize_kernel(const float* __restrict__ partial, int nsplit, const T* __restrict__ z_rows,
+                                    const float* __restrict__ rinv, int D, int rows, float scale,
+                                    const float* __restrict__ grad_out, T* __restrict__ dz) {
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= rows) return;
@@ -576,8 +691,6 @@ __global__ void bwd_finalize_kernel(const float* __restrict__ partial, int nspli
     if constexpr (sizeof(T) == 4) dz[(size_t)i * D + d] = v;
     else dz[(size_t)i * D + d] = __float2bfloat16_rn(v);
   }
-  (void)u_all;
-  (void)row0;
 }
 
 // BYOL: loss = 2 - 2 mean cos(p_i,t_i); dp_i = -(2/n) (t^_i - cos_i p^_i)/|p_i|.  One warp per row.
@@ -674,6 +787,7 @@ static int check_shapes(const char* who, int rows, int cols, int D, int row0, fl
   MIS_REQUIRE(rows > 0 && cols > 0 && D > 0, MIS_ERR_INVALID_ARG, "%s: sizes must be positive", who);
   MIS_REQUIRE(rows % kTile == 0 && cols % kTile == 0 && row0 % kTile == 0, MIS_ERR_UNSUPPORTED,
               "%s: rows (%d), cols (%d) and row0 (%d) must be multiples of %d", who, rows, cols, row0, kTile);
+  MIS_REQUIRE(rows / kTile < kThreads - 1, MIS_ERR_UNSUPPORTED, "%s: at most %d rows per rank", who, (kThreads - 2) * kTile);
   MIS_REQUIRE(D % kKBlock == 0 && D <= 8192, MIS_ERR_UNSUPPORTED, "%s: D=%d must be a multiple of 32 (<= 8192)", who, D);
   MIS_REQUIRE(!bwd || D <= 256 || D % 256 == 0, MIS_ERR_UNSUPPORTED,
               "%s: D=%d > 256 must be a multiple of 256 (the backward walks dU in 256-column slices)", who, D);
@@ -686,6 +800,16 @@ static int check_shapes(const char* who, int rows, int cols, int D, int row0, fl
 }
 
 constexpr size_t kSmemBytes = (size_t)kRingBytes + sizeof(Bars) + 1024;
+constexpr size_t kCounterBytes = 2048;   // [row_tiles + 1] uint32 arrival counters at the start of the scratch
+
+// everything a multi-rank call adds to the single-rank one (world == 1: all null)
+struct Exchange {
+  int world = 1, rank = 0;
+  PeerCtl* ctl_peers[kMaxPeers] = {};
+  float* u_peers[2][kMaxPeers] = {};
+  float* lse_peers[2][kMaxPeers] = {};
+  long long timeout_clk = 0;
+};
 
 }  // namespace ntx
 }  // namespace mis
@@ -697,13 +821,13 @@ extern "C" int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D) {
   if (rows <= 0 || cols <= 0 || D <= 0) return -1;
   const Plan p = make_plan(rows < kTile ? kTile : rows, cols < kTile ? kTile : cols);
   size_t b = 0;
-  b += al256((size_t)cols * 4 + 256);                 // block counter + per-row loss terms
+  b += al256(kCounterBytes + (size_t)cols * 4);       // arrival counters + per-row loss terms
   b += al256((size_t)D * cols * 4);                   // U^T
   b += al256((size_t)p.nsplit * rows * D * 4);        // dU partials (also covers the forward's row-sum partials)
   return (int64_t)b;
 }
 
-static int launch_prep(const void* z, int z_dtype, int rows, int D, int row0, float* rinv, const Peers& pe, cudaStream_t st) {
+static int launch_prep(const void* z, int z_dtype, int rows, int D, int row0, float* rinv, const PrepPeers& pe, cudaStream_t st) {
   const int wpb = 8;
   const dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
   if (z_dtype == MIS_DTYPE_F32)
@@ -713,29 +837,29 @@ static int launch_prep(const void* z, int z_dtype, int rows, int D, int row0, fl
   MIS_CUDA_TRY(cudaGetLastError());
   return MIS_OK;
 }
-static Peers local_peers(float* dst) {
-  Peers pe = {};
-  pe.dst[0] = dst;
-  pe.world = 1;
-  return pe;
-}
-// flag arrays are [2][kMaxPeers] uint32 followed by the producer counter and the timeout word (local only)
-static int make_peers(Peers* pe, const char* who, int world, int rank, void* const* dst_peers, void* const* flag_peers,
-                      int slot, uint32_t epoch) {
-  MIS_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, MIS_ERR_INVALID_ARG,
-              "%s: world %d / rank %d (at most %d ranks of one node)", who, world, rank, kMaxPeers);
-  MIS_REQUIRE(dst_peers && flag_peers && (slot == 0 || slot == 1), MIS_ERR_INVALID_ARG, "%s: null peer table", who);
-  *pe = Peers{};
+
+// peer tables of one call -> Exchange (validated before any CUDA call)
+static int make_exchange(Exchange* ex, const char* who, int world, int rank, void* const* u0, void* const* u1,
+                         void* const* l0, void* const* l1, void* const* ctl, double timeout_s) {
+  MIS_REQUIRE(world >= 2 && world <= kMaxPeers && rank >= 0 && rank < world, MIS_ERR_INVALID_ARG,
+              "%s: world %d / rank %d (2 to %d ranks of one node)", who, world, rank, kMaxPeers);
+  MIS_REQUIRE(u0 && u1 && l0 && l1 && ctl, MIS_ERR_INVALID_ARG, "%s: null peer table", who);
+  MIS_REQUIRE(timeout_s > 0.0, MIS_ERR_INVALID_ARG, "%s: peer time-out must be positive", who);
+  *ex = Exchange{};
   for (int r = 0; r < world; ++r) {
-    MIS_REQUIRE(dst_peers[r] && flag_peers[r], MIS_ERR_INVALID_ARG, "%s: null peer pointer for rank %d", who, r);
-    pe->dst[r] = static_cast<float*>(dst_peers[r]);
-    pe->flag[r] = static_cast<uint32_t*>(flag_peers[r]);
+    MIS_REQUIRE(u0[r] && u1[r] && l0[r] && l1[r] && ctl[r], MIS_ERR_INVALID_ARG, "%s: null peer pointer for rank %d", who, r);
+    ex->u_peers[0][r] = static_cast<float*>(u0[r]);
+    ex->u_peers[1][r] = static_cast<float*>(u1[r]);
+    ex->lse_peers[0][r] = static_cast<float*>(l0[r]);
+    ex->lse_peers[1][r] = static_cast<float*>(l1[r]);
+    ex->ctl_peers[r] = static_cast<PeerCtl*>(ctl[r]);
   }
-  pe->world = world;
-  pe->rank = rank;
-  pe->slot = slot;
-  pe->epoch = epoch;
-  pe->counter = reinterpret_cast<unsigned int*>(pe->flag[rank] + 2 * kMaxPeers + slot);
+  ex->world = world;
+  ex->rank = rank;
+  int dev = 0, khz = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1965000;
+  ex->timeout_clk = (long long)(timeout_s * 1e3 * (double)khz);
   return MIS_OK;
 }
 
@@ -743,60 +867,59 @@ extern "C" int mis_ntxent_prep(const void* z, int z_dtype, int rows, int D, floa
   MIS_REQUIRE(z && u && rinv, MIS_ERR_INVALID_ARG, "mis_ntxent_prep: null pointer");
   MIS_REQUIRE(rows > 0 && D > 0, MIS_ERR_INVALID_ARG, "mis_ntxent_prep: sizes must be positive");
   MIS_REQUIRE(z_dtype == MIS_DTYPE_F32 || z_dtype == MIS_DTYPE_BF16, MIS_ERR_INVALID_ARG, "mis_ntxent_prep: dtype %d", z_dtype);
-  return launch_prep(z, z_dtype, rows, D, 0, rinv, local_peers(u), reinterpret_cast<cudaStream_t>(stream));
+  PrepPeers pe = {};
+  pe.dst[0][0] = u;
+  pe.world = 1;
+  return launch_prep(z, z_dtype, rows, D, 0, rinv, pe, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int mis_ntxent_prep_gather(const void* z, int z_dtype, int rows, int D, int world, int rank,
-                                      void* const* u_all_peers, float* rinv, void* const* flag_peers, uint32_t epoch,
-                                      void* stream) {
-  MIS_REQUIRE(z && rinv, MIS_ERR_INVALID_ARG, "mis_ntxent_prep_gather: null pointer");
-  MIS_REQUIRE(rows > 0 && D > 0, MIS_ERR_INVALID_ARG, "mis_ntxent_prep_gather: sizes must be positive");
-  MIS_REQUIRE(z_dtype == MIS_DTYPE_F32 || z_dtype == MIS_DTYPE_BF16, MIS_ERR_INVALID_ARG, "mis_ntxent_prep_gather: dtype %d", z_dtype);
-  Peers pe;
-  if (int rc = make_peers(&pe, "mis_ntxent_prep_gather", world, rank, u_all_peers, flag_peers, 0, epoch)) return rc;
-  return launch_prep(z, z_dtype, rows, D, rank * rows, rinv, pe, reinterpret_cast<cudaStream_t>(stream));
-}
-
-extern "C" int mis_peer_wait(const void* flags_local, int slot, int world, uint32_t epoch, void* stream) {
-  MIS_REQUIRE(flags_local && (slot == 0 || slot == 1) && world >= 1 && world <= kMaxPeers, MIS_ERR_INVALID_ARG,
-              "mis_peer_wait: bad arguments");
-  const uint32_t* f = static_cast<const uint32_t*>(flags_local);
-  uint32_t* timeout = const_cast<uint32_t*>(f) + 2 * kMaxPeers + 2;
-  peer_wait_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(f, slot, world, epoch, timeout);
-  MIS_CUDA_TRY(cudaGetLastError());
-  return MIS_OK;
-}
-
-static int ntxent_fwd_impl(const float* u_all, int cols, int D, int row0, int rows, float inv_T, const Peers& lse_pe,
-                           int lse_off, float* loss, void* scratch, int64_t scratch_bytes, void* stream) {
-  MIS_REQUIRE(u_all && loss && scratch, MIS_ERR_INVALID_ARG, "mis_ntxent_fwd: null pointer");
+// forward over the gathered matrix: ONE tile-kernel launch (+ a memset node for its arrival counters)
+static int ntxent_fwd_impl(const float* u0, const float* u1, int cols, int D, int row0, int rows, float inv_T,
+                           const Exchange& ex, float* lse_local, float* loss, void* scratch, int64_t scratch_bytes,
+                           cudaStream_t st) {
+  MIS_REQUIRE(u0 && loss && scratch, MIS_ERR_INVALID_ARG, "mis_ntxent_fwd: null pointer");
   if (int rc = check_shapes("mis_ntxent_fwd", rows, cols, D, row0, inv_T, false)) return rc;
   MIS_REQUIRE(scratch_bytes >= mis_ntxent_scratch_bytes(rows, cols, D), MIS_ERR_INVALID_ARG,
               "mis_ntxent_fwd: scratch too small (%lld < %lld)", (long long)scratch_bytes,
               (long long)mis_ntxent_scratch_bytes(rows, cols, D));
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const Plan p = make_plan(rows, cols);
   uint8_t* sc = static_cast<uint8_t*>(scratch);
-  float* partial = reinterpret_cast<float*>(sc + al256((size_t)cols * 4 + 256) + al256((size_t)D * cols * 4));
+  float* partial = reinterpret_cast<float*>(sc + al256(kCounterBytes + (size_t)cols * 4) + al256((size_t)D * cols * 4));
 
-  CUtensorMap map_u;
-  if (int rc = make_map(&map_u, u_all, (uint64_t)D, (uint64_t)cols, kTile)) return rc;
+  CUtensorMap map0, map1;
+  if (int rc = make_map(&map0, u0, (uint64_t)D, (uint64_t)cols, kTile)) return rc;
+  if (int rc = make_map(&map1, u1 ? u1 : u0, (uint64_t)D, (uint64_t)cols, kTile)) return rc;
   TileArgs a = {};
   a.rows = rows; a.cols = cols; a.D = D; a.row0 = row0;
   a.col_tiles = p.col_tiles; a.tiles_per_split = p.tiles_per_split;
   a.k1 = kLog2e * inv_T;
-  a.lse = nullptr;
   a.inv_T = inv_T;
   a.partial = partial;
+  a.world = ex.world; a.rank = ex.rank; a.rows_per_rank = rows;
+  a.epoch_add = 1;
+  a.timeout_clk = ex.timeout_clk;
+  a.fin.fold = 1;
+  a.fin.counters = reinterpret_cast<unsigned int*>(sc);
+  a.fin.row_loss = reinterpret_cast<float*>(sc + kCounterBytes);
+  a.fin.loss = loss;
+  a.fin.u_all[0] = u0;
+  a.fin.u_all[1] = u1 ? u1 : u0;
+  if (ex.world > 1) {
+    a.ctl = ex.ctl_peers[ex.rank];
+    for (int r = 0; r < ex.world; ++r) {
+      a.ctl_peers[r] = ex.ctl_peers[r];
+      a.fin.lse_dst[0][r] = ex.lse_peers[0][r];
+      a.fin.lse_dst[1][r] = ex.lse_peers[1][r];
+    }
+    a.fin.lse_off = row0;
+  } else {
+    a.fin.lse_dst[0][0] = a.fin.lse_dst[1][0] = lse_local;
+    a.fin.lse_off = 0;
+  }
+  MIS_CUDA_TRY(cudaMemsetAsync(sc, 0, kCounterBytes, st));                      // scratch arrives uninitialised
   auto* fn = &ntxent_tile_kernel<false>;
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map_u, map_u, a);
-  MIS_CUDA_TRY(cudaGetLastError());
-  unsigned int* counter = reinterpret_cast<unsigned int*>(sc);                 // first 256 B of the scratch
-  float* row_loss = reinterpret_cast<float*>(sc + 256);
-  MIS_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));         // scratch arrives uninitialised
-  fwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(partial, 2 * p.nsplit, u_all, D, row0, rows, inv_T, lse_pe, lse_off,
-                                                  row_loss, counter, loss);
+  fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map0, map1, map0, a);
   MIS_CUDA_TRY(cudaGetLastError());
   return MIS_OK;
 }
@@ -804,95 +927,128 @@ static int ntxent_fwd_impl(const float* u_all, int cols, int D, int row0, int ro
 extern "C" int mis_ntxent_fwd(const float* u_all, int cols, int D, int row0, int rows, float inv_T, float* lse_rows,
                               float* loss, void* scratch, int64_t scratch_bytes, void* stream) {
   MIS_REQUIRE(lse_rows, MIS_ERR_INVALID_ARG, "mis_ntxent_fwd: null pointer");
-  return ntxent_fwd_impl(u_all, cols, D, row0, rows, inv_T, local_peers(lse_rows), 0, loss, scratch, scratch_bytes, stream);
+  return ntxent_fwd_impl(u_all, nullptr, cols, D, row0, rows, inv_T, Exchange{}, lse_rows, loss, scratch, scratch_bytes,
+                         reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int mis_ntxent_fwd_gather(const float* u_all, int cols, int D, int rows, float inv_T, int world, int rank,
-                                     void* const* lse_all_peers, void* const* flag_peers, uint32_t epoch, float* loss,
-                                     void* scratch, int64_t scratch_bytes, void* stream) {
-  Peers pe;
-  if (int rc = make_peers(&pe, "mis_ntxent_fwd_gather", world, rank, lse_all_peers, flag_peers, 1, epoch)) return rc;
-  MIS_REQUIRE(cols == world * rows, MIS_ERR_INVALID_ARG, "mis_ntxent_fwd_gather: cols %d != world %d x rows %d", cols, world, rows);
-  return ntxent_fwd_impl(u_all, cols, D, rank * rows, rows, inv_T, pe, rank * rows, loss, scratch, scratch_bytes, stream);
-}
-
-extern "C" int mis_ntxent_bwd(const float* u_all, const float* lse_all, const void* z_rows, int z_dtype,
-                              const float* rinv_rows, int cols, int D, int row0, int rows, float inv_T, float grad_scale,
-                              const float* grad_out, void* dz, void* scratch, int64_t scratch_bytes, void* stream) {
-  MIS_REQUIRE(u_all && lse_all && z_rows && rinv_rows && dz && scratch, MIS_ERR_INVALID_ARG, "mis_ntxent_bwd: null pointer");
+// backward: transpose + ONE tile-kernel launch per 256-column slice of dU (+ the finalize kernel when D > 256)
+static int ntxent_bwd_impl(const float* u0, const float* u1, const float* lse0, const float* lse1, const void* z_rows,
+                           int z_dtype, const float* rinv_rows, int cols, int D, int row0, int rows, float inv_T,
+                           float grad_scale, const float* grad_out, void* dz, const Exchange& ex, void* scratch,
+                           int64_t scratch_bytes, cudaStream_t st) {
+  MIS_REQUIRE(u0 && lse0 && z_rows && rinv_rows && dz && scratch, MIS_ERR_INVALID_ARG, "mis_ntxent_bwd: null pointer");
   MIS_REQUIRE(z_dtype == MIS_DTYPE_F32 || z_dtype == MIS_DTYPE_BF16, MIS_ERR_INVALID_ARG, "mis_ntxent_bwd: dtype %d", z_dtype);
   if (int rc = check_shapes("mis_ntxent_bwd", rows, cols, D, row0, inv_T, true)) return rc;
   MIS_REQUIRE(scratch_bytes >= mis_ntxent_scratch_bytes(rows, cols, D), MIS_ERR_INVALID_ARG,
               "mis_ntxent_bwd: scratch too small (%lld < %lld)", (long long)scratch_bytes,
               (long long)mis_ntxent_scratch_bytes(rows, cols, D));
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const Plan p = make_plan(rows, cols);
   uint8_t* sc = static_cast<uint8_t*>(scratch);
-  float* ut = reinterpret_cast<float*>(sc + al256((size_t)cols * 4 + 256));
-  float* partial = reinterpret_cast<float*>(sc + al256((size_t)cols * 4 + 256) + al256((size_t)D * cols * 4));
+  float* ut = reinterpret_cast<float*>(sc + al256(kCounterBytes + (size_t)cols * 4));
+  float* partial = reinterpret_cast<float*>(sc + al256(kCounterBytes + (size_t)cols * 4) + al256((size_t)D * cols * 4));
+  PeerCtl* ctl = ex.world > 1 ? ex.ctl_peers[ex.rank] : nullptr;
 
-  transpose_kernel<<<dim3(cols / 32, D / 32), dim3(32, 8), 0, st>>>(u_all, ut, cols, D);
+  transpose_kernel<<<dim3(cols / 32, D / 32), dim3(32, 8), 0, st>>>(u0, u1 ? u1 : u0, ctl, ut, cols, D);
   MIS_CUDA_TRY(cudaGetLastError());
 
-  CUtensorMap map_u, map_ut;
-  if (int rc = make_map(&map_u, u_all, (uint64_t)D, (uint64_t)cols, kTile)) return rc;
+  CUtensorMap map0, map1, map_ut;
+  if (int rc = make_map(&map0, u0, (uint64_t)D, (uint64_t)cols, kTile)) return rc;
+  if (int rc = make_map(&map1, u1 ? u1 : u0, (uint64_t)D, (uint64_t)cols, kTile)) return rc;
   const int ds = D <= 256 ? D : 256;     // dU lives in TMEM columns 256..511: at most 256 columns per launch;
                                          // wider embeddings recompute S once per 256-column slice
   if (int rc = make_map(&map_ut, ut, (uint64_t)cols, (uint64_t)D, (uint32_t)ds)) return rc;
+  const float scale = grad_scale * inv_T / (float)rows;
   TileArgs a = {};
   a.rows = rows; a.cols = cols; a.D = D; a.row0 = row0;
   a.col_tiles = p.col_tiles; a.tiles_per_split = p.tiles_per_split;
   a.k1 = kLog2e * inv_T;
-  a.lse = lse_all;
+  a.lse[0] = lse0;
+  a.lse[1] = lse1 ? lse1 : lse0;
   a.inv_T = inv_T;
   a.partial = partial;
   a.ds = ds;
+  a.world = ex.world; a.rank = ex.rank; a.rows_per_rank = rows;
+  a.epoch_add = 0;
+  a.timeout_clk = ex.timeout_clk;
+  a.ctl = ctl;
+  a.fin.fold = D <= 256 ? 1 : 0;
+  a.fin.counters = reinterpret_cast<unsigned int*>(sc);
+  a.fin.z_rows = z_rows;
+  a.fin.rinv = rinv_rows;
+  a.fin.dz = dz;
+  a.fin.z_bf16 = z_dtype == MIS_DTYPE_BF16 ? 1 : 0;
+  a.fin.scale = scale;
+  a.fin.grad_out = grad_out;
+  if (a.fin.fold) MIS_CUDA_TRY(cudaMemsetAsync(sc, 0, kCounterBytes, st));
   auto* fn = &ntxent_tile_kernel<true>;
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   for (int d0 = 0; d0 < D; d0 += ds) {
     a.d0 = d0;
-    fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map_u, map_ut, a);
+    fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map0, map1, map_ut, a);
     MIS_CUDA_TRY(cudaGetLastError());
   }
-
-  const float scale = grad_scale * inv_T / (float)rows;
-  const int wpb = 8;
-  const dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
-  if (z_dtype == MIS_DTYPE_F32)
-    bwd_finalize_kernel<float><<<grid, block, 0, st>>>(partial, p.nsplit, u_all, static_cast<const float*>(z_rows),
-                                                        rinv_rows, D, row0, rows, scale, grad_out, static_cast<float*>(dz));
-  else
-    bwd_finalize_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(partial, p.nsplit, u_all,
-                                                                static_cast<const __nv_bfloat16*>(z_rows), rinv_rows, D,
-                                                                row0, rows, scale, grad_out,
-                                                                static_cast<__nv_bfloat16*>(dz));
-  MIS_CUDA_TRY(cudaGetLastError());
+  if (!a.fin.fold) {
+    const int wpb = 8;
+    const dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
+    if (z_dtype == MIS_DTYPE_F32)
+      bwd_finalize_kernel<float><<<grid, block, 0, st>>>(partial, p.nsplit, static_cast<const float*>(z_rows), rinv_rows, D,
+                                                          rows, scale, grad_out, static_cast<float*>(dz));
+    else
+      bwd_finalize_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(partial, p.nsplit, static_cast<const __nv_bfloat16*>(z_rows),
+                                                                  rinv_rows, D, rows, scale, grad_out,
+                                                                  static_cast<__nv_bfloat16*>(dz));
+    MIS_CUDA_TRY(cudaGetLastError());
+  }
   return MIS_OK;
 }
 
-// ---- one ABI call per autograd phase of the peer-exchange path (fewer host round trips per step) ------------------
+extern "C" int mis_ntxent_bwd(const float* u_all, const float* lse_all, const void* z_rows, int z_dtype,
+                              const float* rinv_rows, int cols, int D, int row0, int rows, float inv_T, float grad_scale,
+                              const float* grad_out, void* dz, void* scratch, int64_t scratch_bytes, void* stream) {
+  return ntxent_bwd_impl(u_all, nullptr, lse_all, nullptr, z_rows, z_dtype, rinv_rows, cols, D, row0, rows, inv_T,
+                         grad_scale, grad_out, dz, Exchange{}, scratch, scratch_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- multi-rank: one ABI call per autograd phase; epoch and buffer parity live on the device (PeerCtl::epoch), so both
+// calls can be captured into CUDA graphs and replayed ------------------------------------------------------------------
 extern "C" int mis_ntxent_fwd_peer(const void* z, int z_dtype, int rows, int D, float inv_T, int world, int rank,
-                                   void* const* u_all_peers, void* const* lse_all_peers, void* const* flag_peers,
-                                   uint32_t epoch, float* rinv, float* loss, void* scratch, int64_t scratch_bytes,
-                                   void* stream) {
-  MIS_REQUIRE(u_all_peers && flag_peers && rank >= 0 && rank < world && world <= kMaxPeers, MIS_ERR_INVALID_ARG,
-              "mis_ntxent_fwd_peer: bad peer tables / rank %d of %d", rank, world);
-  if (int rc = mis_ntxent_prep_gather(z, z_dtype, rows, D, world, rank, u_all_peers, rinv, flag_peers, epoch, stream)) return rc;
-  if (int rc = mis_peer_wait(flag_peers[rank], 0, world, epoch, stream)) return rc;
-  return mis_ntxent_fwd_gather(static_cast<const float*>(u_all_peers[rank]), world * rows, D, rows, inv_T, world, rank,
-                               lse_all_peers, flag_peers, epoch, loss, scratch, scratch_bytes, stream);
+                                   void* const* u_peers0, void* const* u_peers1, void* const* lse_peers0,
+                                   void* const* lse_peers1, void* const* ctl_peers, double timeout_s, float* rinv,
+                                   float* loss, void* scratch, int64_t scratch_bytes, void* stream) {
+  MIS_REQUIRE(z && rinv && loss && scratch, MIS_ERR_INVALID_ARG, "mis_ntxent_fwd_peer: null pointer");
+  MIS_REQUIRE(z_dtype == MIS_DTYPE_F32 || z_dtype == MIS_DTYPE_BF16, MIS_ERR_INVALID_ARG, "mis_ntxent_fwd_peer: dtype %d", z_dtype);
+  Exchange ex;
+  if (int rc = make_exchange(&ex, "mis_ntxent_fwd_peer", world, rank, u_peers0, u_peers1, lse_peers0, lse_peers1, ctl_peers,
+                             timeout_s)) return rc;
+  if (int rc = check_shapes("mis_ntxent_fwd_peer", rows, world * rows, D, rank * rows, inv_T, false)) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  PrepPeers pe = {};
+  pe.world = world;
+  pe.rank = rank;
+  for (int r = 0; r < world; ++r) {
+    pe.dst[0][r] = ex.u_peers[0][r];
+    pe.dst[1][r] = ex.u_peers[1][r];
+    pe.ctl[r] = ex.ctl_peers[r];
+  }
+  if (int rc = launch_prep(z, z_dtype, rows, D, rank * rows, rinv, pe, st)) return rc;
+  return ntxent_fwd_impl(ex.u_peers[0][rank], ex.u_peers[1][rank], world * rows, D, rank * rows, rows, inv_T, ex, nullptr,
+                         loss, scratch, scratch_bytes, st);
 }
 
-extern "C" int mis_ntxent_bwd_peer(const float* u_all, const float* lse_all, const void* z_rows, int z_dtype,
-                                   const float* rinv_rows, int D, int rows, float inv_T, float grad_scale,
-                                   const float* grad_out, void* dz, int world, int rank, const void* flags_local,
-                                   uint32_t epoch, void* scratch, int64_t scratch_bytes, void* stream) {
-  if (int rc = mis_peer_wait(flags_local, 1, world, epoch, stream)) return rc;
-  return mis_ntxent_bwd(u_all, lse_all, z_rows, z_dtype, rinv_rows, world * rows, D, rank * rows, rows, inv_T, grad_scale,
-                        grad_out, dz, scratch, scratch_bytes, stream);
+extern "C" int mis_ntxent_bwd_peer(const void* z_rows, int z_dtype, const float* rinv_rows, int rows, int D, float inv_T,
+                                   float grad_scale, const float* grad_out, void* dz, int world, int rank,
+                                   void* const* u_peers0, void* const* u_peers1, void* const* lse_peers0,
+                                   void* const* lse_peers1, void* const* ctl_peers, double timeout_s, void* scratch,
+                                   int64_t scratch_bytes, void* stream) {
+  Exchange ex;
+  if (int rc = make_exchange(&ex, "mis_ntxent_bwd_peer", world, rank, u_peers0, u_peers1, lse_peers0, lse_peers1, ctl_peers,
+                             timeout_s)) return rc;
+  return ntxent_bwd_impl(ex.u_peers[0][rank], ex.u_peers[1][rank], ex.lse_peers[0][rank], ex.lse_peers[1][rank], z_rows,
+                         z_dtype, rinv_rows, world * rows, D, rank * rows, rows, inv_T, grad_scale, grad_out, dz, ex, scratch,
+                         scratch_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
-// ---- single-rank convenience: prep -> forward -> backward in one call (7 launches, one host round trip) ----------
+// ---- single-rank convenience: prep -> forward -> backward in one call (4 kernels + 2 memsets, one host round trip) ----
 static inline size_t ws_u_bytes(int rows, int D) { return al256((size_t)rows * D * 4); }
 static inline size_t ws_row_bytes(int rows) { return al256((size_t)rows * 4); }
 

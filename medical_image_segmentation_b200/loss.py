@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import torch
 import torch.distributed as dist
@@ -75,6 +76,55 @@ class _LocalGraph:
         return self.loss.clone(), self.dz, self
 
 
+class _PeerGraph:
+    """Forward and backward of the multi-rank loss, each captured into a CUDA graph over static buffers.  The first
+    evaluation runs eagerly (it is a real, collective evaluation on every rank), the second is captured and replayed."""
+
+    def __init__(self, ex, z: torch.Tensor, inv_T: float):
+        self.ex, self.inv_T = ex, float(inv_T)
+        self.z = torch.empty_like(z)
+        self.loss = torch.empty((1,), dtype=torch.float32, device=z.device)
+        self.dz = torch.empty_like(z)
+        self.gout = torch.ones((1,), dtype=torch.float32, device=z.device)
+        self.fwd_graph = self.bwd_graph = None
+        self.fwd_calls = self.bwd_calls = 0
+
+    def matches(self, z: torch.Tensor, inv_T: float) -> bool:
+        return z.shape == self.z.shape and z.dtype == self.z.dtype and float(inv_T) == self.inv_T
+
+    def forward(self, z: torch.Tensor):
+        self.z.copy_(z)
+        if self.fwd_calls == 0:
+            CudaKernels._launch_fwd_peer(self.z, self.ex, self.inv_T, self.loss)
+        else:
+            if self.fwd_graph is None:
+                torch.cuda.current_stream(z.device).synchronize()
+                self.fwd_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.fwd_graph):
+                    CudaKernels._launch_fwd_peer(self.z, self.ex, self.inv_T, self.loss)
+            self.fwd_graph.replay()
+        self.fwd_calls += 1
+        return self.z, self.loss.clone(), self
+
+    def backward(self, grad_out: torch.Tensor):
+        self.gout.copy_(grad_out.reshape(1))
+        if self.bwd_calls == 0:
+            CudaKernels._launch_bwd_peer(self.z, self.ex, self.inv_T, self.gout, self.dz)
+        else:
+            if self.bwd_graph is None:
+                torch.cuda.current_stream(self.z.device).synchronize()
+                self.bwd_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.bwd_graph):
+                    CudaKernels._launch_bwd_peer(self.z, self.ex, self.inv_T, self.gout, self.dz)
+            self.bwd_graph.replay()
+        self.bwd_calls += 1
+        return self.dz.clone()
+
+
+class _Pending:
+    """Marks a multi-rank forward whose backward has not run (dies with its autograd graph)."""
+
+
 class CudaKernels:
     """The three device steps of NT-Xent, bound to the C ABI (include/mis_b200.h)."""
 
@@ -83,8 +133,11 @@ class CudaKernels:
     @staticmethod
     def launch_mode(world: int) -> str:
         """How the loss's kernels reach the GPU (reported by bench.py)."""
-        if world == 1 and os.environ.get("MIS_NTXENT_GRAPH") == "1":
-            return "CUDA graph replay (prep, fwd, bwd: 6 kernels + memset)"
+        if os.environ.get("MIS_NTXENT_GRAPH") == "1":
+            if world == 1:
+                return "graph: one CUDA graph replay per step (prep, forward tile kernel, transpose, backward tile kernel)"
+            return ("graph: one CUDA graph replay per autograd phase (forward: prep + tile kernel; backward: transpose + "
+                    "tile kernel); epoch and buffer parity are read from device memory")
         return "eager"
 
     @staticmethod
@@ -101,12 +154,13 @@ class CudaKernels:
         CudaKernels.launches += 1
         return z, u, rinv
 
-    _workspaces: dict = {}   # (device, rows, D) -> uint8 workspace of the single-rank fused path (stream-ordered reuse)
-    _graphs: dict = {}       # (device, rows, D, dtype, inv_T) -> captured single-rank step (MIS_NTXENT_GRAPH=1)
+    _workspaces: dict = {}   # (device, rows, D, stream) -> uint8 workspace of the single-rank fused path (stream-ordered reuse)
+    _graphs: dict = {}       # (device, rows, D, dtype, inv_T, stream) -> captured single-rank step (MIS_NTXENT_GRAPH=1)
 
     @staticmethod
     def _workspace(device, rows: int, D: int) -> torch.Tensor:
-        key = (device, rows, D)
+        # one workspace per stream: reuse is stream-ordered, two streams must not share one
+        key = (device, rows, D, torch.cuda.current_stream(device).cuda_stream)
         ws = CudaKernels._workspaces.get(key)
         if ws is None:
             n = int(_lib.lib.mis_ntxent_fwd_bwd_workspace_bytes(rows, D))
@@ -136,50 +190,81 @@ class CudaKernels:
         rows, D = z.shape
         ws = CudaKernels._workspace(z.device, rows, D)
         if os.environ.get("MIS_NTXENT_GRAPH", "0") == "1":
-            key = (z.device, rows, D, z.dtype, float(inv_T))
+            key = (z.device, rows, D, z.dtype, float(inv_T), torch.cuda.current_stream(z.device).cuda_stream)
             g = CudaKernels._graphs.get(key)
             if g is None:
                 g = CudaKernels._graphs[key] = _LocalGraph(z, inv_T, ws)
             if g.in_flight == 0:
-                CudaKernels.launches += 6
+                CudaKernels.launches += CudaKernels._n_fwd_bwd(D)
                 return g.run(z)
         loss = torch.empty((1,), dtype=torch.float32, device=z.device)
         dz = torch.empty_like(z)
         CudaKernels._launch_local(z, inv_T, loss, dz, ws)
-        CudaKernels.launches += 6
+        CudaKernels.launches += CudaKernels._n_fwd_bwd(D)
         return loss, dz, None
 
     @staticmethod
-    def fwd_peer(z: torch.Tensor, ex, par: int, inv_T: float):
-        """Forward with the NVLink exchange fused into the producing kernels: one ABI call (mis_ntxent_fwd_peer =
-        prep_gather, wait for every rank's rows, fwd_gather)."""
-        z = z.contiguous()
-        rows, D = z.shape
-        if ex.scratch is None:
-            ex.scratch = CudaKernels.scratch(rows, ex.cols, D, z.device)
-            ex.rinv = [torch.empty((rows,), dtype=torch.float32, device=z.device) for _ in range(2)]
-        loss = torch.empty((1,), dtype=torch.float32, device=z.device)
-        with _on_device(z.device):
-            rc = _lib.lib.mis_ntxent_fwd_peer(z.data_ptr(), _dt(z), rows, D, inv_T, ex.world, ex.rank, ex.u_peers[par],
-                                              ex.l_peers[par], ex.flag_peers, ex.epoch, ex.rinv[par].data_ptr(),
-                                              loss.data_ptr(), ex.scratch.data_ptr(), ex.scratch.numel(), _stream(z))
-        _lib.check(rc, "mis_ntxent_fwd_peer")
-        CudaKernels.launches += 4
-        return z, ex.rinv[par], loss
+    def _n_bwd(D: int) -> int:
+        """Kernels of one backward: transpose + one tile kernel per 256-column slice of dU (+ a finalize kernel when the
+        Jacobian is not folded into the tile kernel, D > 256)."""
+        return 2 if D <= 256 else 2 + D // 256
 
     @staticmethod
-    def bwd_peer(z, rinv, ex, epoch: int, inv_T: float, grad_out: torch.Tensor):
-        par = epoch & 1
+    def _n_fwd_bwd(D: int) -> int:
+        return 2 + CudaKernels._n_bwd(D)         # prep + forward tile kernel + backward
+
+    @staticmethod
+    def _peer_buffers(ex, z):
+        if ex.scratch is None:
+            rows, D = z.shape
+            ex.scratch = CudaKernels.scratch(rows, ex.cols, D, z.device)
+            ex.rinv = torch.empty((rows,), dtype=torch.float32, device=z.device)
+
+    @staticmethod
+    def _launch_fwd_peer(z, ex, inv_T, loss):
         rows, D = z.shape
-        dz = torch.empty_like(z)
-        g = grad_out if (grad_out.dtype == torch.float32 and grad_out.is_contiguous()) else grad_out.to(torch.float32).contiguous()
         with _on_device(z.device):
-            rc = _lib.lib.mis_ntxent_bwd_peer(ex.u_all[par].data_ptr(), ex.lse_all[par].data_ptr(), z.data_ptr(), _dt(z),
-                                              rinv.data_ptr(), D, rows, inv_T, 1.0, g.data_ptr(), dz.data_ptr(), ex.world,
-                                              ex.rank, ex.flags_ptr, epoch, ex.scratch.data_ptr(), ex.scratch.numel(),
-                                              _stream(z))
+            rc = _lib.lib.mis_ntxent_fwd_peer(z.data_ptr(), _dt(z), rows, D, inv_T, ex.world, ex.rank, ex.u_peers[0],
+                                              ex.u_peers[1], ex.l_peers[0], ex.l_peers[1], ex.ctl_peers, peer.timeout_s(),
+                                              ex.rinv.data_ptr(), loss.data_ptr(), ex.scratch.data_ptr(),
+                                              ex.scratch.numel(), _stream(z))
+        _lib.check(rc, "mis_ntxent_fwd_peer")
+
+    @staticmethod
+    def _launch_bwd_peer(z, ex, inv_T, g, dz):
+        rows, D = z.shape
+        with _on_device(z.device):
+            rc = _lib.lib.mis_ntxent_bwd_peer(z.data_ptr(), _dt(z), ex.rinv.data_ptr(), rows, D, inv_T, 1.0, g.data_ptr(),
+                                              dz.data_ptr(), ex.world, ex.rank, ex.u_peers[0], ex.u_peers[1], ex.l_peers[0],
+                                              ex.l_peers[1], ex.ctl_peers, peer.timeout_s(), ex.scratch.data_ptr(),
+                                              ex.scratch.numel(), _stream(z))
         _lib.check(rc, "mis_ntxent_bwd_peer")
-        CudaKernels.launches += 4
+
+    @staticmethod
+    def fwd_peer(z: torch.Tensor, ex, inv_T: float):
+        """Forward with the NVLink exchange fused into the kernels: one ABI call (mis_ntxent_fwd_peer = prep kernel with
+        peer stores + ONE tile kernel that waits for the peers' rows itself).  With ``MIS_NTXENT_GRAPH=1`` the call is
+        captured once into a CUDA graph over static buffers and replayed (epoch and buffer parity are device-side)."""
+        z = z.contiguous()
+        CudaKernels._peer_buffers(ex, z)
+        CudaKernels.launches += 2
+        if os.environ.get("MIS_NTXENT_GRAPH", "0") == "1":
+            if ex.graph is None:
+                ex.graph = _PeerGraph(ex, z, inv_T)
+            if ex.graph.matches(z, inv_T):
+                return ex.graph.forward(z)
+        loss = torch.empty((1,), dtype=torch.float32, device=z.device)
+        CudaKernels._launch_fwd_peer(z, ex, inv_T, loss)
+        return z, loss, None
+
+    @staticmethod
+    def bwd_peer(z, ex, inv_T: float, grad_out: torch.Tensor, graph):
+        CudaKernels.launches += CudaKernels._n_bwd(z.shape[1])
+        g = grad_out if (grad_out.dtype == torch.float32 and grad_out.is_contiguous()) else grad_out.to(torch.float32).contiguous()
+        if graph is not None:
+            return graph.backward(g)
+        dz = torch.empty_like(z)
+        CudaKernels._launch_bwd_peer(z, ex, inv_T, g.reshape(1), dz)
         return dz
 
     @staticmethod
@@ -196,7 +281,7 @@ class CudaKernels:
             rc = _lib.lib.mis_ntxent_fwd(u_all.data_ptr(), cols, D, row0, rows, inv_T, lse.data_ptr(), loss.data_ptr(),
                                          scratch.data_ptr(), scratch.numel(), _stream(u_all))
         _lib.check(rc, "mis_ntxent_fwd")
-        CudaKernels.launches += 2
+        CudaKernels.launches += 1
         return lse, loss
 
     @staticmethod
@@ -210,7 +295,7 @@ class CudaKernels:
                                          cols, D, row0, rows, inv_T, 1.0, g.data_ptr(), dz.data_ptr(),
                                          scratch.data_ptr(), scratch.numel(), _stream(z))
         _lib.check(rc, "mis_ntxent_bwd")
-        CudaKernels.launches += 3
+        CudaKernels.launches += CudaKernels._n_bwd(D)
         return dz
 
 
@@ -241,15 +326,21 @@ class _NTXent(torch.autograd.Function):
             return loss.reshape(())
         if distributed and kernels is CudaKernels:
             ex = peer.get_exchange(group, rows, z.shape[1], z.device)
-            if ex is not None and ex.in_flight[(ex.epoch + 1) & 1] == 0:
-                # NVLink peer stores: prep writes the rows into every rank's matrix, the forward its lse rows
-                ex.epoch += 1
-                par = ex.epoch & 1
+            if ex is not None:
+                # One evaluation outstanding: the backward reads the device-side epoch of the LAST forward, and buffer
+                # parity alone makes reuse safe only if backward(k) is enqueued before forward(k+1).  Every rank runs the
+                # same autograd program, so every rank raises here together (no silent change of transport).
+                if ex.pending is not None and ex.pending() is not None:
+                    raise RuntimeError(
+                        "nt_xent_loss: a second multi-rank forward was issued before the backward of the previous one. "
+                        "The NVLink exchange supports one evaluation in flight; run backward first, wrap evaluations that "
+                        "need no gradient in torch.no_grad(), or set MIS_NTXENT_EXCHANGE=nccl.")
+                z, loss, graph = kernels.fwd_peer(z, ex, inv_T)
                 if ctx.needs_input_grad[0]:
-                    ex.in_flight[par] += 1                # this parity's buffers are read again by the backward
-                z, rinv, loss = kernels.fwd_peer(z, ex, par, inv_T)
-                ctx.save_for_backward(z, rinv)
-                ctx.meta = ("peer", inv_T, ex, ex.epoch, kernels)
+                    ctx.token = _Pending()
+                    ex.pending = weakref.ref(ctx.token)
+                ctx.save_for_backward(z)
+                ctx.meta = ("peer", inv_T, ex, kernels, graph)
                 return loss.reshape(())
         z, u, rinv = kernels.prep(z)
         u_all = _all_gather_rows(u, group) if distributed else u
@@ -268,10 +359,10 @@ class _NTXent(torch.autograd.Function):
                 ctx.holder.in_flight -= 1
             return out, None, None, None
         if ctx.meta[0] == "peer":
-            z, rinv = ctx.saved_tensors
-            _, inv_T, ex, epoch, kernels = ctx.meta
-            dz = kernels.bwd_peer(z, rinv, ex, epoch, inv_T, grad_out)
-            ex.in_flight[epoch & 1] -= 1
+            (z,) = ctx.saved_tensors
+            _, inv_T, ex, kernels, graph = ctx.meta
+            dz = kernels.bwd_peer(z, ex, inv_T, grad_out, graph)
+            ex.pending = None
             return dz, None, None, None
         z, u_all, rinv, lse = ctx.saved_tensors
         inv_T, group, distributed, rank, kernels, scratch = ctx.meta

@@ -31,7 +31,7 @@ for (B, D, T) in ((64, 64, 0.1), (256, 128, 0.1), (128, 256, 0.2), (256, 128, 0.
 from medical_image_segmentation_b200 import peer
 print(f"rank {rank}: exchange mode {peer.mode()}, peer exchanges in use: {len(peer._cache)}, disabled: {peer._disabled_reason}", flush=True)
 try:
-    peer.check_timeouts()
+    peer.check_health()
 except RuntimeError as e:
     ok = False
     print(f"rank {rank}: {e}", flush=True)

@@ -94,18 +94,27 @@ def test_peer_exchange_argument_errors_and_mode_switch(monkeypatch):
     p = buf.ctypes.data
     tbl = (C.c_void_p * 8)(*([p] * 8))
     null_tbl = (C.c_void_p * 8)(*([p] + [None] * 7))
-    assert lib.mis_ntxent_prep_gather(p, 1, 128, 64, 9, 0, tbl, p, tbl, 1, None) == _lib.MIS_ERR_INVALID_ARG      # > 8 ranks
-    assert lib.mis_ntxent_prep_gather(p, 1, 128, 64, 2, 2, tbl, p, tbl, 1, None) == _lib.MIS_ERR_INVALID_ARG      # rank >= world
-    assert lib.mis_ntxent_prep_gather(p, 1, 128, 64, 2, 0, null_tbl, p, tbl, 1, None) == _lib.MIS_ERR_INVALID_ARG  # null peer
+
+    def fwd(world, rank, u0=tbl, timeout=600.0, rows=128):
+        return lib.mis_ntxent_fwd_peer(p, 1, rows, 64, 10.0, world, rank, u0, tbl, tbl, tbl, tbl, timeout, p, p, p, 1 << 30, None)
+
+    assert fwd(9, 0) == _lib.MIS_ERR_INVALID_ARG            # > 8 ranks
+    assert fwd(2, 2) == _lib.MIS_ERR_INVALID_ARG            # rank >= world
+    assert fwd(1, 0) == _lib.MIS_ERR_INVALID_ARG            # a single rank has nothing to exchange (mis_ntxent_fwd_bwd)
+    assert fwd(2, 0, u0=null_tbl) == _lib.MIS_ERR_INVALID_ARG
     assert b"rank 1" in lib.mis_last_error()
-    assert lib.mis_ntxent_fwd_gather(p, 256, 64, 100, 10.0, 2, 0, tbl, tbl, 1, p, p, 1 << 30, None) == _lib.MIS_ERR_INVALID_ARG
-    assert lib.mis_peer_wait(None, 0, 2, 1, None) == _lib.MIS_ERR_INVALID_ARG
-    assert lib.mis_peer_wait(p, 2, 2, 1, None) == _lib.MIS_ERR_INVALID_ARG
+    assert fwd(2, 0, timeout=0.0) == _lib.MIS_ERR_INVALID_ARG
+    assert fwd(2, 0, rows=100) == _lib.MIS_ERR_UNSUPPORTED   # rows per rank must be a multiple of 128
+    assert lib.mis_ntxent_bwd_peer(p, 1, p, 128, 64, 10.0, 1.0, None, p, 2, 5, tbl, tbl, tbl, tbl, tbl, 600.0, p, 1 << 30,
+                                   None) == _lib.MIS_ERR_INVALID_ARG
     monkeypatch.setenv("MIS_NTXENT_EXCHANGE", "nccl")
     assert peer.mode() == "nccl" and peer.get_exchange(None, 128, 64, None) is None
     monkeypatch.delenv("MIS_NTXENT_EXCHANGE")
     assert peer.mode() == "auto"
-    assert peer._FLAG_BYTES >= 4 * (2 * peer.MAX_PEERS + 3)       # flags [2][8] + 2 counters + timeout word (csrc/ntxent.cu)
+    assert peer._CTL_BYTES >= 4 * (2 * peer.MAX_PEERS + 4)        # PeerCtl: flags [2][8], counter, epoch, abort, pad
+    assert peer.timeout_s() == 600.0
+    monkeypatch.setenv("MIS_PEER_TIMEOUT_S", "30")
+    assert peer.timeout_s() == 30.0
 
 
 def test_h2d_staging_argument_errors_without_gpu():
