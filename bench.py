@@ -351,7 +351,8 @@ def run_b200(args):
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x_dev = torch.randint(0, 65536, (B, 1, H, W), dtype=torch.int32, device=dev, generator=g).to(torch.uint16)
     z = torch.randn(2 * B, D, device=dev, generator=g).requires_grad_(True)
-    t = FusedTwoViewTransforms(s, (MEAN,), (STD,), prefetch_params=True)   # host RNG replay of step k+1 overlaps step k
+    t = FusedTwoViewTransforms(s, (MEAN,), (STD,), blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0), prefetch_params=True,
+                               generator=torch.Generator().manual_seed(1000 + rank))   # host RNG replay of step k+1 overlaps step k
     out = torch.empty((2 * B, 1, s, s), dtype=torch.bfloat16, device=dev)
     torch.manual_seed(1000 + rank)
     aug_only = args.config == "cfg5"
@@ -393,7 +394,7 @@ def run_b200(args):
         sweep = []
         for crop in (96, 224):
             for window in (None, (1000.0, 30000.0)):
-                tt = FusedTwoViewTransforms(crop, (MEAN,), (STD,), window=window)
+                tt = FusedTwoViewTransforms(crop, (MEAN,), (STD,), blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0), window=window)
                 torch.manual_seed(7)
                 pp = tt.to_view_major(tt.draw_params(B, H, W))
                 oo = torch.empty((2 * B, 1, crop, crop), dtype=torch.bfloat16, device=dev)

@@ -39,8 +39,15 @@ enum {
 enum { MIS_DTYPE_BF16 = 0, MIS_DTYPE_F32 = 1 };
 
 /* flags of MisViewParams */
-#define MIS_VIEW_FLIP   1u   /* RandomHorizontalFlip fired   (torchvision v2/_transform.py:181) */
-#define MIS_VIEW_JITTER 2u   /* RandomApply(ColorJitter) fired (v2/_container.py:104)           */
+#define MIS_VIEW_FLIP     1u   /* RandomHorizontalFlip fired   (torchvision v2/_transform.py:181)   */
+#define MIS_VIEW_JITTER   2u   /* RandomApply(ColorJitter) fired (v2/_container.py:104)             */
+#define MIS_VIEW_GRAY     4u   /* RandomGrayscale fired (v2/_color.py:33-55); identity for C == 1   */
+#define MIS_VIEW_BLUR     8u   /* RandomApply([GaussianBlur(23)]) fired; sigma in blur_sigma        */
+#define MIS_VIEW_SOLARIZE 16u  /* RandomSolarize fired (v2/_color.py:312-337)                       */
+
+/* Solarize threshold of the reference chain, RandomSolarize(128) on the 0..255 scale
+ * (lightning_module.py:54), expressed on [0,1]: x >= 128/255 -> 1 - x (functional/_color.py:497-501). */
+#define MIS_SOLARIZE_THRESHOLD (128.0f / 255.0f)
 
 /*
  * One augmented view = one record (48 bytes).  Filled on the host by the RNG replay of
@@ -57,7 +64,7 @@ typedef struct MisViewParams {
   float contrast;
   float saturation;       /* drawn (RNG parity) but identity for C == 1                     */
   float hue;
-  int32_t reserved;
+  float blur_sigma;       /* GaussianBlur sigma ~ U(0.1, 2) (v2/_misc.py:209-211); with MIS_VIEW_BLUR */
 } MisViewParams;
 
 int mis_version(void);
@@ -74,8 +81,8 @@ const char* mis_last_error(void);
  *
  *   rng_state      host, the byte blob of torch.get_rng_state() (read and advanced in place)
  *   rng_state_len  its length (5056 for torch's CPUGeneratorImpl)
- *   blur_prob / solarize_prob  host float[2]; only 0.0 is implemented on the device side, the
- *                  draws are still consumed for parity (lightning_module.py:53-54)
+ *   blur_prob / solarize_prob  host float[2]: per-view probabilities of RandomApply([GaussianBlur(23)]) and
+ *                  RandomSolarize(128) (lightning_module.py:53-54; reference defaults (1.0, 0.1) / (0.0, 0.2))
  *   n_done         host, out: number of images completed.  n_done < n_images means image
  *                  img0+n_done has a crop box that depends on the last bit of torch.exp (SLEEF
  *                  vs libm expf); the generator is left at that image's first draw and the caller
@@ -103,8 +110,9 @@ int mis_draw_resize_jitter_params(uint8_t* rng_state, int64_t rng_state_len, int
  * resize_image, torchvision v2/functional/_geometry.py:1785-1800, 271-340) ->
  * horizontal flip (:56-57) -> ColorJitter brightness/contrast in fn_idx order
  * (functional/_color.py:114-125, 190-205, _blend :92-97) -> ToDtype(float32, scale=True)
- * (functional/_misc.py:304) -> Normalize (functional/_misc.py:37-67), i.e.
- * lightning_module.py:47-58 with blur_prob = solarize_prob = 0.
+ * (functional/_misc.py:304) -> Normalize (functional/_misc.py:37-67), i.e. lightning_module.py:47-58.
+ * RandomSolarize (MIS_VIEW_SOLARIZE) is applied in the store epilogue of variant 0; a view with MIS_VIEW_BLUR is left
+ * for mis_aug_blur_views (below), which must follow on the same stream.  Variants 1-3 implement neither.
  *
  *   src        uint16 [n_images, C, H, W], plane stride H*W, image stride img_stride elements.
  *              W must be even; the allocation must be readable up to the next 16-byte boundary
@@ -116,10 +124,12 @@ int mis_draw_resize_jitter_params(uint8_t* rng_state, int64_t rng_state_len, int
  *   out        [n_views, C, s, s] in out_dtype (MIS_DTYPE_BF16 or MIS_DTYPE_F32), NCHW
  *   s          output crop size, 8 <= s <= 256
  *   use_tma    kernel variant (the name is historical):
- *              0: warp-tile kernel (csrc/aug_tile.cu; default, fastest measured on B200: one warp per 32x32 output
- *                 tile, rows straight from global memory through refill-on-consume register slots, taps in
- *                 registers) for C == 1, s <= 256 and at most 5.5x downscaling of the whole slice per axis; other
- *                 shapes fall through to variant 2
+ *              0: strip kernel (csrc/aug_strip.cu; default, fastest measured on B200: one CTA per view, one warp per
+ *                 strip of 32 output columns and vertical part, rows straight from global memory through
+ *                 refill-on-consume register slots behind an L2 prefetch, the pre-colour tile parked as uint16 in
+ *                 shared memory) for C == 1, s <= 256 and at most 5.5x downscaling of the whole slice per axis;
+ *                 other shapes fall through to variant 3, then 2
+ *              3: warp-tile kernel (csrc/aug_tile.cu, round 1: cluster per view, one warp per 32x32 output tile)
  *              1: band kernel, a producer warp stages crop rows with 2-D TMA tensor-map boxes (cp.async.bulk.tensor)
  *                 into a shared-memory ring (needs W % 8 == 0 and dense images, otherwise variant 2)
  *              2: band kernel, every thread stages its own columns with cp.async into a private ring, two 16-row
@@ -129,6 +139,20 @@ int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H, int W, int
                      const MisViewParams* params, int n_views, float win_lo, float win_hi,
                      const float* mean, const float* std, void* out, int s, int out_dtype,
                      int use_tma, void* stream);
+
+/* The variant mis_aug_two_view runs for this shape and selector: 0 strip, 3 warp-tile, 1 TMA band, 2 cp.async band. */
+int mis_aug_kernel_variant(int C, int H, int W, int64_t img_stride, int s, int use_tma);
+
+/* GaussianBlur(23) + RandomSolarize(128) + Normalize for the views whose record carries MIS_VIEW_BLUR
+ * (RandomApply([GaussianBlur(kernel_size=23)], p) -> RandomSolarize(128, p) -> ToDtype -> Normalize,
+ * lightning_module.py:53-57; torchvision v2/functional/_misc.py:104-165: softmax kernel, reflect padding).
+ * The blur follows the colour jitter, whose clamps do not commute with it: mis_aug_two_view (variant 0) leaves the
+ * post-colour image of such a view as uint16 (round(x*65535)) in the first 2*s*s bytes of the view's output plane and
+ * this call finishes those planes in place; other views are not touched.  Call it right after mis_aug_two_view on the
+ * same stream with the same `out`, params, C, s, out_dtype, mean, std whenever a record has MIS_VIEW_BLUR.
+ * s a multiple of 8 in [16, 224]. */
+int mis_aug_blur_views(void* out, int out_dtype, const MisViewParams* params, int n_views, int C, int s,
+                       const float* mean, const float* std, void* stream);
 
 /* Host -> device staging for mis_aug_two_view: copies only the full-width rows [lo, hi) of each slice that the slice's
  * records read, into the same offsets of `dst_dev` (the other rows keep whatever they held and are never read by K1

@@ -2,7 +2,7 @@
 
 Public surface (mirrors the reference's transform / loss call sites):
 
-    FusedTwoViewTransforms(crop_size, mean, std, blur_prob=(0,0), solarize_prob=(0,0))(x) -> [view1, view2]
+    FusedTwoViewTransforms(crop_size, mean, std, blur_prob=(1.0,0.1), solarize_prob=(0.0,0.2))(x) -> [view1, view2]
     nt_xent_loss(z_a, z_b, temperature=0.1, group=None) -> scalar
     byol_cosine_loss(preds, targets) -> scalar
     compute_mean_and_std(loader) -> (mean, std)      (analyze_data/compute_dataset_metrics.py:12-29)

@@ -16,13 +16,13 @@ LIB_PATH = os.path.join(PKG_DIR, "libmis_b200.so")
 
 MIS_OK, MIS_ERR_INVALID_ARG, MIS_ERR_UNSUPPORTED, MIS_ERR_CUDA = 0, 1, 2, 3
 MIS_DTYPE_BF16, MIS_DTYPE_F32 = 0, 1
-MIS_VIEW_FLIP, MIS_VIEW_JITTER = 1, 2
+MIS_VIEW_FLIP, MIS_VIEW_JITTER, MIS_VIEW_GRAY, MIS_VIEW_BLUR, MIS_VIEW_SOLARIZE = 1, 2, 4, 8, 16
 
 # numpy mirror of struct MisViewParams (48 bytes)
 VIEW_PARAMS_DTYPE = np.dtype([
     ("img", "<i4"), ("top", "<i4"), ("left", "<i4"), ("h", "<i4"), ("w", "<i4"), ("flags", "<u4"),
     ("order", "u1", (4,)), ("brightness", "<f4"), ("contrast", "<f4"), ("saturation", "<f4"), ("hue", "<f4"),
-    ("reserved", "<i4"),
+    ("blur_sigma", "<f4"),
 ], align=False)
 assert VIEW_PARAMS_DTYPE.itemsize == 48
 
@@ -37,6 +37,9 @@ EXPORTS = {
     "mis_aug_two_view": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int,
                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p]),
+    "mis_aug_kernel_variant": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int]),
+    "mis_aug_blur_views": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
     "mis_h2d_needed_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p,
                                       C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "mis_aug_algorithmic_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),

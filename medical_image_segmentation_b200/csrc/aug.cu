@@ -1187,6 +1187,15 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
   return window ? launch<false, true>(a, maps, grid, smem, st) : launch<false, false>(a, maps, grid, smem, st);
 }
 
+// Which K1 variant mis_aug_two_view runs for this shape and selector (0 strip, 3 warp-tile, 1 TMA band, 2 cp.async band).
+extern "C" int mis_aug_kernel_variant(int C, int H, int W, int64_t img_stride, int s, int use_tma) {
+  using namespace mis::aug;
+  if (use_tma == 0 && mis::augs::strip_supported(C, H, W, img_stride, s)) return 0;
+  if ((use_tma == 0 || use_tma == 3) && mis::augt::tile_supported(C, H, W, img_stride, s)) return 3;
+  const bool bulk = use_tma == 1 && (W % 8 == 0) && (img_stride == (int64_t)C * H * W);
+  return bulk ? 1 : 2;
+}
+
 extern "C" int64_t mis_aug_algorithmic_bytes(const MisViewParams* p, int n_views, int C, int s, int out_dtype) {
   if (!p || n_views < 0) return -1;
   const int64_t ob = out_dtype == MIS_DTYPE_F32 ? 4 : 2;

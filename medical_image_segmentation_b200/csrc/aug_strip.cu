@@ -409,18 +409,20 @@ __device__ __forceinline__ float run_part(const Part& t) {
   return sum;
 }
 
-// 8 pixels per lane from the parked tile: contrast / late brightness / normalise / flip, one 16-byte store (bf16)
-template <bool kFlip, bool kF32>
-__device__ __forceinline__ void store_tile(uint32_t tile, int nrows, int lane, int x0, int s, void* out_base,
-                                           size_t plane_row0, bool jitter, bool has_post, float cs, float cadd, float pb,
+// 8 pixels per lane from the parked tile: contrast / late brightness / solarize / normalise / flip, one 16-byte store
+// (bf16).  kRaw: the view drew a GaussianBlur -- the post-colour image is left as uint16 (round(x * 65535)) in the first
+// 2*s*s bytes of its output plane for mis_aug_blur_views (aug_blur.cu), which blurs, solarizes and normalises it.
+template <bool kFlip, bool kF32, bool kRaw>
+__device__ __forceinline__ void store_tile(uint32_t tile, int nrows, int lane, int x0, int s, uint8_t* plane_ptr, int y0,
+                                           bool jitter, bool has_post, bool sol, float cs, float cadd, float pb,
                                            float mean, float inv_std) {
   const int chunk = lane & 3, r0 = lane >> 2;
   const int xs = x0 + 8 * chunk;
   if (xs >= s) return;
   const int col = kFlip ? (s - xs - 8) : xs;
   uint32_t ta = tile + (uint32_t)(r0 * kTilePitch + 16 * chunk);
-  constexpr size_t esz = kF32 ? 4 : 2;
-  uint8_t* op = static_cast<uint8_t*>(out_base) + ((plane_row0 + r0) * (size_t)s + col) * esz;
+  constexpr size_t esz = kRaw ? 2 : (kF32 ? 4 : 2);
+  uint8_t* op = plane_ptr + ((size_t)(y0 + r0) * (size_t)s + col) * esz;
   const size_t step = (size_t)8 * s * esz;
   const uint64_t nmagic = pack2(-kMagic, -kMagic);
   const uint64_t nmean = pack2(-mean, -mean), istd = pack2(inv_std, inv_std);
@@ -453,9 +455,32 @@ __device__ __forceinline__ void store_tile(uint32_t tile, int nrows, int lane, i
 #pragma unroll
       for (int i = 0; i < 4; ++i) u[i] = fmul2(u[i], unit);
     }
+    float v[8];
+    if (kRaw) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) unpack2(u[i], v[2 * i], v[2 * i + 1]);
+      uint32_t pk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float e0 = kFlip ? v[7 - 2 * i] : v[2 * i], e1 = kFlip ? v[6 - 2 * i] : v[2 * i + 1];
+        const uint32_t b0 = __float_as_uint(fmaf(e0, 65535.f, kMagic)), b1 = __float_as_uint(fmaf(e1, 65535.f, kMagic));
+        pk[i] = __byte_perm(b0, b1, 0x5410);          // low 16 mantissa bits = round-to-nearest(x * 65535)
+      }
+      *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      continue;
+    }
+    if (sol) {        // RandomSolarize(128) on the [0,1] scale: x >= 128/255 -> 1 - x (functional/_color.py:497-501)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a, b;
+        unpack2(u[i], a, b);
+        a = a >= MIS_SOLARIZE_THRESHOLD ? 1.f - a : a;
+        b = b >= MIS_SOLARIZE_THRESHOLD ? 1.f - b : b;
+        u[i] = pack2(a, b);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) u[i] = fmul2(fadd2(u[i], nmean), istd);
-    float v[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) unpack2(u[i], v[2 * i], v[2 * i + 1]);
     if (kF32) {
@@ -706,16 +731,23 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) aug_strip_kernel(cons
   const bool flip = (P.flags & MIS_VIEW_FLIP) != 0;
   const float pb = P.brightness;
   const float cs = cf * (1.f / 65535.f);
+  const bool sol = (P.flags & MIS_VIEW_SOLARIZE) != 0;
+  const bool raw = (P.flags & MIS_VIEW_BLUR) != 0;       // finished by mis_aug_blur_views
+  uint8_t* const plane_ptr = static_cast<uint8_t*>(a.out) + (size_t)plane * s * s * (a.out_f32 ? 4 : 2);
   if ((s & 7) == 0) {
-    const size_t prow0 = (size_t)plane * s + y0;
     const bool f32 = a.out_f32 != 0;
-    if (!f32) {
-      if (flip) store_tile<true, false>(t.tile, nrows, lane, x0, s, a.out, prow0, jitter, has_post, cs, cadd, pb, mean, inv_std);
-      else store_tile<false, false>(t.tile, nrows, lane, x0, s, a.out, prow0, jitter, has_post, cs, cadd, pb, mean, inv_std);
+#define MIS_STORE(F, T, R) store_tile<F, T, R>(t.tile, nrows, lane, x0, s, plane_ptr, y0, jitter, has_post, sol, cs, cadd, pb, mean, inv_std)
+    if (raw) {
+      if (flip) MIS_STORE(true, false, true);
+      else MIS_STORE(false, false, true);
+    } else if (!f32) {
+      if (flip) MIS_STORE(true, false, false);
+      else MIS_STORE(false, false, false);
     } else {
-      if (flip) store_tile<true, true>(t.tile, nrows, lane, x0, s, a.out, prow0, jitter, has_post, cs, cadd, pb, mean, inv_std);
-      else store_tile<false, true>(t.tile, nrows, lane, x0, s, a.out, prow0, jitter, has_post, cs, cadd, pb, mean, inv_std);
+      if (flip) MIS_STORE(true, true, false);
+      else MIS_STORE(false, true, false);
     }
+#undef MIS_STORE
     return;
   }
   // crop sizes that are not a multiple of 8: element-wise stores
@@ -745,6 +777,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) aug_strip_kernel(cons
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = v[i] * (1.f / 65535.f);
+      }
+      if (sol) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = v[i] >= MIS_SOLARIZE_THRESHOLD ? 1.f - v[i] : v[i];
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * inv_std;

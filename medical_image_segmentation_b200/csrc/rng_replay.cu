@@ -154,7 +154,7 @@ static bool draw_view(Engine& e, int H, int W, float blur_p, float sol_p, MisVie
   out.flags = 0;
   out.order[0] = 0; out.order[1] = 1; out.order[2] = 2; out.order[3] = 3;
   out.brightness = 1.f; out.contrast = 1.f; out.saturation = 1.f; out.hue = 0.f;
-  out.reserved = 0;
+  out.blur_sigma = 0.f;
   if (!(e.uniform(0.f, 1.f) >= kFlipP)) out.flags |= MIS_VIEW_FLIP;
   if (!(e.uniform(0.f, 1.f) >= kJitterP)) {
     out.flags |= MIS_VIEW_JITTER;
@@ -171,12 +171,12 @@ static bool draw_view(Engine& e, int H, int W, float blur_p, float sol_p, MisVie
     out.saturation = e.uniform(0.8f, 1.2f);
     out.hue = e.uniform(-0.1f, 0.1f);
   }
-  (void)e.uniform(0.f, 1.f);                                   // RandomGrayscale(p=0.2): identity at C == 1
-  const bool blur = !(e.uniform(0.f, 1.f) >= blur_p);          // RandomApply([GaussianBlur(23)])
-  if (blur) (void)e.uniform(0.1f, 2.0f);                       //   sigma draw, v2/_misc.py:209-211
-  (void)e.uniform(0.f, 1.f);                                   // RandomSolarize
-  (void)sol_p;
-  (void)kGrayP;
+  if (!(e.uniform(0.f, 1.f) >= kGrayP)) out.flags |= MIS_VIEW_GRAY;       // RandomGrayscale(p=0.2): identity at C == 1
+  if (!(e.uniform(0.f, 1.f) >= blur_p)) {                                 // RandomApply([GaussianBlur(23)])
+    out.flags |= MIS_VIEW_BLUR;
+    out.blur_sigma = e.uniform(0.1f, 2.0f);                               //   sigma draw, v2/_misc.py:209-211
+  }
+  if (!(e.uniform(0.f, 1.f) >= sol_p)) out.flags |= MIS_VIEW_SOLARIZE;    // RandomSolarize(128)
   return true;
 }
 
@@ -259,7 +259,7 @@ extern "C" int mis_draw_resize_jitter_params(uint8_t* rng_state, int64_t rng_sta
     p.contrast = contrast > 0.f ? e.uniform(clo, 1.f + contrast) : 1.f;
     p.saturation = 1.f;
     p.hue = 0.f;
-    p.reserved = 0;
+    p.blur_sigma = 0.f;
   }
   store(rng_state, e);
   return MIS_OK;

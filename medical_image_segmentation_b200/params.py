@@ -17,7 +17,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import MIS_VIEW_FLIP, MIS_VIEW_JITTER, VIEW_PARAMS_DTYPE
+from ._lib import (MIS_VIEW_BLUR, MIS_VIEW_FLIP, MIS_VIEW_GRAY, MIS_VIEW_JITTER, MIS_VIEW_SOLARIZE,
+                   VIEW_PARAMS_DTYPE)
 
 # constants of the reference chain (lightning_module.py:44,49-52; torchvision RandomResizedCrop defaults)
 _RRC_SCALE = (0.08, 1.0)
@@ -25,23 +26,23 @@ _RRC_RATIO = (3.0 / 4.0, 4.0 / 3.0)
 _JITTER = dict(brightness=(0.6, 1.4), contrast=(0.6, 1.4), saturation=(0.8, 1.2), hue=(-0.1, 0.1))
 
 
-def _u(lo, hi) -> float:
-    return torch.empty(1).uniform_(lo, hi).item()
+def _u(lo, hi, gen=None) -> float:
+    return torch.empty(1).uniform_(lo, hi, generator=gen).item()
 
 
-def _draw_view_torch(rec, H: int, W: int, blur_p: float, sol_p: float) -> None:
+def _draw_view_torch(rec, H: int, W: int, blur_p: float, sol_p: float, gen=None) -> None:
     """One view, torch calls in torchvision's order (v2/_geometry.py:272-308, _transform.py:181,
     _container.py:104, _color.py:146-154)."""
     area = H * W
     log_ratio = torch.log(torch.tensor(_RRC_RATIO))
     for _ in range(10):
-        target_area = area * _u(_RRC_SCALE[0], _RRC_SCALE[1])
-        aspect = torch.exp(torch.empty(1).uniform_(log_ratio[0], log_ratio[1])).item()
+        target_area = area * _u(_RRC_SCALE[0], _RRC_SCALE[1], gen)
+        aspect = torch.exp(torch.empty(1).uniform_(log_ratio[0], log_ratio[1], generator=gen)).item()
         w = int(round(math.sqrt(target_area * aspect)))
         h = int(round(math.sqrt(target_area / aspect)))
         if 0 < w <= W and 0 < h <= H:
-            top = torch.randint(0, H - h + 1, size=(1,)).item()
-            left = torch.randint(0, W - w + 1, size=(1,)).item()
+            top = torch.randint(0, H - h + 1, size=(1,), generator=gen).item()
+            left = torch.randint(0, W - w + 1, size=(1,), generator=gen).item()
             break
     else:
         in_ratio = float(W) / float(H)
@@ -58,44 +59,50 @@ def _draw_view_torch(rec, H: int, W: int, blur_p: float, sol_p: float) -> None:
     flags = 0
     rec["order"] = (0, 1, 2, 3)
     rec["brightness"], rec["contrast"], rec["saturation"], rec["hue"] = 1.0, 1.0, 1.0, 0.0
-    if not bool(torch.rand(1) >= 0.5):
+    if not bool(torch.rand(1, generator=gen) >= 0.5):
         flags |= MIS_VIEW_FLIP
-    if not bool(torch.rand(1) >= 0.8):
+    if not bool(torch.rand(1, generator=gen) >= 0.8):
         flags |= MIS_VIEW_JITTER
-        rec["order"] = torch.randperm(4).numpy().astype(np.uint8)
-        rec["brightness"] = _u(*_JITTER["brightness"])
-        rec["contrast"] = _u(*_JITTER["contrast"])
-        rec["saturation"] = _u(*_JITTER["saturation"])
-        rec["hue"] = _u(*_JITTER["hue"])
-    torch.rand(1)                                   # RandomGrayscale: identity for one channel
-    if not bool(torch.rand(1) >= blur_p):           # RandomApply([GaussianBlur(23)])
-        _u(0.1, 2.0)
-    torch.rand(1)                                   # RandomSolarize
+        rec["order"] = torch.randperm(4, generator=gen).numpy().astype(np.uint8)
+        rec["brightness"] = _u(*_JITTER["brightness"], gen)
+        rec["contrast"] = _u(*_JITTER["contrast"], gen)
+        rec["saturation"] = _u(*_JITTER["saturation"], gen)
+        rec["hue"] = _u(*_JITTER["hue"], gen)
+    if not bool(torch.rand(1, generator=gen) >= 0.2):    # RandomGrayscale(p=0.2): identity for one channel
+        flags |= MIS_VIEW_GRAY
+    rec["blur_sigma"] = 0.0
+    if not bool(torch.rand(1, generator=gen) >= blur_p):  # RandomApply([GaussianBlur(23)]); sigma: v2/_misc.py:209-211
+        flags |= MIS_VIEW_BLUR
+        rec["blur_sigma"] = _u(0.1, 2.0, gen)
+    if not bool(torch.rand(1, generator=gen) >= sol_p):   # RandomSolarize(128)
+        flags |= MIS_VIEW_SOLARIZE
     rec["flags"] = flags
-    rec["reserved"] = 0
 
 
 def draw_two_view_params_torch(n_images: int, H: int, W: int, blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0),
-                               img0: int = 0) -> np.ndarray:
+                               img0: int = 0, generator: torch.Generator | None = None) -> np.ndarray:
     out = np.zeros(2 * n_images, VIEW_PARAMS_DTYPE)
     for i in range(n_images):
         for v in range(2):
             rec = out[2 * i + v]
             rec["img"] = img0 + i
-            _draw_view_torch(rec, H, W, blur_prob[v], solarize_prob[v])
+            _draw_view_torch(rec, H, W, blur_prob[v], solarize_prob[v], generator)
     return out
 
 
 def draw_two_view_params(n_images: int, H: int, W: int, blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0),
-                         out: np.ndarray | None = None) -> np.ndarray:
-    """2*n_images records (image-major: [2*i+v]) drawn from torch's global CPU generator."""
+                         out: np.ndarray | None = None, generator: torch.Generator | None = None) -> np.ndarray:
+    """2*n_images records (image-major: [2*i+v]) drawn from torch's global CPU generator, or from ``generator`` (a
+    private ``torch.Generator``: nothing else can then move the stream between two draws)."""
+    get_state = torch.get_rng_state if generator is None else generator.get_state
+    set_state = torch.set_rng_state if generator is None else generator.set_state
     if out is None:
         out = np.zeros(2 * n_images, VIEW_PARAMS_DTYPE)
     assert out.dtype == VIEW_PARAMS_DTYPE and out.shape == (2 * n_images,) and out.flags.c_contiguous
     bp = (C.c_float * 2)(*[float(p) for p in blur_prob])
     sp = (C.c_float * 2)(*[float(p) for p in solarize_prob])
     n_done = C.c_int(0)
-    state = torch.get_rng_state()
+    state = get_state()
     blob = state.numpy()
     done = 0
     while done < n_images:
@@ -106,10 +113,11 @@ def draw_two_view_params(n_images: int, H: int, W: int, blur_prob=(0.0, 0.0), so
         done += n_done.value
         if done < n_images:
             # this image's crop box depends on the last bit of torch.exp: let torch draw it
-            torch.set_rng_state(state)
-            out[2 * done:2 * done + 2] = draw_two_view_params_torch(1, H, W, blur_prob, solarize_prob, img0=done)
-            state = torch.get_rng_state()
+            set_state(state)
+            out[2 * done:2 * done + 2] = draw_two_view_params_torch(1, H, W, blur_prob, solarize_prob, img0=done,
+                                                                    generator=generator)
+            state = get_state()
             blob = state.numpy()
             done += 1
-    torch.set_rng_state(state)
+    set_state(state)
     return out

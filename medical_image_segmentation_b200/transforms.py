@@ -18,9 +18,15 @@ per-sample CPU callable to a per-batch GPU kernel:
   parity-tested against the same oracle.
 * ``prefetch_params=True`` draws the next batch's parameters on a helper thread while the GPU works on the current
   one (same records in the same order; see ``next_params``).
-* GaussianBlur and Solarize (lightning_module.py:53-54) are not implemented on the device yet:
-  ``blur_prob`` / ``solarize_prob`` must be 0 (their RNG draws are still consumed).  The CIFAR data
-  modules of the reference run with exactly this setting (lightning_module.py:482-488).
+* ``blur_prob`` / ``solarize_prob`` default to the reference's ``(1.0, 0.1)`` / ``(0.0, 0.2)``
+  (lightning_module.py:40).  GaussianBlur(23) runs as a second kernel over the views that drew it
+  (``mis_aug_blur_views``), RandomSolarize in K1's store epilogue; both need the strip kernel (``use_tma=0``, one
+  channel).  ``RandomSolarize(128)`` is written for 0..255 images: on the [0,1] scale the threshold is 128/255
+  (torchvision itself refuses 128 on a float image, functional/_color.py:498-499; the reference only ever feeds it
+  uint8 PIL images).  ``RandomGrayscale`` is the identity for one channel.
+* ``generator``: a private ``torch.Generator`` to draw the parameters from instead of torch's global CPU generator
+  (recommended with ``prefetch_params=True``: the helper thread then cannot be disturbed by, or disturb, other users
+  of the global stream).
 """
 from __future__ import annotations
 
@@ -31,7 +37,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import MIS_DTYPE_BF16, MIS_DTYPE_F32, VIEW_PARAMS_DTYPE
+from ._lib import MIS_DTYPE_BF16, MIS_DTYPE_F32, MIS_VIEW_BLUR, MIS_VIEW_SOLARIZE, VIEW_PARAMS_DTYPE
 from .params import draw_two_view_params
 
 
@@ -63,14 +69,12 @@ def _as_float_seq(v, n: int, name: str) -> list[float]:
 
 class FusedTwoViewTransforms:
     def __init__(self, crop_size: int, mean: Sequence[float], std: Sequence[float],
-                 blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0), *, out_dtype=torch.bfloat16,
+                 blur_prob=(1.0, 0.1), solarize_prob=(0.0, 0.2), *, out_dtype=torch.bfloat16,
                  window: tuple[float, float] | None = None, use_tma: bool | int = False,
-                 prefetch_params: bool = False):
+                 prefetch_params: bool = False, generator: torch.Generator | None = None):
         assert len(blur_prob) == 2 and len(solarize_prob) == 2, "atm only 2 views are supported"
-        if any(p != 0 for p in blur_prob) or any(p != 0 for p in solarize_prob):
-            raise NotImplementedError(
-                "GaussianBlur / RandomSolarize are not fused yet (SURVEY 8f N2): pass blur_prob=(0,0), "
-                "solarize_prob=(0,0) as the reference's CIFAR modules do (lightning_module.py:482-488)")
+        if any(not 0.0 <= float(p) <= 1.0 for p in tuple(blur_prob) + tuple(solarize_prob)):
+            raise ValueError("blur_prob / solarize_prob must be probabilities")
         if isinstance(crop_size, (tuple, list)):
             if len(crop_size) != 2 or crop_size[0] != crop_size[1]:
                 raise NotImplementedError("only square crops are implemented")
@@ -89,6 +93,7 @@ class FusedTwoViewTransforms:
             raise ValueError("use_tma must be 0 (strip kernel), 1 (TMA band kernel), 2 (cp.async band kernel) or "
                              "3 (warp-tile kernel)")
         self.prefetch_params = bool(prefetch_params)
+        self.generator = generator
         self._pool = None                     # one helper thread drawing the NEXT batch's parameters
         self._pending = None                  # ((B, H, W), future)
         self._x_stage: torch.Tensor | None = None      # device staging buffer of host batches
@@ -103,13 +108,14 @@ class FusedTwoViewTransforms:
     # -- parameters ---------------------------------------------------------------------------
     def draw_params(self, B: int, H: int, W: int) -> np.ndarray:
         """Image-major records [2*i+v], drawn like B calls of the reference's __call__."""
-        return draw_two_view_params(B, H, W, self.blur_prob, self.solarize_prob)
+        return draw_two_view_params(B, H, W, self.blur_prob, self.solarize_prob, generator=self.generator)
 
     def next_params(self, B: int, H: int, W: int) -> np.ndarray:
         """``draw_params`` with the draw of the FOLLOWING batch started on a helper thread (``prefetch_params=True``):
         the host RNG replay (~0.4 ms per 1024 slices) then overlaps the GPU work of the current batch.  The records are
         the same, in the same order, as back-to-back ``draw_params`` calls -- as long as nothing else consumes torch's
-        global CPU generator between calls (the helper thread reads and writes its state)."""
+        global CPU generator between calls (the helper thread reads and writes its state); pass ``generator=`` to the
+        constructor to draw from a private generator instead."""
         if not self.prefetch_params:
             return self.draw_params(B, H, W)
         if self._pool is None:
@@ -161,6 +167,14 @@ class FusedTwoViewTransforms:
         n_views = int(params_view_major.shape[0])
         assert params_view_major.dtype == VIEW_PARAMS_DTYPE
         s = self.crop_size
+        flags_any = self._validate_table(params_view_major, B, H, W)
+        extra = flags_any & (MIS_VIEW_BLUR | MIS_VIEW_SOLARIZE)
+        if extra:
+            variant = _lib.lib.mis_aug_kernel_variant(Cc, H, W, Cc * H * W, s, self.use_tma)
+            if variant != 0:
+                raise NotImplementedError(
+                    "GaussianBlur / RandomSolarize are fused into the strip kernel only (use_tma=0, one channel, "
+                    f"8 <= crop <= 256, at most 5.5x downscaling); this call would run K1 variant {variant}")
         if out is None:
             out = torch.empty((n_views, Cc, s, s), dtype=self.out_dtype, device=x.device)
         else:
@@ -176,9 +190,32 @@ class FusedTwoViewTransforms:
                 self.window[0], self.window[1], C.cast(mean_c, C.c_void_p), C.cast(std_c, C.c_void_p),
                 out.data_ptr(), s, MIS_DTYPE_F32 if self.out_dtype == torch.float32 else MIS_DTYPE_BF16,
                 self.use_tma, C.c_void_p(stream))
-        _lib.check(rc, "mis_aug_two_view")
-        self.launches += 1
+            _lib.check(rc, "mis_aug_two_view")
+            self.launches += 1
+            if extra & MIS_VIEW_BLUR:      # GaussianBlur(23) -> solarize -> normalise for the views that drew a blur
+                rc = _lib.lib.mis_aug_blur_views(
+                    out.data_ptr(), MIS_DTYPE_F32 if self.out_dtype == torch.float32 else MIS_DTYPE_BF16, dev.data_ptr(),
+                    n_views, Cc, s, C.cast(mean_c, C.c_void_p), C.cast(std_c, C.c_void_p), C.c_void_p(stream))
+                _lib.check(rc, "mis_aug_blur_views")
+                self.launches += 1
         return out
+
+    @staticmethod
+    def _validate_table(p: np.ndarray, B: int, H: int, W: int) -> int:
+        """The kernel trusts the table: check every record addresses a slice of the batch and a box inside it.
+        Returns the OR of all flag words."""
+        if p.shape[0] == 0:
+            return 0
+        img, top, left, h, w = (p[k].astype(np.int64) for k in ("img", "top", "left", "h", "w"))
+        bad = (img < 0) | (img >= B) | (top < 0) | (left < 0) | (h < 1) | (w < 1) | (top + h > H) | (left + w > W)
+        if bad.any():
+            k = int(np.flatnonzero(bad)[0])
+            raise ValueError(f"view record {k} is outside the batch: img {int(img[k])} of {B}, box (top {int(top[k])}, left "
+                             f"{int(left[k])}, h {int(h[k])}, w {int(w[k])}) in {H}x{W}")
+        sig = p["blur_sigma"][(p["flags"] & MIS_VIEW_BLUR) != 0]
+        if sig.size and not (np.isfinite(sig).all() and (sig > 0).all()):
+            raise ValueError("a record with MIS_VIEW_BLUR needs a positive blur_sigma")
+        return int(np.bitwise_or.reduce(p["flags"]))
 
     def _stage_params(self, params: np.ndarray, device) -> torch.Tensor:
         """Copy the table through one of three persistent pinned buffers (no per-call cudaHostAlloc)."""

@@ -231,6 +231,37 @@ def aa_resize(x: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
 # ----------------------------------------------------------------------------------
 # (2c) colour ops + normalise (A.3), and the whole view
 # ----------------------------------------------------------------------------------
+SOLARIZE_THRESHOLD = 128.0 / 255.0   # RandomSolarize(128) of lightning_module.py:54 on the [0,1] scale
+
+
+def gaussian_kernel1d(sigma: float, kernel_size: int = 23) -> np.ndarray:
+    """_get_gaussian_kernel1d (v2/functional/_misc.py:86-90) in float32: softmax(-(linspace(-lim, lim) / sigma)^2)."""
+    f32 = np.float32
+    lim = f32((kernel_size - 1) / (2.0 * math.sqrt(2.0)))
+    step = f32((lim - (-lim)) / f32(kernel_size - 1))
+    idx = np.arange(kernel_size)
+    x = np.where(idx < kernel_size // 2, -lim + step * idx.astype(f32), lim - step * (kernel_size - 1 - idx).astype(f32)).astype(f32)
+    v = -np.square((x / f32(sigma)).astype(f32)).astype(f32)
+    e = np.exp(v - v.max()).astype(f32)
+    return (e / e.sum(dtype=f32)).astype(f32)
+
+
+def gaussian_blur(x: np.ndarray, sigma: float, kernel_size: int = 23) -> np.ndarray:
+    """gaussian_blur_image (v2/functional/_misc.py:104-165) for one float plane: reflect padding by kernel_size // 2,
+    then ONE 2-D convolution with the outer product of the 1-D kernels (float32)."""
+    f32 = np.float32
+    k1 = gaussian_kernel1d(sigma, kernel_size)
+    k2 = (k1[:, None] * k1[None, :]).astype(f32)
+    r = kernel_size // 2
+    pad = np.pad(np.asarray(x, f32), r, mode="reflect")
+    h, w = x.shape
+    out = np.zeros((h, w), f32)
+    for ky in range(kernel_size):
+        for kx in range(kernel_size):
+            out += k2[ky, kx] * pad[ky:ky + h, kx:kx + w]
+    return out
+
+
 def color_and_normalize(x: np.ndarray, params: dict, mean: float, std: float) -> np.ndarray:
     f32 = np.float32
     x = np.asarray(x, f32)
@@ -244,6 +275,11 @@ def color_and_normalize(x: np.ndarray, params: dict, mean: float, std: float) ->
                 x = np.clip(x * f32(c) + mu * f32(1.0 - c), f32(0), f32(1)).astype(f32)
             # k == 2 (saturation) and k == 3 (hue) are identities when C == 1
             # (functional/_color.py:159-160, 380-381)
+    # RandomGrayscale: identity when C == 1 (functional/_color.py:31-36)
+    if params.get("blur"):          # RandomApply([GaussianBlur(23)]), lightning_module.py:53
+        x = gaussian_blur(x, params["sigma"])
+    if params.get("solarize"):      # RandomSolarize(128) on the [0,1] scale: x >= thr -> 1 - x (functional/_color.py:497-501)
+        x = np.where(x >= f32(SOLARIZE_THRESHOLD), f32(1) - x, x).astype(f32)
     return ((x - f32(mean)) / f32(std)).astype(f32)
 
 

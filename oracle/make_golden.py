@@ -18,6 +18,8 @@ aug_512.npz     4 synthetic 512x512 slices (regenerated from seed by tests/synth
                 crops 224, 96 and 256: params, strided output samples out[::7, ::7], sums.
 params_stream.npz  crop boxes / flags for 400 images (800 views) at 512x512, 256x768 and
                 448x448 + the generator state after, pinning the RNG replay.
+aug_blur.npz    the reference's DEFAULT blur_prob=(1.0, 0.1) (GaussianBlur(23) on view 1 always): 6 slices 96x128 at crops
+                32 / 48 (full outputs, params, blur flags, sigmas) and 4 slices 512x512 at crop 224 (samples, sums).
 byol_loss.npz   inputs and outputs of the reference BYOL loss.
 """
 from __future__ import annotations
@@ -115,8 +117,63 @@ def run_reference(Ref, images, crop, seeds):
     return np.stack(outs), pack_params(views)
 
 
+def run_reference_blur(Ref, images, crop, seeds):
+    """The reference class with its DEFAULT blur_prob=(1.0, 0.1) (lightning_module.py:40); solarize_prob=(0, 0) because
+    RandomSolarize(128) raises on a float image (functional/_color.py:498-499).  Also records which views drew a blur
+    and their sigma (GaussianBlur.make_params, v2/_misc.py:209-211)."""
+    chain = Ref(crop_size=crop, mean=(MEAN,), std=(STD,), solarize_prob=(0.0, 0.0))
+    rec = Recorder(chain)
+    sig_log = []
+    for view_idx, compose in enumerate(chain.transforms):
+        blur = compose.transforms[4].transforms[0]
+        orig = blur.make_params
+
+        def wrapped(flat_inputs, _orig=orig, _v=view_idx):
+            p = _orig(flat_inputs)
+            sig_log.append((_v, p["sigma"][0]))
+            return p
+
+        blur.make_params = wrapped
+    outs, views, blur_flag, sigma = [], [], [], []
+    for img, seed in zip(images, seeds):
+        torch.manual_seed(int(seed))
+        sig_log.clear()
+        v1, v2 = chain(u16_to_tv_image(img))
+        outs.append(np.stack([v1[0].numpy(), v2[0].numpy()]))
+        views.extend(rec.pop_views())
+        got = dict(sig_log)
+        for v in range(2):
+            blur_flag.append(1 if v in got else 0)
+            sigma.append(got.get(v, 0.0))
+    return np.stack(outs), pack_params(views), np.array(blur_flag, np.int32), np.array(sigma, np.float64)
+
+
+def make_blur_golden(Ref):
+    """aug_blur.npz: the reference's default-argument chain (GaussianBlur on view 1 always, on view 2 with p = 0.1)."""
+    imgs = np.stack([synth.ct_like_slice(96, 128, seed=70 + i) if i % 2 == 0
+                     else synth.uniform_slice(96, 128, seed=70 + i) for i in range(6)])
+    seeds = 3000 + np.arange(6)
+    blob = dict(images=imgs, seeds=seeds, mean=MEAN, std=STD)
+    for crop in (32, 48):
+        out, (ints, order, fac), bf, sg = run_reference_blur(Ref, imgs, crop, seeds)
+        blob[f"out_{crop}"] = out
+        blob[f"ints_{crop}"], blob[f"order_{crop}"], blob[f"fac_{crop}"] = ints, order, fac
+        blob[f"blur_{crop}"], blob[f"sigma_{crop}"] = bf, sg
+    big = synth.batch_512(4)
+    seeds512 = 1000 + np.arange(4)
+    out, (ints, order, fac), bf, sg = run_reference_blur(Ref, big, 224, seeds512)
+    blob["seeds_512"] = seeds512
+    blob["sample_224"] = out[:, :, ::7, ::7].copy()
+    blob["sum_224"] = out.astype(np.float64).sum(axis=(2, 3))
+    blob["ints_224"], blob["blur_224"], blob["sigma_224"] = ints, bf, sg
+    np.savez_compressed(os.path.join(GOLD, "aug_blur.npz"), **blob)
+
+
 def main():
     import cv2
+    if "--blur-only" in sys.argv:
+        make_blur_golden(ref_import.load_reference_transforms())
+        return
 
     Ref = ref_import.load_reference_transforms()
     os.makedirs(GOLD, exist_ok=True)
@@ -159,6 +216,8 @@ def main():
         blob[f"sumsq_{crop}"] = (out.astype(np.float64) ** 2).sum(axis=(2, 3))
         blob[f"ints_{crop}"], blob[f"order_{crop}"], blob[f"fac_{crop}"] = ints, order, fac
     np.savez_compressed(os.path.join(GOLD, "aug_512.npz"), **blob)
+
+    make_blur_golden(Ref)
 
     # ---- params_stream: RNG replay pin ----------------------------------------------
     blob = {}

@@ -10,7 +10,7 @@ use_tma = int(sys.argv[1])
 MEAN, STD = 0.227358, 0.237160
 for (H, W, crop, B) in ((96, 128, 32, 4), (512, 512, 224, 4), (512, 512, 96, 4), (512, 512, 256, 2), (256, 768, 112, 2)):
     imgs = synth.batch_512(B, seed=77, H=H, W=W)
-    t = FusedTwoViewTransforms(crop, (MEAN,), (STD,), out_dtype=torch.float32, use_tma=use_tma)
+    t = FusedTwoViewTransforms(crop, (MEAN,), (STD,), blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0), out_dtype=torch.float32, use_tma=use_tma)
     torch.manual_seed(31)
     t(torch.from_numpy(imgs).cuda())
     torch.cuda.synchronize()
@@ -31,7 +31,7 @@ for (H, W, crop, B) in ((96, 128, 32, 4), (512, 512, 224, 4), (512, 512, 96, 4),
 # timing at the bench config
 B, crop = 1024, 224
 x = torch.randint(0, 65536, (B, 1, 512, 512), dtype=torch.int32, device="cuda").to(torch.uint16)
-t = FusedTwoViewTransforms(crop, (MEAN,), (STD,), use_tma=use_tma)
+t = FusedTwoViewTransforms(crop, (MEAN,), (STD,), blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0), use_tma=use_tma)
 torch.manual_seed(0)
 params = t.to_view_major(t.draw_params(B, 512, 512))
 nbytes = algorithmic_bytes(params, 1, crop)

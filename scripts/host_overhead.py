@@ -18,7 +18,7 @@ if world > 1:
 B, H, W, s, D = 1024, 512, 512, 224, 128
 x = torch.randint(0, 65536, (B, 1, H, W), dtype=torch.int32, device="cuda").to(torch.uint16)
 z = torch.randn(2 * B, D, device="cuda").requires_grad_(True)
-t = FusedTwoViewTransforms(s, (0.227,), (0.237,), prefetch_params=True)
+t = FusedTwoViewTransforms(s, (0.227,), (0.237,), blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0), prefetch_params=True)
 out = torch.empty((2 * B, 1, s, s), dtype=torch.bfloat16, device="cuda")
 torch.manual_seed(rank)
 acc = {"next_params": 0.0, "view_major": 0.0, "apply": 0.0, "loss_fwd": 0.0, "loss_bwd": 0.0}

@@ -15,7 +15,7 @@ for crop in (96, 224, 256):
     for B in (64, 256, 1024, 4096):
         for variant in (0, 2):
             x = x_all[:B]
-            t = FusedTwoViewTransforms(crop, (0.227358,), (0.237160,), use_tma=variant)
+            t = FusedTwoViewTransforms(crop, (0.227358,), (0.237160,), blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0), use_tma=variant)
             torch.manual_seed(0)
             params = t.to_view_major(t.draw_params(B, 512, 512))
             nbytes = algorithmic_bytes(params, 1, crop)

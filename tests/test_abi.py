@@ -34,7 +34,7 @@ def test_version_and_struct_layout():
     d = _lib.VIEW_PARAMS_DTYPE
     assert d.itemsize == 48
     assert [d.fields[k][1] for k in ("img", "top", "left", "h", "w", "flags", "order", "brightness", "contrast",
-                                     "saturation", "hue", "reserved")] == [0, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 44]
+                                     "saturation", "hue", "blur_sigma")] == [0, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 44]
 
 
 def test_argument_errors_without_gpu():

@@ -121,3 +121,45 @@ def test_live_reference_agrees_with_golden():
     v1, v2 = chain(A.u16_to_tv_image(g["images"][1]))
     assert np.array_equal(v1[0].numpy(), g["out_48"][1, 0])
     assert np.array_equal(v2[0].numpy(), g["out_48"][1, 1])
+
+
+def test_restatement_matches_reference_golden_with_default_blur():
+    """GaussianBlur(23) restated in numpy vs the reference class run with its default blur_prob=(1.0, 0.1)."""
+    g = np.load(os.path.join(GOLD, "aug_blur.npz"))
+    mean, std = float(g["mean"]), float(g["std"])
+    worst = 0.0
+    for crop in (32, 48):
+        for k, seed in enumerate(g["seeds"]):
+            torch.manual_seed(int(seed))
+            ps = A.draw_two_view_params(96, 128, blur_prob=(1.0, 0.1), solarize_prob=(0.0, 0.0))
+            for v in range(2):
+                assert int(ps[v]["blur"]) == int(g[f"blur_{crop}"][2 * k + v])
+                if ps[v]["blur"]:
+                    assert ps[v]["sigma"] == g[f"sigma_{crop}"][2 * k + v]
+                out = A.apply_view(g["images"][k], ps[v], crop, mean, std)
+                worst = max(worst, float(np.abs(out - g[f"out_{crop}"][k, v]).max()))
+    assert worst < 2e-5, worst
+
+
+def test_native_replay_records_blur_and_solarize_draws():
+    """csrc/rng_replay.cu records the GaussianBlur sigma and the RandomSolarize / RandomGrayscale outcomes it used to
+    consume silently: identical to the torch replay and to the reference's recorded sigmas."""
+    from medical_image_segmentation_b200 import params as P
+    g = np.load(os.path.join(GOLD, "aug_blur.npz"))
+    for k, seed in enumerate(g["seeds"]):
+        torch.manual_seed(int(seed))
+        p = P.draw_two_view_params(1, 96, 128, (1.0, 0.1), (0.0, 0.0))
+        assert [int(f >> 3) & 1 for f in p["flags"]] == [int(b) for b in g["blur_32"][2 * k:2 * k + 2]]
+        for v in range(2):
+            if g["blur_32"][2 * k + v]:
+                assert p["blur_sigma"][v] == np.float32(g["sigma_32"][2 * k + v])
+    torch.manual_seed(5)
+    a = P.draw_two_view_params_torch(200, 128, 160, (1.0, 0.1), (0.0, 0.2))
+    torch.manual_seed(5)
+    b = P.draw_two_view_params(200, 128, 160, (1.0, 0.1), (0.0, 0.2))
+    assert a.tobytes() == b.tobytes()
+    assert (a["flags"] & 16).any() and (a["flags"] & 4).any() and ((a["flags"] & 8) != 0)[::2].all()
+    gen = torch.Generator().manual_seed(5)                  # a private generator draws the same stream
+    before = torch.get_rng_state()
+    c = P.draw_two_view_params(200, 128, 160, (1.0, 0.1), (0.0, 0.2), generator=gen)
+    assert c.tobytes() == a.tobytes() and torch.equal(before, torch.get_rng_state())
