@@ -6,6 +6,15 @@
 ``ntxent_*``          canonical SimCLR NT-Xent.  PARITY
                       UNPINNED: the reference has no NT-Xent; these are
                       checked against torch autograd in fp64 only.
+``ntxent_*_bolts``    a SECOND, independently written restatement: the exp-sum form of the
+                      lightning-bolts SimCLR module the reference's callbacks / optimiser were
+                      adapted from (pl_bolts @748715e, models/self_supervised/simclr/simclr_module.py
+                      ``nt_xent_loss``; source not under /root/reference, restated from the
+                      published algorithm): no -inf mask, no log-sum-exp -- the self term is
+                      removed by subtracting e^(1/T), with eps = 1e-6 clamps.  The two forms, the
+                      committed vectors (tests/golden/ntxent.npz, oracle/make_ntxent_golden.py) and
+                      the CUDA kernels are tested against each other; that removes single-author
+                      risk, it does not pin the loss to the reference (nothing can).
 """
 from __future__ import annotations
 
@@ -91,3 +100,42 @@ def ntxent_rank_sharded(z_locals: list[torch.Tensor], temperature: float = 0.1):
         row0 += rows
     torch.stack(losses).sum().backward()
     return [float(l) for l in losses], [z.grad.clone() for z in zs]
+
+
+def ntxent_loss_bolts(z_a: torch.Tensor, z_b: torch.Tensor, temperature: float = 0.1, eps: float = 1e-6) -> torch.Tensor:
+    """lightning-bolts SimCLR ``nt_xent_loss`` (single process): out = normalize(z);
+    cov = out out^T; neg_i = sum_j exp(cov_ij / T) - e^(1/T) (clamped at eps);
+    pos_i = exp(<out1_i, out2_i> / T); loss = -mean log(pos / (neg + eps))."""
+    import math
+    out_1 = F.normalize(z_a, dim=1)
+    out_2 = F.normalize(z_b, dim=1)
+    out = torch.cat([out_1, out_2], dim=0)
+    cov = torch.mm(out, out.t().contiguous())
+    sim = torch.exp(cov / temperature)
+    neg = sim.sum(dim=-1)
+    row_sub = torch.full_like(neg, math.e ** (1 / temperature))
+    neg = torch.clamp(neg - row_sub, min=eps)
+    pos = torch.exp(torch.sum(out_1 * out_2, dim=-1) / temperature)
+    pos = torch.cat([pos, pos], dim=0)
+    return -torch.log(pos / (neg + eps)).mean()
+
+
+def ntxent_rank_sharded_bolts(z_locals: list[torch.Tensor], temperature: float = 0.1, eps: float = 1e-6):
+    """The bolts form with its SyncFunction gather, simulated in one process (fp64 autograd): every rank r computes
+    -mean log(pos / (neg + eps)) over ITS rows [z1_r; z2_r] against out_dist = [z1_all; z2_all] (bolts' canonical
+    gathered layout, not the rank-major one of the product -- the loss is invariant to that permutation), and
+    SyncFunction's backward hands each rank the SUM over ranks of dL_r'/dz_local.  Returns (losses, dz_locals)."""
+    import math
+    zs = [z.detach().double().clone().requires_grad_(True) for z in z_locals]
+    halves = [(F.normalize(z[:z.shape[0] // 2], dim=1), F.normalize(z[z.shape[0] // 2:], dim=1)) for z in zs]
+    out_dist = torch.cat([h[0] for h in halves] + [h[1] for h in halves], dim=0)
+    losses = []
+    for o1, o2 in halves:
+        out = torch.cat([o1, o2], dim=0)
+        sim = torch.exp(torch.mm(out, out_dist.t().contiguous()) / temperature)
+        neg = torch.clamp(sim.sum(dim=-1) - math.e ** (1 / temperature), min=eps)
+        pos = torch.exp(torch.sum(o1 * o2, dim=-1) / temperature)
+        pos = torch.cat([pos, pos], dim=0)
+        losses.append(-torch.log(pos / (neg + eps)).mean())
+    torch.stack(losses).sum().backward()
+    return [float(l.detach()) for l in losses], [z.grad.clone() for z in zs]

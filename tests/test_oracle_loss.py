@@ -45,3 +45,25 @@ def test_rank_sharded_convention_equals_global():
     for r in range(W):
         assert np.abs(grads[r][:B].numpy() - W * d1[r * B:(r + 1) * B]).max() < 1e-13
         assert np.abs(grads[r][B:].numpy() - W * d2[r * B:(r + 1) * B]).max() < 1e-13
+
+
+def test_two_independent_ntxent_forms_and_the_committed_vectors_agree():
+    """tests/golden/ntxent.npz was produced by the lightning-bolts exp-sum form (oracle/make_ntxent_golden.py); the
+    cross-entropy form the kernels were specified against must reproduce it (loss, lse, gradients), and the bolts form
+    must reproduce itself from the stored inputs.  (eps = 1e-6 against exp-sums >= 1e2: agreement ~1e-9.)"""
+    g = np.load(os.path.join(GOLD, "ntxent.npz"))
+    for tag in "abcd":
+        z1, z2, T = g[f"{tag}_z1"], g[f"{tag}_z2"], float(g[f"{tag}_T"])
+        loss, lse, d1, d2 = L.ntxent_closed_form(z1, z2, T)
+        assert abs(loss - float(g[f"{tag}_loss"])) <= 1e-7 * abs(loss)
+        assert np.abs(lse - g[f"{tag}_lse"]).max() <= 1e-10
+        ref = np.concatenate([g[f"{tag}_dz1"], g[f"{tag}_dz2"]])
+        got = np.concatenate([d1, d2])
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-6
+        again = L.ntxent_loss_bolts(torch.from_numpy(z1).double(), torch.from_numpy(z2).double(), T)
+        assert abs(float(again) - float(g[f"{tag}_loss"])) <= 1e-13
+    zl = [torch.from_numpy(z) for z in g["w4_z"]]
+    losses, grads = L.ntxent_rank_sharded(zl, float(g["w4_T"]))
+    assert np.abs(np.array(losses) - g["w4_loss"]).max() <= 1e-7
+    for r in range(4):
+        assert np.linalg.norm(grads[r].numpy() - g["w4_dz"][r]) / np.linalg.norm(g["w4_dz"][r]) <= 1e-6
