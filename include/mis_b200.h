@@ -190,10 +190,15 @@ int64_t mis_aug_algorithmic_bytes(const MisViewParams* params_host, int n_views,
  *                     TMEM as the A operand of the second MMA; dU (128 x D fp32) stays in TMEM for
  *                     the whole column walk.  grad_out may be NULL (= 1).  dz has z's dtype.
  *
- * rows, cols, row0 multiples of 128; D a multiple of 32 (backward: D <= 256, or a multiple of 256 -- wider
- * embeddings are walked in 256-column slices of dU, recomputing S per slice); T >= 0.025.
- * `scratch` must hold mis_ntxent_scratch_bytes(rows, cols, D) bytes.
+ * `rows` is the number of embedding rows the rank really has (any even number: a per-GPU batch of 96 gives 192).
+ * Every rank's block of the gathered matrix is padded to P = mis_ntxent_padded_rows(rows) (the next multiple of 128):
+ * u / u_all hold P (resp. world * P) rows, rinv / lse P (world * P) floats, and `cols`, `row0` are in PADDED
+ * coordinates (cols = world * P, row0 = rank * P).  The padding rows are zero vectors, masked as columns inside the
+ * tile kernels and skipped as rows; z and dz hold the valid rows only.
+ * D a multiple of 32 (backward: D <= 256, or a multiple of 256 -- wider embeddings are walked in 256-column slices
+ * of dU, recomputing S per slice); T >= 0.025.  `scratch` must hold mis_ntxent_scratch_bytes(rows, cols, D) bytes.
  * ------------------------------------------------------------------------------------------ */
+int mis_ntxent_padded_rows(int rows);
 int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D);
 
 int mis_ntxent_prep(const void* z, int z_dtype, int rows, int D, float* u, float* rinv, void* stream);
@@ -230,7 +235,8 @@ int mis_ntxent_bwd(const float* u_all, const float* lse_all, const void* z_rows,
  * epoch k is enqueued before its forward of epoch k+1 (one evaluation outstanding -- loss.py enforces it).
  * A consumer waits `timeout_s` seconds for a peer's flag; after that the kernel sets the abort word and TRAPS (the step
  * fails with a CUDA error instead of continuing on stale rows).  Use a time-out of the order of the NCCL watchdog's.
- * rows a multiple of 128 (at most 414 * 128 per rank), D as for mis_ntxent_fwd / mis_ntxent_bwd.
+ * rows: any even number (padded per rank as for mis_ntxent_fwd; at most 414 * 128 per rank); every peer buffer is
+ * sized with the padded rows; D as for mis_ntxent_fwd / mis_ntxent_bwd.
  * ------------------------------------------------------------------------------------------ */
 int mis_ntxent_fwd_peer(const void* z, int z_dtype, int rows, int D, float inv_T, int world, int rank,
                         void* const* u_peers0, void* const* u_peers1, void* const* lse_peers0,
@@ -260,6 +266,23 @@ int mis_ntxent_fwd_bwd(const void* z, int z_dtype, int rows, int D, float inv_T,
  * ------------------------------------------------------------------------------------------ */
 int mis_byol_loss_fwd_bwd(const float* preds, const float* targets, int rows, int D, float* loss,
                           float* dpreds, float* scratch_rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * EMA update of the momentum encoder as ONE multi-tensor kernel.
+ * Replaces BYOL.momentum_update (byol_pytorch.py:291-296, called at :253-255):
+ *     for po, pm in zip(online.parameters(), momentum.parameters()): pm.data.mul_(m).add_(po.data, alpha=1.0 - m)
+ * with pm = fma(po, float(1 - m), fl(pm * m)) over a device table of float32 tensors (bit-identical to the two ATen
+ * kernels).  table_dev[i].chunk0 = sum_{j<i} mis_ema_chunks(table[j].n); total_chunks = that sum over all tensors.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MisEmaEntry {
+  const void* online;     /* float32 [n], device  */
+  void* momentum;         /* float32 [n], device, updated in place */
+  int64_t n;
+  int64_t chunk0;
+} MisEmaEntry;
+
+int64_t mis_ema_chunks(int64_t n_elements);
+int mis_ema_update(const MisEmaEntry* table_dev, int n_tensors, int64_t total_chunks, float m, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Exact per-channel moments of uint16 slices: the statistics behind the normalisation constants.

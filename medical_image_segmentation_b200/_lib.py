@@ -26,6 +26,9 @@ VIEW_PARAMS_DTYPE = np.dtype([
 ], align=False)
 assert VIEW_PARAMS_DTYPE.itemsize == 48
 
+# numpy mirror of struct MisEmaEntry (32 bytes)
+EMA_ENTRY_DTYPE = np.dtype([("online", "<u8"), ("momentum", "<u8"), ("n", "<i8"), ("chunk0", "<i8")], align=False)
+
 EXPORTS = {
     "mis_version": (C.c_int, []),
     "mis_last_error": (C.c_char_p, []),
@@ -43,6 +46,7 @@ EXPORTS = {
     "mis_h2d_needed_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p,
                                       C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "mis_aug_algorithmic_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mis_ntxent_padded_rows": (C.c_int, [C.c_int]),
     "mis_ntxent_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "mis_ntxent_prep": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mis_ntxent_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
@@ -59,6 +63,8 @@ EXPORTS = {
     "mis_ntxent_fwd_bwd_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "mis_ntxent_fwd_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p]),
+    "mis_ema_chunks": (C.c_int64, [C.c_int64]),
+    "mis_ema_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_void_p]),
     "mis_u16_moments": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "mis_byol_loss_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),

@@ -34,6 +34,15 @@
 
 #include "aug_math.cuh"
 #include "aug_strip.cuh"
+
+namespace mis {
+namespace augc {
+bool rgb_supported(int s);
+int launch_rgb_color(void* out, int out_f32, const MisViewParams* params, int n_views, int s, const float* mean,
+                     const float* inv_std, cudaStream_t stream);
+}  // namespace augc
+}  // namespace mis
+
 #include "aug_tile.cuh"
 #include "common.cuh"
 
@@ -1055,9 +1064,11 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
   MIS_REQUIRE(out_dtype == MIS_DTYPE_BF16 || out_dtype == MIS_DTYPE_F32, MIS_ERR_INVALID_ARG,
               "mis_aug_two_view: out_dtype %d", out_dtype);
   MIS_REQUIRE(win_hi > win_lo, MIS_ERR_INVALID_ARG, "mis_aug_two_view: empty window [%g,%g]", win_lo, win_hi);
-  MIS_REQUIRE(C == 1, MIS_ERR_UNSUPPORTED,
-              "mis_aug_two_view: C=%d; only single-channel slices are implemented (3-channel saturation/hue "
-              "are a SURVEY 8f 'next' row)", C);
+  MIS_REQUIRE(C == 1 || C == 3, MIS_ERR_UNSUPPORTED, "mis_aug_two_view: C=%d; 1 or 3 channels", C);
+  MIS_REQUIRE(C == 1 || (use_tma == 0 && mis::augc::rgb_supported(s) && mis::augs::strip_supported(C, H, W, img_stride, s)),
+              MIS_ERR_UNSUPPORTED,
+              "mis_aug_two_view: 3-channel input runs on the strip kernel + colour kernel only: variant 0, crop a multiple "
+              "of 8 up to 192, even W, at most 5.5x downscaling (got s=%d, H=%d, W=%d, variant %d)", s, H, W, use_tma);
   MIS_REQUIRE(s >= 8 && s <= kBandRows * kMaxBands, MIS_ERR_UNSUPPORTED, "mis_aug_two_view: crop size %d not in [8,256]", s);
   MIS_REQUIRE((W & 1) == 0 && (img_stride & 1) == 0, MIS_ERR_UNSUPPORTED,
               "mis_aug_two_view: W (%d) and img_stride must be even", W);
@@ -1088,7 +1099,11 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
     t.out = out;
     t.s = s;
     t.out_f32 = out_dtype == MIS_DTYPE_F32 ? 1 : 0;
-    return mis::augs::launch_strip(t, n_views, window, reinterpret_cast<cudaStream_t>(stream));
+    t.raw_all = C == 3 ? 1 : 0;
+    if (int rc = mis::augs::launch_strip(t, n_views, window, reinterpret_cast<cudaStream_t>(stream))) return rc;
+    if (C == 3)      // colour ops mix the channels: a second kernel over the three parked planes of every view
+      return mis::augc::launch_rgb_color(out, t.out_f32, params, n_views, s, t.mean, t.inv_std, reinterpret_cast<cudaStream_t>(stream));
+    return MIS_OK;
   }
   if ((use_tma == 0 || use_tma == 3) && mis::augt::tile_supported(C, H, W, img_stride, s)) {
     mis::augt::TileArgs t = {};

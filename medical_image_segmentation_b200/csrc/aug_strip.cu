@@ -605,7 +605,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) aug_strip_kernel(cons
   t.vscale = vscale;
   t.vsup = vsup;
   t.vinv = vinv;
-  const bool jitter = (P.flags & MIS_VIEW_JITTER) != 0;
+  // raw_all (3-channel input): the colour ops mix channels, so this kernel only resamples and flips and leaves every
+  // plane as uint16 for the colour kernel (aug_rgb.cu)
+  const bool jitter = !a.raw_all && (P.flags & MIS_VIEW_JITTER) != 0;
   // brightness (op 0) before contrast (op 1) is applied while the tile is produced: the contrast mean needs it
   int pos_b = 0, pos_c = 0;
 #pragma unroll
@@ -732,7 +734,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) aug_strip_kernel(cons
   const float pb = P.brightness;
   const float cs = cf * (1.f / 65535.f);
   const bool sol = (P.flags & MIS_VIEW_SOLARIZE) != 0;
-  const bool raw = (P.flags & MIS_VIEW_BLUR) != 0;       // finished by mis_aug_blur_views
+  const bool raw = a.raw_all || (P.flags & MIS_VIEW_BLUR) != 0;       // finished by the colour / blur kernels
   uint8_t* const plane_ptr = static_cast<uint8_t*>(a.out) + (size_t)plane * s * s * (a.out_f32 ? 4 : 2);
   if ((s & 7) == 0) {
     const bool f32 = a.out_f32 != 0;
@@ -853,7 +855,8 @@ static bool make_plan(int H, int W, int s, Plan* best) {
 
 bool strip_supported(int C, int H, int W, int64_t img_stride, int s) {
   // class (3,4) covers 5.5x downscaling per axis: 31*5.5 + 2*5.5 + 2 <= 192 staged columns, 3 + 13 <= 16 aligned taps
-  if (!(C == 1 && s >= 8 && s <= 256 && (W & 1) == 0 && (img_stride & 1) == 0 && 2 * W <= 11 * s && 2 * H <= 11 * s))
+  if (!((C == 1 || (C == 3 && (s & 7) == 0)) && s >= 8 && s <= 256 && (W & 1) == 0 && (img_stride & 1) == 0 &&
+        ((int64_t)H * W & 1) == 0 && 2 * W <= 11 * s && 2 * H <= 11 * s))
     return false;
   Plan p;
   return make_plan(H, W, s, &p);

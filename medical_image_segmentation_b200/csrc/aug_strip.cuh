@@ -22,11 +22,12 @@ struct StripArgs {
   int nsx, nsy, rp;        // strips of 32 output columns, vertical parts, output rows per part
   int rowbuf;              // floats per intermediate-row buffer of a warp
   int dbl;                 // 1: two row buffers per warp (no second warp barrier per output row)
+  int raw_all;             // 1 (C == 3): resample + flip only; every plane is left as uint16 for mis rgb colour kernel
   uint32_t off_sched, off_fmask, off_row, off_misc;   // byte offsets into dynamic shared memory (parked tiles at 0)
 };
 
-// shapes the strip kernel covers: single channel, 8 <= s <= 256, even W / img_stride, at most 5.5x downscaling of the
-// whole slice per axis, and the shared-memory plan fits one SM
+// shapes the strip kernel covers: 1 or 3 channels (3: resample + flip only, crop a multiple of 8), 8 <= s <= 256, even
+// W / img_stride, at most 5.5x downscaling of the whole slice per axis, and the shared-memory plan fits one SM
 bool strip_supported(int C, int H, int W, int64_t img_stride, int s);
 int launch_strip(StripArgs a, int n_views, bool window, cudaStream_t stream);
 

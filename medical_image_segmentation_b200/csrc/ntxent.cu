@@ -79,7 +79,9 @@ struct Finish {
 };
 
 struct TileArgs {
-  int rows, cols, D, row0;
+  int rows, cols, D, row0;   // rows / cols / row0 are PADDED to multiples of 128
+  int rows_valid;            // embedding rows a rank really has; rows [rows_valid, rows) of every rank's block are padding:
+                             // masked as columns, skipped as rows
   int col_tiles, tiles_per_split;
   float k1;                // log2(e) / T
   int d0, ds;              // backward: columns [d0, d0 + ds) of dU are produced by this launch (ds <= 256)
@@ -431,7 +433,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
     const float ci = kBwd ? __expf(a.inv_T - lse_all[g_row_tile0 + r_in]) : 0.f;
     const float k1 = a.k1;
     const int il = row_tile * kTile + r_in;                       // local row index
-    const int pos_col = a.row0 + (il + (a.rows >> 1)) % a.rows;   // global column of this row's positive
+    const int pos_col = a.row0 + (il + (a.rows_valid >> 1)) % a.rows_valid;   // global column of this row's positive
     float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;         // independent partial sums: no serial FADD chain
     for (int t = grp; t < T; t += 2) {
       const int buf = grp;
@@ -448,7 +450,9 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
       // the cancellation P_ip + P_pi - 2 keeps full relative precision.
       const bool diag = (col0 == g_row_tile0);
       const int jpos = kBwd ? (pos_col - col0) : -1;
-      const bool special = diag || (jpos >= 0 && jpos < kTile);
+      // columns of a rank's block beyond its valid rows are padding: they must not enter any sum
+      const int jpad = a.rows_valid - (col0 % a.rows_per_rank);
+      const bool special = diag || (jpos >= 0 && jpos < kTile) || jpad < kTile;
 #pragma unroll 1
       for (int c = 0; c < kTile / 32; ++c) {
         uint32_t v[32];
@@ -471,7 +475,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float e = ex2f(fmaf(__uint_as_float(v[j]), k1, -k1));
-            if (j == jd) e = 0.f;
+            if (j == jd || c * 32 + j >= jpad) e = 0.f;
             if (kBwd) {
               float w = e * (ci + bars.cj[buf][c * 32 + j]);
               if (j == jp) w -= 2.f;
@@ -532,12 +536,19 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
     const float* u_all = fin.u_all[par];
     for (int r = warp; r < kTile; r += kThreads / 32) {
       const int i = row_tile * kTile + r;
+      if (i >= a.rows_valid) {       // padding row: a finite lse for the peers' c_j, no loss term
+        if (lane == 0) {
+          for (int q = 0; q < a.world; ++q) fin.lse_dst[par][q][fin.lse_off + i] = 0.f;
+          fin.row_loss[i] = 0.f;
+        }
+        continue;
+      }
       float sacc = 0.f;
       for (int k = lane; k < 2 * nsplit; k += 32) sacc += ldcg_f32(a.partial + (size_t)k * a.rows + i);
       sacc = warp_sum(sacc);
       const float lse = a.inv_T + logf(sacc);
       const float* ui = u_all + (size_t)(a.row0 + i) * a.D;
-      const float* up = u_all + (size_t)(a.row0 + (i + (a.rows >> 1)) % a.rows) * a.D;
+      const float* up = u_all + (size_t)(a.row0 + (i + (a.rows_valid >> 1)) % a.rows_valid) * a.D;
       float dot = 0.f;
       for (int d = lane; d < a.D; d += 32) dot = fmaf(ui[d], up[d], dot);
       dot = warp_sum(dot);
@@ -552,6 +563,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
     const float g = fin.scale * (fin.grad_out ? fin.grad_out[0] : 1.f);
     for (int r = warp; r < kTile; r += kThreads / 32) {
       const int i = row_tile * kTile + r;
+      if (i >= a.rows_valid) continue;            // padding row: z / dz hold the valid rows only
       const float rv = fin.rinv[i];
       auto z_at = [&](int d) {
         return fin.z_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(fin.z_rows)[(size_t)i * a.D + d])
@@ -589,7 +601,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
     if (tid == 0) {
       float tot = 0.f;
       for (int w = 0; w < kThreads / 32; ++w) tot += s_red[w];
-      fin.loss[0] = tot / (float)a.rows;
+      fin.loss[0] = tot / (float)a.rows_valid;
     }
   }
   if (tid <= row_tiles) fin.counters[tid] = 0u;          // (row_tiles < kThreads is checked on the host)
@@ -623,12 +635,18 @@ struct PrepPeers {
 
 // one warp per row: rinv = 1/max(|z|,1e-12), u = tf32(z * rinv), written to every rank's gathered matrix at row row0 + i
 template <typename T>
-__global__ void prep_kernel(const T* __restrict__ z, int rows, int D, int row0, float* __restrict__ rinv, const PrepPeers pe) {
+__global__ void prep_kernel(const T* __restrict__ z, int rows, int rows_pad, int D, int row0, float* __restrict__ rinv,
+                            const PrepPeers pe) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   PeerCtl* const ctl = pe.world > 1 ? pe.ctl[pe.rank] : nullptr;
   const uint32_t epoch = ctl ? ctl->epoch + 1u : 0u;
   const int par = (int)(epoch & 1u);
+  if (row >= rows && row < rows_pad) {            // padding rows of the 128-row tiles: zero vectors (masked as columns)
+    for (int d = lane; d < D; d += 32)
+      for (int q = 0; q < pe.world; ++q) pe.dst[par][q][(size_t)(row0 + row) * D + d] = 0.f;
+    if (lane == 0) rinv[row] = 0.f;
+  }
   if (row < rows) {
     float ss = 0.f;
     for (int d = lane; d < D; d += 32) {
@@ -671,11 +689,11 @@ __global__ void transpose_kernel(const float* __restrict__ u0, const float* __re
 // where the backward runs one tile-kernel launch per 256-column slice of dU (smaller D: folded into the tile kernel).
 template <typename T>
 __global__ void bwd_finalize_kernel(const float* __restrict__ partial, int nsplit, const T* __restrict__ z_rows,
-                                    const float* __restrict__ rinv, int D, int rows, float scale,
+                                    const float* __restrict__ rinv, int D, int rows, int rows_valid, float scale,
                                     const float* __restrict__ grad_out, T* __restrict__ dz) {
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (i >= rows) return;
+  if (i >= rows_valid) return;
   const float g = scale * (grad_out ? grad_out[0] : 1.f);
   const float r = rinv[i];
   auto du_at = [&](int d) {
@@ -783,10 +801,18 @@ static Plan make_plan(int rows, int cols) {
 }
 static inline size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
 
+static inline int pad_rows(int rows) { return (rows + kTile - 1) / kTile * kTile; }
+
+// `rows` = the embedding rows a rank really has (any even number); its block of the gathered matrix is padded to
+// pad_rows(rows); cols and row0 are in padded coordinates
 static int check_shapes(const char* who, int rows, int cols, int D, int row0, float inv_T, bool bwd) {
   MIS_REQUIRE(rows > 0 && cols > 0 && D > 0, MIS_ERR_INVALID_ARG, "%s: sizes must be positive", who);
-  MIS_REQUIRE(rows % kTile == 0 && cols % kTile == 0 && row0 % kTile == 0, MIS_ERR_UNSUPPORTED,
-              "%s: rows (%d), cols (%d) and row0 (%d) must be multiples of %d", who, rows, cols, row0, kTile);
+  MIS_REQUIRE(rows % 2 == 0, MIS_ERR_INVALID_ARG, "%s: rows (%d) = [view 1; view 2] must be even", who, rows);
+  const int rp = pad_rows(rows);
+  MIS_REQUIRE(cols % rp == 0 && row0 % rp == 0, MIS_ERR_INVALID_ARG,
+              "%s: cols (%d) and row0 (%d) must be multiples of the padded rows per rank (%d = %d rows padded to %d)", who,
+              cols, row0, rp, rows, kTile);
+  rows = rp;
   MIS_REQUIRE(rows / kTile < kThreads - 1, MIS_ERR_UNSUPPORTED, "%s: at most %d rows per rank", who, (kThreads - 2) * kTile);
   MIS_REQUIRE(D % kKBlock == 0 && D <= 8192, MIS_ERR_UNSUPPORTED, "%s: D=%d must be a multiple of 32 (<= 8192)", who, D);
   MIS_REQUIRE(!bwd || D <= 256 || D % 256 == 0, MIS_ERR_UNSUPPORTED,
@@ -817,9 +843,13 @@ struct Exchange {
 using namespace mis;
 using namespace mis::ntx;
 
+extern "C" int mis_ntxent_padded_rows(int rows) { return rows <= 0 ? 0 : pad_rows(rows); }
+
 extern "C" int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D) {
   if (rows <= 0 || cols <= 0 || D <= 0) return -1;
-  const Plan p = make_plan(rows < kTile ? kTile : rows, cols < kTile ? kTile : cols);
+  rows = pad_rows(rows);
+  cols = pad_rows(cols);
+  const Plan p = make_plan(rows, cols);
   size_t b = 0;
   b += al256(kCounterBytes + (size_t)cols * 4);       // arrival counters + per-row loss terms
   b += al256((size_t)D * cols * 4);                   // U^T
@@ -829,11 +859,12 @@ extern "C" int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D) {
 
 static int launch_prep(const void* z, int z_dtype, int rows, int D, int row0, float* rinv, const PrepPeers& pe, cudaStream_t st) {
   const int wpb = 8;
-  const dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
+  const int rp = pad_rows(rows);
+  const dim3 grid((rp + wpb - 1) / wpb), block(wpb * 32);
   if (z_dtype == MIS_DTYPE_F32)
-    prep_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(z), rows, D, row0, rinv, pe);
+    prep_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(z), rows, rp, D, row0, rinv, pe);
   else
-    prep_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(z), rows, D, row0, rinv, pe);
+    prep_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(z), rows, rp, D, row0, rinv, pe);
   MIS_CUDA_TRY(cudaGetLastError());
   return MIS_OK;
 }
@@ -882,6 +913,8 @@ static int ntxent_fwd_impl(const float* u0, const float* u1, int cols, int D, in
   MIS_REQUIRE(scratch_bytes >= mis_ntxent_scratch_bytes(rows, cols, D), MIS_ERR_INVALID_ARG,
               "mis_ntxent_fwd: scratch too small (%lld < %lld)", (long long)scratch_bytes,
               (long long)mis_ntxent_scratch_bytes(rows, cols, D));
+  const int rows_valid = rows;
+  rows = pad_rows(rows);
   const Plan p = make_plan(rows, cols);
   uint8_t* sc = static_cast<uint8_t*>(scratch);
   float* partial = reinterpret_cast<float*>(sc + al256(kCounterBytes + (size_t)cols * 4) + al256((size_t)D * cols * 4));
@@ -891,11 +924,12 @@ static int ntxent_fwd_impl(const float* u0, const float* u1, int cols, int D, in
   if (int rc = make_map(&map1, u1 ? u1 : u0, (uint64_t)D, (uint64_t)cols, kTile)) return rc;
   TileArgs a = {};
   a.rows = rows; a.cols = cols; a.D = D; a.row0 = row0;
+  a.rows_valid = rows_valid;
   a.col_tiles = p.col_tiles; a.tiles_per_split = p.tiles_per_split;
   a.k1 = kLog2e * inv_T;
   a.inv_T = inv_T;
   a.partial = partial;
-  a.world = ex.world; a.rank = ex.rank; a.rows_per_rank = rows;
+  a.world = ex.world; a.rank = ex.rank; a.rows_per_rank = rows;      // (padded)
   a.epoch_add = 1;
   a.timeout_clk = ex.timeout_clk;
   a.fin.fold = 1;
@@ -942,6 +976,8 @@ static int ntxent_bwd_impl(const float* u0, const float* u1, const float* lse0, 
   MIS_REQUIRE(scratch_bytes >= mis_ntxent_scratch_bytes(rows, cols, D), MIS_ERR_INVALID_ARG,
               "mis_ntxent_bwd: scratch too small (%lld < %lld)", (long long)scratch_bytes,
               (long long)mis_ntxent_scratch_bytes(rows, cols, D));
+  const int rows_valid = rows;
+  rows = pad_rows(rows);
   const Plan p = make_plan(rows, cols);
   uint8_t* sc = static_cast<uint8_t*>(scratch);
   float* ut = reinterpret_cast<float*>(sc + al256(kCounterBytes + (size_t)cols * 4));
@@ -957,9 +993,10 @@ static int ntxent_bwd_impl(const float* u0, const float* u1, const float* lse0, 
   const int ds = D <= 256 ? D : 256;     // dU lives in TMEM columns 256..511: at most 256 columns per launch;
                                          // wider embeddings recompute S once per 256-column slice
   if (int rc = make_map(&map_ut, ut, (uint64_t)cols, (uint64_t)D, (uint32_t)ds)) return rc;
-  const float scale = grad_scale * inv_T / (float)rows;
+  const float scale = grad_scale * inv_T / (float)rows_valid;
   TileArgs a = {};
   a.rows = rows; a.cols = cols; a.D = D; a.row0 = row0;
+  a.rows_valid = rows_valid;
   a.col_tiles = p.col_tiles; a.tiles_per_split = p.tiles_per_split;
   a.k1 = kLog2e * inv_T;
   a.lse[0] = lse0;
@@ -992,10 +1029,10 @@ static int ntxent_bwd_impl(const float* u0, const float* u1, const float* lse0, 
     const dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
     if (z_dtype == MIS_DTYPE_F32)
       bwd_finalize_kernel<float><<<grid, block, 0, st>>>(partial, p.nsplit, static_cast<const float*>(z_rows), rinv_rows, D,
-                                                          rows, scale, grad_out, static_cast<float*>(dz));
+                                                          rows, rows_valid, scale, grad_out, static_cast<float*>(dz));
     else
       bwd_finalize_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(partial, p.nsplit, static_cast<const __nv_bfloat16*>(z_rows),
-                                                                  rinv_rows, D, rows, scale, grad_out,
+                                                                  rinv_rows, D, rows, rows_valid, scale, grad_out,
                                                                   static_cast<__nv_bfloat16*>(dz));
     MIS_CUDA_TRY(cudaGetLastError());
   }
@@ -1020,7 +1057,8 @@ extern "C" int mis_ntxent_fwd_peer(const void* z, int z_dtype, int rows, int D, 
   Exchange ex;
   if (int rc = make_exchange(&ex, "mis_ntxent_fwd_peer", world, rank, u_peers0, u_peers1, lse_peers0, lse_peers1, ctl_peers,
                              timeout_s)) return rc;
-  if (int rc = check_shapes("mis_ntxent_fwd_peer", rows, world * rows, D, rank * rows, inv_T, false)) return rc;
+  const int rp = pad_rows(rows > 0 ? rows : 1);
+  if (int rc = check_shapes("mis_ntxent_fwd_peer", rows, world * rp, D, rank * rp, inv_T, false)) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   PrepPeers pe = {};
   pe.world = world;
@@ -1030,8 +1068,8 @@ extern "C" int mis_ntxent_fwd_peer(const void* z, int z_dtype, int rows, int D, 
     pe.dst[1][r] = ex.u_peers[1][r];
     pe.ctl[r] = ex.ctl_peers[r];
   }
-  if (int rc = launch_prep(z, z_dtype, rows, D, rank * rows, rinv, pe, st)) return rc;
-  return ntxent_fwd_impl(ex.u_peers[0][rank], ex.u_peers[1][rank], world * rows, D, rank * rows, rows, inv_T, ex, nullptr,
+  if (int rc = launch_prep(z, z_dtype, rows, D, rank * rp, rinv, pe, st)) return rc;
+  return ntxent_fwd_impl(ex.u_peers[0][rank], ex.u_peers[1][rank], world * rp, D, rank * rp, rows, inv_T, ex, nullptr,
                          loss, scratch, scratch_bytes, st);
 }
 
@@ -1043,16 +1081,18 @@ extern "C" int mis_ntxent_bwd_peer(const void* z_rows, int z_dtype, const float*
   Exchange ex;
   if (int rc = make_exchange(&ex, "mis_ntxent_bwd_peer", world, rank, u_peers0, u_peers1, lse_peers0, lse_peers1, ctl_peers,
                              timeout_s)) return rc;
+  const int rp = pad_rows(rows > 0 ? rows : 1);
   return ntxent_bwd_impl(ex.u_peers[0][rank], ex.u_peers[1][rank], ex.lse_peers[0][rank], ex.lse_peers[1][rank], z_rows,
-                         z_dtype, rinv_rows, world * rows, D, rank * rows, rows, inv_T, grad_scale, grad_out, dz, ex, scratch,
+                         z_dtype, rinv_rows, world * rp, D, rank * rp, rows, inv_T, grad_scale, grad_out, dz, ex, scratch,
                          scratch_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ---- single-rank convenience: prep -> forward -> backward in one call (4 kernels + 2 memsets, one host round trip) ----
-static inline size_t ws_u_bytes(int rows, int D) { return al256((size_t)rows * D * 4); }
-static inline size_t ws_row_bytes(int rows) { return al256((size_t)rows * 4); }
+static inline size_t ws_u_bytes(int rows, int D) { return al256((size_t)pad_rows(rows) * D * 4); }
+static inline size_t ws_row_bytes(int rows) { return al256((size_t)pad_rows(rows) * 4); }
 
 extern "C" int64_t mis_ntxent_fwd_bwd_workspace_bytes(int rows, int D) {
+  if (rows <= 0 || D <= 0) return -1;
   const int64_t sc = mis_ntxent_scratch_bytes(rows, rows, D);
   if (sc < 0) return -1;
   return (int64_t)(ws_u_bytes(rows, D) + 2 * ws_row_bytes(rows)) + sc;
@@ -1072,9 +1112,10 @@ extern "C" int mis_ntxent_fwd_bwd(const void* z, int z_dtype, int rows, int D, f
   float* lse = reinterpret_cast<float*>(w + ws_u_bytes(rows, D) + ws_row_bytes(rows));
   void* scratch = w + ws_u_bytes(rows, D) + 2 * ws_row_bytes(rows);
   const int64_t sc = mis_ntxent_scratch_bytes(rows, rows, D);
+  const int rp = pad_rows(rows);
   if (int rc = mis_ntxent_prep(z, z_dtype, rows, D, u, rinv, stream)) return rc;
-  if (int rc = mis_ntxent_fwd(u, rows, D, 0, rows, inv_T, lse, loss, scratch, sc, stream)) return rc;
-  return mis_ntxent_bwd(u, lse, z, z_dtype, rinv, rows, D, 0, rows, inv_T, 1.0f, nullptr, dz, scratch, sc, stream);
+  if (int rc = mis_ntxent_fwd(u, rp, D, 0, rows, inv_T, lse, loss, scratch, sc, stream)) return rc;
+  return mis_ntxent_bwd(u, lse, z, z_dtype, rinv, rp, D, 0, rows, inv_T, 1.0f, nullptr, dz, scratch, sc, stream);
 }
 
 extern "C" int mis_byol_loss_fwd_bwd(const float* preds, const float* targets, int rows, int D, float* loss,

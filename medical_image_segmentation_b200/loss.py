@@ -146,13 +146,19 @@ class CudaKernels:
             raise RuntimeError("nt_xent_loss has no CPU path: embeddings must be CUDA tensors")
         z = z.contiguous()
         rows, D = z.shape
-        u = torch.empty((rows, D), dtype=torch.float32, device=z.device)
-        rinv = torch.empty((rows,), dtype=torch.float32, device=z.device)
+        rp = CudaKernels.padded_rows(rows)          # the rank's block of the gathered matrix: rows padded to 128
+        u = torch.empty((rp, D), dtype=torch.float32, device=z.device)
+        rinv = torch.empty((rp,), dtype=torch.float32, device=z.device)
         with _on_device(z.device):
             rc = _lib.lib.mis_ntxent_prep(z.data_ptr(), _dt(z), rows, D, u.data_ptr(), rinv.data_ptr(), _stream(z))
         _lib.check(rc, "mis_ntxent_prep")
         CudaKernels.launches += 1
         return z, u, rinv
+
+    @staticmethod
+    def padded_rows(rows: int) -> int:
+        """Rows of one rank's block in the gathered matrix (mis_ntxent_padded_rows: the next multiple of 128)."""
+        return int(_lib.lib.mis_ntxent_padded_rows(int(rows)))
 
     _workspaces: dict = {}   # (device, rows, D, stream) -> uint8 workspace of the single-rank fused path (stream-ordered reuse)
     _graphs: dict = {}       # (device, rows, D, dtype, inv_T, stream) -> captured single-rank step (MIS_NTXENT_GRAPH=1)
@@ -218,7 +224,7 @@ class CudaKernels:
         if ex.scratch is None:
             rows, D = z.shape
             ex.scratch = CudaKernels.scratch(rows, ex.cols, D, z.device)
-            ex.rinv = torch.empty((rows,), dtype=torch.float32, device=z.device)
+            ex.rinv = torch.empty((CudaKernels.padded_rows(rows),), dtype=torch.float32, device=z.device)
 
     @staticmethod
     def _launch_fwd_peer(z, ex, inv_T, loss):
@@ -275,7 +281,7 @@ class CudaKernels:
     @staticmethod
     def fwd(u_all: torch.Tensor, row0: int, rows: int, inv_T: float, scratch: torch.Tensor):
         cols, D = u_all.shape
-        lse = torch.empty((rows,), dtype=torch.float32, device=u_all.device)
+        lse = torch.empty((CudaKernels.padded_rows(rows),), dtype=torch.float32, device=u_all.device)
         loss = torch.empty((1,), dtype=torch.float32, device=u_all.device)
         with _on_device(u_all.device):
             rc = _lib.lib.mis_ntxent_fwd(u_all.data_ptr(), cols, D, row0, rows, inv_T, lse.data_ptr(), loss.data_ptr(),
@@ -345,7 +351,7 @@ class _NTXent(torch.autograd.Function):
         z, u, rinv = kernels.prep(z)
         u_all = _all_gather_rows(u, group) if distributed else u
         scratch = kernels.scratch(rows, u_all.shape[0], u_all.shape[1], z.device)
-        lse, loss = kernels.fwd(u_all, rank * rows, rows, inv_T, scratch)
+        lse, loss = kernels.fwd(u_all, rank * kernels.padded_rows(rows), rows, inv_T, scratch)
         ctx.save_for_backward(z, u_all, rinv, lse)
         ctx.meta = (inv_T, group, distributed, rank, kernels, scratch)
         return loss.reshape(())
@@ -367,7 +373,7 @@ class _NTXent(torch.autograd.Function):
         z, u_all, rinv, lse = ctx.saved_tensors
         inv_T, group, distributed, rank, kernels, scratch = ctx.meta
         lse_all = _all_gather_rows(lse, group) if distributed else lse
-        dz = kernels.bwd(u_all, lse_all, z, rinv, rank * z.shape[0], inv_T, grad_out, scratch)
+        dz = kernels.bwd(u_all, lse_all, z, rinv, rank * kernels.padded_rows(z.shape[0]), inv_T, grad_out, scratch)
         return dz, None, None, None
 
 

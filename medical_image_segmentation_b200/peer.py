@@ -44,8 +44,10 @@ class PeerExchange:
         self.rank = dist.get_rank(group)
         if self.world > MAX_PEERS:
             raise RuntimeError(f"peer exchange covers one node (<= {MAX_PEERS} ranks), got {self.world}")
+        from . import _lib
         self.rows, self.D = rows, D
-        self.cols = self.world * rows
+        self.rows_pad = int(_lib.lib.mis_ntxent_padded_rows(rows))     # every rank's block is padded to 128-row tiles
+        self.cols = self.world * self.rows_pad
         u_bytes = _al256(self.cols * D * 4)
         l_bytes = _al256(self.cols * 4)
         self.off_u = [_CTL_BYTES, _CTL_BYTES + u_bytes]

@@ -262,6 +262,76 @@ def gaussian_blur(x: np.ndarray, sigma: float, kernel_size: int = 23) -> np.ndar
     return out
 
 
+def _gray(x: np.ndarray) -> np.ndarray:
+    """_rgb_to_grayscale_image (functional/_color.py:31-48): r.mul(0.2989).add_(g, alpha=0.587).add_(b, alpha=0.114)."""
+    f32 = np.float32
+    return ((x[0] * f32(0.2989) + x[1] * f32(0.587)).astype(f32) + x[2] * f32(0.114)).astype(f32)
+
+
+def _adjust_hue(x: np.ndarray, hue: float) -> np.ndarray:
+    """adjust_hue_image for a float [3,h,w] image (functional/_color.py:300-396): _rgb_to_hsv, h = (h + hue) mod 1,
+    _hsv_to_rgb -- the same expressions in float32."""
+    f32 = np.float32
+    r, g, b = x[0], x[1], x[2]
+    maxc = x.max(axis=0)
+    minc = x.min(axis=0)
+    eqc = maxc == minc
+    rng = (maxc - minc).astype(f32)
+    sat = (rng / np.where(eqc, f32(1), maxc)).astype(f32)
+    div = np.where(eqc, f32(1), rng).astype(f32)
+    rc, gc, bc = (((maxc - c) / div).astype(f32) for c in (r, g, b))
+    neq_r = maxc != r
+    eq_g = maxc == g
+    hg = ((rc + f32(2.0)).astype(f32) - bc).astype(f32) * (eq_g & neq_r)
+    hr = (bc - gc).astype(f32) * (~neq_r)
+    hb = ((gc + f32(4.0)).astype(f32) - rc).astype(f32) * (neq_r & ~eq_g)
+    h = ((hr + hg).astype(f32) + hb).astype(f32)
+    h = np.fmod((h * f32(1.0 / 6.0)).astype(f32) + f32(1.0), f32(1.0)).astype(f32)
+    h = np.remainder((h + f32(hue)).astype(f32), f32(1.0)).astype(f32)
+    h6 = (h * f32(6)).astype(f32)
+    i = np.floor(h6)
+    f = (h6 - i).astype(f32)
+    i = np.remainder(i.astype(np.int32), 6)
+    v = maxc
+    sxf = (sat * f).astype(f32)
+    oms = (f32(1.0) - sat).astype(f32)
+    q = np.clip(((f32(1.0) - sxf).astype(f32) * v).astype(f32), 0, 1)
+    t = np.clip(((sxf + oms).astype(f32) * v).astype(f32), 0, 1)
+    p = np.clip((oms * v).astype(f32), 0, 1)
+    vpqt = np.stack([v, p, q, t])
+    select = np.array([[0, 2, 1, 1, 3, 0], [3, 0, 0, 2, 1, 1], [1, 1, 3, 0, 0, 2]])
+    return np.take_along_axis(vpqt, select[:, i], axis=0).astype(f32)
+
+
+def color_and_normalize_rgb(x: np.ndarray, params: dict, mean, std) -> np.ndarray:
+    """The colour part of the chain for a float32 [3,s,s] image in [0,1] (lightning_module.py:51-57):
+    ColorJitter ops in fn_idx order, RandomGrayscale, GaussianBlur, RandomSolarize, Normalize."""
+    f32 = np.float32
+    x = np.asarray(x, f32)
+    if params["jitter"]:
+        for k in params["order"]:
+            if k == 0:
+                x = np.clip(x * f32(params["brightness"]), f32(0), f32(1)).astype(f32)
+            elif k == 1:      # mean over the grayscale image, functional/_color.py:199-204
+                mu = _gray(x).mean(dtype=np.float64).astype(f32)
+                c = float(params["contrast"])
+                x = np.clip(x * f32(c) + mu * f32(1.0 - c), f32(0), f32(1)).astype(f32)
+            elif k == 2:      # blend(x, gray(x), s), :151-166
+                sf = float(params["saturation"])
+                x = np.clip(x * f32(sf) + _gray(x)[None] * f32(1.0 - sf), f32(0), f32(1)).astype(f32)
+            else:
+                x = _adjust_hue(x, float(params["hue"]))
+    if params.get("gray"):    # RandomGrayscale: gray replicated over the three channels (v2/_color.py:33-55)
+        x = np.repeat(_gray(x)[None], 3, axis=0)
+    if params.get("blur"):
+        x = np.stack([gaussian_blur(x[c], params["sigma"]) for c in range(3)])
+    if params.get("solarize"):
+        x = np.where(x >= f32(SOLARIZE_THRESHOLD), f32(1) - x, x).astype(f32)
+    m = np.asarray(mean, f32).reshape(3, 1, 1)
+    sd = np.asarray(std, f32).reshape(3, 1, 1)
+    return ((x - m) / sd).astype(f32)
+
+
 def color_and_normalize(x: np.ndarray, params: dict, mean: float, std: float) -> np.ndarray:
     f32 = np.float32
     x = np.asarray(x, f32)
@@ -298,6 +368,11 @@ def apply_view(img_u16: np.ndarray, params: dict, crop_size: int, mean: float, s
     else:
         x = np.clip((x - f32(lo)) * f32(1.0 / (hi - lo)), f32(0), f32(1)).astype(f32)
     t, l, h, w = params["top"], params["left"], params["h"], params["w"]
+    if x.ndim == 3:                                  # [3,H,W]: resample per channel, colour ops across channels
+        out = np.stack([aa_resize(x[c, t:t + h, l:l + w], crop_size, crop_size) for c in range(x.shape[0])])
+        if params["flip"]:
+            out = out[:, :, ::-1]
+        return color_and_normalize_rgb(out, params, mean, std)
     crop = x[t:t + h, l:l + w]                       # crop_image: slice before resize
     out = aa_resize(crop, crop_size, crop_size)
     if params["flip"]:

@@ -20,6 +20,8 @@ params_stream.npz  crop boxes / flags for 400 images (800 views) at 512x512, 256
                 448x448 + the generator state after, pinning the RNG replay.
 aug_blur.npz    the reference's DEFAULT blur_prob=(1.0, 0.1) (GaussianBlur(23) on view 1 always): 6 slices 96x128 at crops
                 32 / 48 (full outputs, params, blur flags, sigmas) and 4 slices 512x512 at crop 224 (samples, sums).
+aug_rgb.npz     8 synthetic 3-channel uint16 images 80x96 at crop 32 through the reference class (saturation, hue,
+                RandomGrayscale live), without and with its default GaussianBlur.
 byol_loss.npz   inputs and outputs of the reference BYOL loss.
 """
 from __future__ import annotations
@@ -169,10 +171,33 @@ def make_blur_golden(Ref):
     np.savez_compressed(os.path.join(GOLD, "aug_blur.npz"), **blob)
 
 
+def make_rgb_golden(Ref):
+    """aug_rgb.npz: the reference class on 3-channel float input (what its IMAGENET / CIFAR modules feed it after
+    decoding, lightning_module.py:408,482-488, here from uint16 RGB so that no 8-bit rounding enters): saturation, hue,
+    RandomGrayscale and the default GaussianBlur(23); solarize_prob=(0, 0) (RandomSolarize(128) raises on float images)."""
+    imgs = np.stack([np.stack([synth.ct_like_slice(80, 96, seed=90 + 3 * i + c) if (i + c) % 2 == 0
+                               else synth.uniform_slice(80, 96, seed=90 + 3 * i + c) for c in range(3)]) for i in range(8)])
+    seeds = 5000 + np.arange(8)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    blob = dict(images=imgs, seeds=seeds, mean=np.array(mean), std=np.array(std))
+    for tag, kw in (("noblur", dict(blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0))), ("blur", dict(solarize_prob=(0.0, 0.0)))):
+        chain = Ref(crop_size=32, mean=mean, std=std, **kw)
+        outs = []
+        for img, seed in zip(imgs, seeds):
+            torch.manual_seed(int(seed))
+            v1, v2 = chain(u16_to_tv_image(img))
+            outs.append(np.stack([v1.numpy(), v2.numpy()]))
+        blob[f"out_{tag}"] = np.stack(outs)
+    np.savez_compressed(os.path.join(GOLD, "aug_rgb.npz"), **blob)
+
+
 def main():
     import cv2
     if "--blur-only" in sys.argv:
         make_blur_golden(ref_import.load_reference_transforms())
+        return
+    if "--rgb-only" in sys.argv:
+        make_rgb_golden(ref_import.load_reference_transforms())
         return
 
     Ref = ref_import.load_reference_transforms()
@@ -218,6 +243,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "aug_512.npz"), **blob)
 
     make_blur_golden(Ref)
+    make_rgb_golden(Ref)
 
     # ---- params_stream: RNG replay pin ----------------------------------------------
     blob = {}

@@ -8,6 +8,10 @@ import torch
 
 class TorchKernels:
     @staticmethod
+    def padded_rows(rows):
+        return rows          # the stand-in needs no 128-row tiles
+
+    @staticmethod
     def prep(z):
         z = z.contiguous()
         zd = z.double()

@@ -48,7 +48,8 @@ def test_argument_errors_without_gpu():
     p = buf.ctypes.data
     args = lambda **kw: [kw.get("src", p), 1, kw.get("C", 1), 8, kw.get("W", 8), 64, p, 1, 0.0, kw.get("hi", 65535.0),
                          C.cast(f, C.c_void_p), C.cast(f, C.c_void_p), p, kw.get("s", 8), kw.get("dt", 0), 1, None]
-    assert lib.mis_aug_two_view(*args(C=3)) == _lib.MIS_ERR_UNSUPPORTED
+    assert lib.mis_aug_two_view(*args(C=2)) == _lib.MIS_ERR_UNSUPPORTED
+    assert lib.mis_aug_two_view(*args(C=3, s=12)) == _lib.MIS_ERR_UNSUPPORTED      # 3 channels: crop a multiple of 8
     assert lib.mis_aug_two_view(*args(W=7)) == _lib.MIS_ERR_UNSUPPORTED
     assert lib.mis_aug_two_view(*args(s=300)) == _lib.MIS_ERR_UNSUPPORTED
     assert lib.mis_aug_two_view(*args(dt=7)) == _lib.MIS_ERR_INVALID_ARG
@@ -57,7 +58,9 @@ def test_argument_errors_without_gpu():
         _lib.check(_lib.MIS_ERR_UNSUPPORTED, "x")
     with pytest.raises(ValueError):
         _lib.check(_lib.MIS_ERR_INVALID_ARG, "x")
-    assert lib.mis_ntxent_fwd(p, 100, 64, 0, 100, 10.0, p, p, p, 1 << 30, None) == _lib.MIS_ERR_UNSUPPORTED
+    assert lib.mis_ntxent_fwd(p, 100, 64, 0, 100, 10.0, p, p, p, 1 << 30, None) == _lib.MIS_ERR_INVALID_ARG   # cols not padded
+    assert lib.mis_ntxent_fwd(p, 128, 64, 0, 99, 10.0, p, p, p, 1 << 30, None) == _lib.MIS_ERR_INVALID_ARG    # odd rows
+    assert lib.mis_ntxent_padded_rows(100) == 128 and lib.mis_ntxent_padded_rows(256) == 256
     assert lib.mis_ntxent_fwd(p, 128, 64, 0, 128, 100.0, p, p, p, 1 << 30, None) == _lib.MIS_ERR_UNSUPPORTED
     assert lib.mis_ntxent_fwd(p, 128, 64, 0, 128, 10.0, p, p, p, 16, None) == _lib.MIS_ERR_INVALID_ARG
     assert lib.mis_ntxent_scratch_bytes(2048, 2048, 128) > 2048 * 128 * 4
@@ -104,7 +107,7 @@ def test_peer_exchange_argument_errors_and_mode_switch(monkeypatch):
     assert fwd(2, 0, u0=null_tbl) == _lib.MIS_ERR_INVALID_ARG
     assert b"rank 1" in lib.mis_last_error()
     assert fwd(2, 0, timeout=0.0) == _lib.MIS_ERR_INVALID_ARG
-    assert fwd(2, 0, rows=100) == _lib.MIS_ERR_UNSUPPORTED   # rows per rank must be a multiple of 128
+    assert fwd(2, 0, rows=99) == _lib.MIS_ERR_INVALID_ARG    # rows = [view 1; view 2] must be even
     assert lib.mis_ntxent_bwd_peer(p, 1, p, 128, 64, 10.0, 1.0, None, p, 2, 5, tbl, tbl, tbl, tbl, tbl, 600.0, p, 1 << 30,
                                    None) == _lib.MIS_ERR_INVALID_ARG
     monkeypatch.setenv("MIS_NTXENT_EXCHANGE", "nccl")

@@ -238,6 +238,62 @@ def test_default_arguments_full_size_blur_and_solarize():
             _check_view(out[v * 4 + i, 0], imgs[i], p[2 * i + v], 224, f"default args img {i} view {v}")
 
 
+@pytest.mark.parametrize("tag", ["noblur", "blur"])
+def test_three_channel_input_matches_reference_golden(tag):
+    """[B,3,H,W] uint16 input: saturation, hue and RandomGrayscale are live.  Golden: the unmodified reference class on
+    the same 3-channel float image (aug_rgb.npz), without and with its default GaussianBlur(23)."""
+    g = np.load(os.path.join(GOLD, "aug_rgb.npz"))
+    from medical_image_segmentation_b200.transforms import FusedTwoViewTransforms
+    kw = dict(blur_prob=(0.0, 0.0)) if tag == "noblur" else {}
+    t = FusedTwoViewTransforms(32, tuple(g["mean"]), tuple(g["std"]), solarize_prob=(0.0, 0.0), out_dtype=torch.float32, **kw)
+    x = torch.from_numpy(g["images"]).cuda()
+    worst = 0.0
+    for k, seed in enumerate(g["seeds"]):
+        torch.manual_seed(int(seed))
+        v1, v2 = t(x[k:k + 1])
+        assert v1.shape == (1, 3, 32, 32)
+        for v, out in enumerate((v1, v2)):
+            worst = max(worst, _check(out[0].cpu().numpy(), g[f"out_{tag}"][k, v], f"rgb {tag} img {k} view {v}"))
+    assert worst < 2e-4
+
+
+def test_three_channel_batch_matches_oracle():
+    """3-channel batch at the reference's RADIOLOGY / IMAGENET_FFCV crop (112), default ctor arguments (blur, solarize),
+    bf16 == round(fp32), gray-replicated slices (what the reference's beton stores, pytorch_datasets.py:144) give three
+    equal planes."""
+    from medical_image_segmentation_b200.transforms import FusedTwoViewTransforms
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    B, H, W, crop = 4, 200, 232, 112
+    imgs = np.stack([synth.batch_512(3, seed=60 + i, H=H, W=W) for i in range(B)])      # [B,3,H,W]
+    x = torch.from_numpy(imgs).cuda()
+    tf = FusedTwoViewTransforms(crop, mean, std, out_dtype=torch.float32)
+    tb = FusedTwoViewTransforms(crop, mean, std)
+    torch.manual_seed(31)
+    tf(x)
+    torch.manual_seed(31)
+    tb(x)
+    assert torch.equal(tf.views_buffer.to(torch.bfloat16), tb.views_buffer)
+    out, p = tf.views_buffer.cpu().numpy(), tf.last_params
+    for i in range(B):
+        for v in range(2):
+            par = _oracle_params(p[2 * i + v])
+            par.update(saturation=float(p[2 * i + v]["saturation"]), hue=float(p[2 * i + v]["hue"]),
+                       gray=bool(p[2 * i + v]["flags"] & 4))
+            ref = A.apply_view(imgs[i], par, crop, mean, std)
+            skip = None
+            if par["solarize"]:
+                pre = A.apply_view(imgs[i], dict(par, solarize=False), crop, mean, std)
+                pre = pre * np.asarray(std, np.float32).reshape(3, 1, 1) + np.asarray(mean, np.float32).reshape(3, 1, 1)
+                skip = np.abs(pre - A.SOLARIZE_THRESHOLD) < 1e-4
+            _check(out[v * B + i], ref, f"rgb batch img {i} view {v}", skip)
+    gray3 = torch.from_numpy(np.repeat(imgs[:, :1], 3, axis=1)).cuda()
+    tg = FusedTwoViewTransforms(crop, (0.2,) * 3, (0.2,) * 3, out_dtype=torch.float32)
+    torch.manual_seed(5)
+    tg(gray3)
+    o = tg.views_buffer
+    assert (o[:, 0] - o[:, 1]).abs().max().item() <= 2e-4 and (o[:, 0] - o[:, 2]).abs().max().item() <= 2e-4
+
+
 def test_solarize_and_blur_flags_on_hand_made_records():
     """Every combination of flip / jitter order / blur / solarize on one slice, against the oracle (the solarize
     threshold is the reference's 128 on the 0..255 scale = 128/255 here)."""
@@ -276,8 +332,10 @@ def test_argument_errors_mirror_reference_style():
     with pytest.raises(NotImplementedError):          # odd width
         t(torch.zeros(1, 1, 64, 63, dtype=torch.uint16).cuda())
     from medical_image_segmentation_b200.transforms import FusedTwoViewTransforms
-    with pytest.raises(NotImplementedError):          # 3 channels
-        FusedTwoViewTransforms(32, (0.5,) * 3, (0.2,) * 3)(torch.zeros(1, 3, 64, 64, dtype=torch.uint16).cuda())
+    with pytest.raises(NotImplementedError):          # 3 channels: crop must be a multiple of 8 (and <= 192)
+        FusedTwoViewTransforms(36, (0.5,) * 3, (0.2,) * 3)(torch.zeros(1, 3, 64, 64, dtype=torch.uint16).cuda())
+    with pytest.raises(NotImplementedError):          # 2 channels
+        FusedTwoViewTransforms(32, (0.5,) * 2, (0.2,) * 2)(torch.zeros(1, 2, 64, 64, dtype=torch.uint16).cuda())
     with pytest.raises(ValueError):                   # mean/std length must match the channel count
         t(torch.zeros(1, 3, 64, 64, dtype=torch.uint16).cuda())
     with pytest.raises(NotImplementedError):

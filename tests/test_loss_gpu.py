@@ -81,6 +81,25 @@ def test_ntxent_rank_sharded_matches_committed_vectors():
     assert CudaKernels.launches > 0
 
 
+@pytest.mark.parametrize("n,d", [(50, 64), (96, 128), (200, 128), (1, 32), (321, 256), (70, 512)])
+def test_ntxent_any_batch_size(n, d):
+    """Per-GPU batches that are not a multiple of 64 (the reference takes any --batch_size, train_ssl.py:28-41): the
+    rank's block is padded to 128-row tiles with masked columns; loss and gradients match the oracle on the valid rows."""
+    from medical_image_segmentation_b200 import nt_xent_loss
+    z1, z2 = synth.embeddings(n, d, seed=3 * n + d, clustered=(n % 2 == 0))
+    a = z1.cuda().requires_grad_(True)
+    b = z2.cuda().requires_grad_(True)
+    loss = nt_xent_loss(a, b, 0.1)
+    loss.backward()
+    ref_loss, _, d1, d2 = L.ntxent_closed_form(z1.numpy(), z2.numpy(), 0.1)
+    # (tiny batches of clustered pairs give losses ~0.01 = lse - s_pos with both terms ~10: the relative gate is floored
+    # at a loss of 0.1, i.e. 1e-5 relative to the terms)
+    assert abs(float(loss.detach()) - ref_loss) <= 1e-3 * max(abs(ref_loss), 0.1), (float(loss), ref_loss)
+    if n > 1:
+        _grad_ok(a.grad.cpu().numpy(), d1, "dz_a")
+        _grad_ok(b.grad.cpu().numpy(), d2, "dz_b")
+
+
 @pytest.mark.parametrize("temperature", [0.5, 0.07])
 def test_ntxent_temperatures_and_grad_scale(temperature):
     from medical_image_segmentation_b200 import nt_xent_loss
@@ -113,27 +132,27 @@ def test_ntxent_bf16_embeddings():
 def test_ntxent_rank_sharded_layout_single_gpu():
     """A.5 on one GPU: feed each simulated rank's rows with the all-gathered matrix through the ABI."""
     from medical_image_segmentation_b200.loss import CudaKernels
-    W, B, D = 2, 64, 64
+    W, B, D = 3, 40, 64                        # 80 rows per rank: every block is padded to one 128-row tile
     g = torch.Generator().manual_seed(3)
     z_locals = [torch.randn(2 * B, D, generator=g) for _ in range(W)]
     ref_losses, ref_grads = L.ntxent_rank_sharded(z_locals, 0.1)
     preps = [CudaKernels.prep(z.cuda()) for z in z_locals]
     u_all = torch.cat([p[1] for p in preps])
     rows = 2 * B
-    scratch = CudaKernels.scratch(rows, W * rows, D, "cuda")
-    outs = [CudaKernels.fwd(u_all, r * rows, rows, 10.0, scratch) for r in range(W)]
+    rp = CudaKernels.padded_rows(rows)
+    assert rp == 128 and u_all.shape[0] == W * rp
+    scratch = CudaKernels.scratch(rows, W * rp, D, "cuda")
+    outs = [CudaKernels.fwd(u_all, r * rp, rows, 10.0, scratch) for r in range(W)]
     lse_all = torch.cat([o[0] for o in outs])
     one = torch.ones(1, device="cuda")
     for r in range(W):
         assert abs(float(outs[r][1]) - ref_losses[r]) <= 1e-3 * abs(ref_losses[r])
-        dz = CudaKernels.bwd(u_all, lse_all, preps[r][0], preps[r][2], r * rows, 10.0, one, scratch)
+        dz = CudaKernels.bwd(u_all, lse_all, preps[r][0], preps[r][2], r * rp, 10.0, one, scratch)
         _grad_ok(dz.cpu().numpy(), ref_grads[r].numpy(), f"rank {r}")
 
 
 def test_ntxent_errors():
     from medical_image_segmentation_b200 import nt_xent_loss
-    with pytest.raises(NotImplementedError):      # rows not a multiple of 128
-        nt_xent_loss(torch.randn(50, 64).cuda(), torch.randn(50, 64).cuda())
     with pytest.raises(NotImplementedError):      # D not a multiple of 32
         nt_xent_loss(torch.randn(64, 48).cuda(), torch.randn(64, 48).cuda())
     with pytest.raises(NotImplementedError):      # temperature below the fixed-max range
@@ -156,6 +175,30 @@ def test_byol_loss_matches_reference_golden():
         pr = torch.from_numpy(g[f"preds_{i}"]).double().requires_grad_(True)
         L.byol_cosine_loss(pr, torch.from_numpy(g[f"targets_{i}"]).double()).backward()
         _grad_ok(p.grad.cpu().numpy(), pr.grad.numpy(), f"byol case {i}")
+
+
+def test_momentum_update_is_bit_identical_to_the_reference_loop():
+    """BYOL.momentum_update (byol_pytorch.py:291-296) on a small model: the multi-tensor kernel vs the reference's
+    per-tensor mul_ / add_ loop, bit for bit, including odd lengths and unaligned views."""
+    from medical_image_segmentation_b200 import momentum_update
+    torch.manual_seed(0)
+    online = torch.nn.Sequential(torch.nn.Conv2d(3, 17, 3), torch.nn.BatchNorm2d(17), torch.nn.Linear(301, 77),
+                                 torch.nn.Linear(77, 5000)).cuda()
+    mom = torch.nn.Sequential(torch.nn.Conv2d(3, 17, 3), torch.nn.BatchNorm2d(17), torch.nn.Linear(301, 77),
+                              torch.nn.Linear(77, 5000)).cuda()
+    ref = [p.detach().clone() for p in mom.parameters()]
+    for m in (0.996, 0.99, 1.0, 0.5):
+        for po, pr in zip(online.parameters(), ref):
+            pr.mul_(m).add_(po.data, alpha=1.0 - m)                 # the reference loop
+        momentum_update(online, mom, m)
+        for pm, pr in zip(mom.parameters(), ref):
+            assert torch.equal(pm.data, pr)
+    flat_o, flat_m = torch.randn(10001, device="cuda"), torch.randn(10001, device="cuda")
+    want = flat_m[1:].clone().mul_(0.9).add_(flat_o[1:], alpha=1.0 - 0.9)
+    momentum_update([flat_o[1:]], [flat_m[1:]], 0.9)                # 4-byte aligned only: scalar path
+    assert torch.equal(flat_m[1:], want)
+    with pytest.raises(RuntimeError):
+        momentum_update([torch.zeros(4)], [torch.zeros(4)], 0.9)
 
 
 def test_mean_std_matches_reference_formula():
