@@ -271,8 +271,8 @@ int mis_byol_loss_fwd_bwd(const float* preds, const float* targets, int rows, in
  * EMA update of the momentum encoder as ONE multi-tensor kernel.
  * Replaces BYOL.momentum_update (byol_pytorch.py:291-296, called at :253-255):
  *     for po, pm in zip(online.parameters(), momentum.parameters()): pm.data.mul_(m).add_(po.data, alpha=1.0 - m)
- * with pm = fma(po, float(1 - m), fl(pm * m)) over a device table of float32 tensors (bit-identical to the two ATen
- * kernels).  table_dev[i].chunk0 = sum_{j<i} mis_ema_chunks(table[j].n); total_chunks = that sum over all tensors.
+ * with pm = fma(po, one_minus_m, fl(pm * m)) over a device table of float32 tensors (bit-identical to the two ATen
+ * kernels when m = float(m64), one_minus_m = float(1.0 - m64): the reference forms 1 - m in double).  table_dev[i].chunk0 = sum_{j<i} mis_ema_chunks(table[j].n); total_chunks = that sum over all tensors.
  * ------------------------------------------------------------------------------------------ */
 typedef struct MisEmaEntry {
   const void* online;     /* float32 [n], device  */
@@ -282,7 +282,8 @@ typedef struct MisEmaEntry {
 } MisEmaEntry;
 
 int64_t mis_ema_chunks(int64_t n_elements);
-int mis_ema_update(const MisEmaEntry* table_dev, int n_tensors, int64_t total_chunks, float m, void* stream);
+int mis_ema_update(const MisEmaEntry* table_dev, int n_tensors, int64_t total_chunks, float m, float one_minus_m,
+                   void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Exact per-channel moments of uint16 slices: the statistics behind the normalisation constants.

@@ -55,12 +55,13 @@ extern "C" int64_t mis_ema_chunks(int64_t n_elements) {
   return n_elements <= 0 ? 0 : (n_elements + mis::ema::kChunk - 1) / mis::ema::kChunk;
 }
 
-extern "C" int mis_ema_update(const MisEmaEntry* table_dev, int n_tensors, int64_t total_chunks, float m, void* stream) {
+extern "C" int mis_ema_update(const MisEmaEntry* table_dev, int n_tensors, int64_t total_chunks, float m, float one_minus_m,
+                              void* stream) {
   MIS_REQUIRE(table_dev && n_tensors > 0, MIS_ERR_INVALID_ARG, "mis_ema_update: empty table");
   MIS_REQUIRE(total_chunks > 0 && total_chunks < (1ll << 31), MIS_ERR_INVALID_ARG, "mis_ema_update: %lld chunks",
               (long long)total_chunks);
   MIS_REQUIRE(m >= 0.f && m <= 1.f, MIS_ERR_INVALID_ARG, "mis_ema_update: momentum %g outside [0, 1]", (double)m);
-  const float om = (float)(1.0 - (double)m);
+  const float om = one_minus_m;
   mis::ema::ema_kernel<<<dim3((unsigned)total_chunks), mis::ema::kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       table_dev, n_tensors, m, om);
   MIS_CUDA_TRY(cudaGetLastError());

@@ -61,7 +61,7 @@ def momentum_update(online_encoder, momentum_encoder, m: float) -> None:
             _tables.clear()
         tab = _tables[key] = _Table(pairs, device)
     with torch.cuda.device(device):
-        rc = _lib.lib.mis_ema_update(tab.dev.data_ptr(), tab.n, tab.total_chunks, float(m),
+        rc = _lib.lib.mis_ema_update(tab.dev.data_ptr(), tab.n, tab.total_chunks, float(m), 1.0 - float(m),
                                      C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
     _lib.check(rc, "mis_ema_update")
     launches += 1
