@@ -811,7 +811,7 @@ static bool make_plan(int H, int W, int s, Plan* best) {
   const int sched_cap = (((H > s ? H : s) + 7) & ~7) + 8;
   const size_t kSmPerSm = 233472, kSmPerBlock = 232448;
   bool found = false;
-  int best_warps = 0;
+  int best_score = 0;
   for (int nsy = 1; nsy <= kMaxParts; ++nsy) {
     const int threads = 32 * nsx * nsy;
     if (threads > 1024) break;
@@ -842,13 +842,41 @@ static bool make_plan(int H, int W, int s, Plan* best) {
       if (ctas < 1) continue;
       p.ctas = ctas;
       const int warps = ctas * nwarps;
-      // more resident warps win; on a tie fewer parts (less halo, fewer redundant set-ups), then two row buffers
-      if (!found || warps > best_warps) {
+      // More resident warps win; on a tie fewer parts (less halo, fewer redundant set-ups), then two row buffers.
+      // The 1024-thread instantiation has 64 registers per thread and spills the load slots of the wide classes
+      // (a spilled slot serialises the prefetch), so it only competes when the 72-register one cannot reach 20 warps.
+      const int score = p.big ? warps : warps + 1000;
+      if (!found || score > best_score) {
+        if (!p.big && warps < 20) continue;
         *best = p;
-        best_warps = warps;
+        best_score = score;
         found = true;
       }
     }
+  }
+  if (found) return true;
+  // second pass without the 20-warp floor (small crops on small slices)
+  for (int nsy = 1; nsy <= kMaxParts && !found; ++nsy) {
+    const int threads = 32 * nsx * nsy;
+    if (threads > 448) break;
+    const int rp = (s + nsy - 1) / nsy;
+    if ((s + rp - 1) / rp != nsy) continue;
+    const int nwarps = nsx * nsy;
+    size_t park = (size_t)nwarps * rp * kTilePitch;
+    const size_t vtab = (size_t)s * (kVK * 4 + 8);
+    if (park < vtab) park = vtab;
+    Plan p = {};
+    p.nsx = nsx; p.nsy = nsy; p.rp = rp; p.rowbuf = rowbuf; p.dbl = 0; p.threads = threads; p.big = 0;
+    size_t off = al16(park);
+    p.off_sched = (uint32_t)off; off += (size_t)sched_cap * 16;
+    p.off_fmask = (uint32_t)off; off += al16((size_t)(sched_cap / 32 + 2) * 4);
+    p.off_row = (uint32_t)off; off += (size_t)nwarps * rowbuf * 4;
+    p.off_misc = (uint32_t)off; off += sizeof(Misc);
+    p.smem = off;
+    if (p.smem > kSmPerBlock) continue;
+    p.ctas = 1;
+    *best = p;
+    found = true;
   }
   return found;
 }

@@ -12,7 +12,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for (B, D, T) in ((64, 64, 0.1), (256, 128, 0.1), (128, 256, 0.2), (256, 128, 0.1), (256, 128, 0.1)):
+for (B, D, T) in ((64, 64, 0.1), (256, 128, 0.1), (128, 256, 0.2), (256, 128, 0.1), (256, 128, 0.1), (96, 64, 0.1), (96, 64, 0.1), (200, 128, 0.1)):
     g = torch.Generator().manual_seed(11)
     z_locals = [torch.randn(2 * B, D, generator=g) for _ in range(world)]
     ref_losses, ref_grads = L.ntxent_rank_sharded(z_locals, T)
