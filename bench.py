@@ -458,6 +458,8 @@ def run_b200(args):
     # ---- e2e: pinned host slices -> H2D -> K1 -> NT-Xent fwd+bwd -> loss read back ---------------------
     e2e = None
     if not args.no_e2e:
+        from medical_image_segmentation_b200.numa import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local)              # pinned staging memory on the GPU's own socket (first touch)
         x_host = torch.empty((B, 1, H, W), dtype=torch.uint16).pin_memory()
         x_host.copy_(x_dev)
         loss_host = torch.empty((), dtype=torch.float32).pin_memory()
@@ -484,6 +486,7 @@ def run_b200(args):
         ms_e2e = timed(step_e2e, e2e_steps) / e2e_steps
         e2e = {"value": world * 2 * B / (ms_e2e * 1e-3), "unit": "views/s", "ms_per_step": ms_e2e, "steps": e2e_steps,
                "h2d_bytes_per_step": int(sum(h2d_bytes[-e2e_steps:]) / e2e_steps + params.nbytes), "d2h_bytes_per_step": 4,
+               "h2d_gbs_per_gpu": sum(h2d_bytes[-e2e_steps:]) / e2e_steps / (ms_e2e * 1e-3) / 1e9, "numa": numa,
                "h2d_note": f"rows no crop reads are skipped when the gap exceeds 256 KB "
                            f"({sum(h2d_bytes[-e2e_steps:]) / e2e_steps / (x_host.numel() * 2):.0%} of the {x_host.numel() * 2} B batch moved)"}
 

@@ -3,6 +3,7 @@
 Public surface (mirrors the reference's transform / loss call sites):
 
     FusedTwoViewTransforms(crop_size, mean, std, blur_prob=(1.0,0.1), solarize_prob=(0.0,0.2))(x) -> [view1, view2]
+    FusedFFCVTwoViewTransforms(device, crop_size, mean, std, solarize_prob).get_transforms() / .on_after_batch_transfer
     nt_xent_loss(z_a, z_b, temperature=0.1, group=None) -> scalar
     byol_cosine_loss(preds, targets) -> scalar
     compute_mean_and_std(loader) -> (mean, std)      (analyze_data/compute_dataset_metrics.py:12-29)
@@ -18,10 +19,11 @@ from .loss import byol_cosine_loss, nt_xent_loss, nt_xent_rows
 from .metrics import compute_mean_and_std
 from .params import draw_two_view_params, draw_two_view_params_torch
 from .registry import DATAMODULE_REGISTRY, get_datamodule, register_datamodule
-from .transforms import FusedResizeJitterTransforms, FusedTwoViewTransforms, algorithmic_bytes
+from .transforms import (FusedFFCVTwoViewTransforms, FusedResizeJitterTransforms, FusedTwoViewTransforms,
+                         algorithmic_bytes)
 
 __all__ = [
-    "FusedTwoViewTransforms", "FusedResizeJitterTransforms", "algorithmic_bytes", "nt_xent_loss", "nt_xent_rows", "byol_cosine_loss",
+    "FusedTwoViewTransforms", "FusedResizeJitterTransforms", "FusedFFCVTwoViewTransforms", "algorithmic_bytes", "nt_xent_loss", "nt_xent_rows", "byol_cosine_loss",
     "compute_mean_and_std", "momentum_update", "draw_two_view_params", "draw_two_view_params_torch", "register_datamodule", "get_datamodule",
     "DATAMODULE_REGISTRY",
 ]

@@ -99,7 +99,7 @@ class FusedTwoViewTransforms:
         self._pool = None                     # one helper thread drawing the NEXT batch's parameters
         self._pending = None                  # ((B, H, W), future)
         self._x_stage: torch.Tensor | None = None      # device staging buffer of host batches
-        self._x_host_keepalive = None
+        self._x_host_ring = []                          # (pinned host batch, event after its copies): alive while in flight
         self.last_h2d_bytes = 0
         self.views_buffer: torch.Tensor | None = None
         self.last_params: np.ndarray | None = None
@@ -264,7 +264,13 @@ class FusedTwoViewTransforms:
                                               p.ctypes.data, p.shape[0], int(min_gap_bytes),
                                               C.c_void_p(torch.cuda.current_stream(device).cuda_stream), C.byref(nbytes))
         _lib.check(rc, "mis_h2d_needed_rows")
-        self._x_host_keepalive = x_host                 # the async copies read it until the stream gets there
+        # The raw cudaMemcpyAsync calls inside the library are invisible to torch's pinned-memory allocator: every host
+        # batch stays referenced until an event recorded behind its copies has completed (a lagging GPU may still have
+        # copies of older batches queued), so a freshly pinned block can never be recycled under a pending copy.
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self._x_host_ring = [(h, e) for (h, e) in self._x_host_ring if not e.query()]
+        self._x_host_ring.append((x_host, ev))
         self.last_h2d_bytes = int(nbytes.value)
         return self._x_stage
 
@@ -285,6 +291,67 @@ class FusedTwoViewTransforms:
         out = self.apply(x, self.to_view_major(params))
         self.views_buffer = out
         return [out[:B], out[B:]]
+
+
+class FusedFFCVTwoViewTransforms(FusedTwoViewTransforms):
+    """The FFCV flavour of the chain: ``BYOLRGBFFCVDataTransforms(device, crop_size, mean, std, solarize_prob)``
+    (train/data_loaders/lightning_module.py:67-98), whose per-view pipeline is RandomResizedCrop(scale (0.08, 1), ratio
+    (3/4, 4/3)) -> RandomHorizontalFlip(0.5) -> RandomGrayscale(0.2) -> RandomSolarization(p, 128) -> Normalize --
+    colour jitter and GaussianBlur are commented out there (:81-86).
+
+    The reference runs those ops as FFCV numba stages on the CPU, followed by an H2D copy; FFCV-SSL is an un-vendored
+    fork that is not installed here, so its pipelines cannot be built.  What can be made real without it is the other end
+    of the seam: the loader yields the RAW uint16 batch (an ``NDArrayField`` instead of the 8-bit ``RGBImageField``),
+    Lightning moves it to the GPU, and ``on_after_batch_transfer`` produces ``(view_1, labels, view_2)`` -- the tuple
+    ``BYOL.training_step`` unpacks (byol_pytorch.py:201-204) -- with the fused kernel, the same op set and the same
+    probabilities.  Two deliberate differences: the parameters come from torch's CPU generator (FFCV draws from numpy's
+    inside numba; that stream cannot be reproduced without its source), and the resample is torchvision's antialiased
+    bilinear filter rather than FFCV's ``cv::resize`` (recalled, not verifiable here: SURVEY A.6).
+
+    ``get_transforms()`` keeps the reference's return shape -- one pipeline (list of stages) per view; a stage is a
+    callable on the raw device batch.  Both pipelines share one kernel launch per batch.
+    """
+
+    def __init__(self, device, crop_size, mean, std, solarize_prob=(0.0, 0.2), *, out_dtype=torch.bfloat16, **kw):
+        if isinstance(crop_size, (tuple, list)) and len(crop_size) == 2 and crop_size[0] == crop_size[1]:
+            crop_size = crop_size[0]
+        super().__init__(crop_size, mean, std, blur_prob=(0.0, 0.0), solarize_prob=solarize_prob, out_dtype=out_dtype, **kw)
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self._cached = None            # (batch identity, [view1, view2])
+
+    def draw_params(self, B: int, H: int, W: int) -> np.ndarray:
+        """Crop box, flip, grayscale and solarize draws of the FFCV op set: the jitter flag is cleared (the op is not
+        in this pipeline) -- torch's stream is used, so the draw ORDER is the torchvision chain's."""
+        p = super().draw_params(B, H, W)
+        p["flags"] &= ~np.uint32(2 | 8)
+        p["order"] = (0, 1, 2, 3)
+        p["brightness"] = p["contrast"] = p["saturation"] = 1.0
+        p["hue"] = 0.0
+        return p
+
+    class _Stage:
+        def __init__(self, owner, view: int):
+            self.owner, self.view = owner, view
+
+        def __call__(self, x):
+            return self.owner._views_of(x)[self.view]
+
+    def _views_of(self, x):
+        key = (x.data_ptr(), tuple(x.shape), x._version)
+        if self._cached is None or self._cached[0] != key:
+            self._cached = (key, FusedTwoViewTransforms.__call__(self, x))
+        return self._cached[1]
+
+    def get_transforms(self):
+        return [[self._Stage(self, 0)], [self._Stage(self, 1)]]
+
+    def on_after_batch_transfer(self, batch, dataloader_idx: int = 0):
+        """Lightning hook: ``batch = (x_u16 [B,C,H,W] on the GPU, labels, ...)`` -> ``(view_1, labels, view_2)``."""
+        x, labels = batch[0], batch[1]
+        if not x.is_cuda:
+            x = x.to(self.device, non_blocking=True)
+        v1, v2 = FusedTwoViewTransforms.__call__(self, x)
+        return v1, labels, v2
 
 
 def algorithmic_bytes(params: np.ndarray, C_: int, crop_size: int, out_dtype=torch.bfloat16) -> int:

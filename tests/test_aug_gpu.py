@@ -342,6 +342,29 @@ def test_argument_errors_mirror_reference_style():
         _mk(300)(torch.zeros(1, 1, 64, 64, dtype=torch.uint16).cuda())
 
 
+def test_ffcv_flavour_hook_yields_the_training_step_tuple():
+    """FusedFFCVTwoViewTransforms.on_after_batch_transfer: raw uint16 batch + labels -> (view_1, labels, view_2), the
+    tuple BYOL.training_step unpacks (byol_pytorch.py:201-204); pipelines from get_transforms() give the same views."""
+    from medical_image_segmentation_b200 import FusedFFCVTwoViewTransforms
+    imgs = synth.batch_512(6, seed=29, H=200, W=240)
+    x = torch.from_numpy(imgs)[:, None].cuda()
+    labels = torch.arange(6).cuda()
+    f = FusedFFCVTwoViewTransforms(0, 112, (MEAN,), (STD,), out_dtype=torch.float32)
+    torch.manual_seed(77)
+    v1, lab, v2 = f.on_after_batch_transfer((x, labels), 0)
+    assert lab is labels and v1.shape == (6, 1, 112, 112) and v2.shape == (6, 1, 112, 112)
+    p = f.last_params
+    assert not (p["flags"] & (2 | 8)).any()
+    out = f.views_buffer.cpu().numpy()
+    for i in range(6):
+        for v in range(2):
+            _check_view(out[v * 6 + i, 0], imgs[i], p[2 * i + v], 112, f"ffcv flavour img {i} view {v}")
+    torch.manual_seed(77)
+    pipes = f.get_transforms()
+    a, b = pipes[0][0](x), pipes[1][0](x)            # one launch serves both pipelines
+    assert torch.equal(a, v1) and torch.equal(b, v2)
+
+
 def test_determinism_and_view_halves():
     x = torch.from_numpy(synth.batch_512(4, seed=11)).cuda()
     t = _mk(96)

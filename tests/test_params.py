@@ -142,3 +142,20 @@ def test_prefetched_parameter_stream_is_the_same_stream():
     torch.manual_seed(5)
     assert b.next_params(4, 64, 64).tobytes() == x.tobytes()
     b.drain_prefetch()
+
+
+def test_ffcv_flavour_parameter_records():
+    """BYOLRGBFFCVDataTransforms' op set (lightning_module.py:77-95): crop, flip, grayscale, solarize -- no colour jitter,
+    no blur.  Same crop boxes / flips as the torchvision-flavour stream for the same seed."""
+    from medical_image_segmentation_b200 import FusedFFCVTwoViewTransforms, FusedTwoViewTransforms
+    f = FusedFFCVTwoViewTransforms("cuda:0", (112, 112), (0.2,), (0.2,))
+    assert f.crop_size == 112 and f.blur_prob == (0.0, 0.0) and f.solarize_prob == (0.0, 0.2)
+    assert len(f.get_transforms()) == 2 and all(len(p) == 1 and callable(p[0]) for p in f.get_transforms())
+    torch.manual_seed(9)
+    a = f.draw_params(300, 256, 256)
+    torch.manual_seed(9)
+    b = FusedTwoViewTransforms(112, (0.2,), (0.2,), blur_prob=(0.0, 0.0)).draw_params(300, 256, 256)
+    assert not (a["flags"] & (2 | 8)).any() and (a["flags"] & 16).any() and (a["flags"] & 4).any()
+    for k in ("img", "top", "left", "h", "w"):
+        assert np.array_equal(a[k], b[k])
+    assert np.array_equal(a["flags"] & 1, b["flags"] & 1) and np.array_equal(a["flags"] & 16, b["flags"] & 16)
