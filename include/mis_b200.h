@@ -182,8 +182,8 @@ int64_t mis_aug_algorithmic_bytes(const MisViewParams* params_host, int n_views,
  *                     container) and rinv = 1/max(|z|,1e-12).  u is what gets all-gathered.
  *   mis_ntxent_fwd    lse_i = log sum_{j != g(i)} exp(<u_i,u_j>/T) over all `cols` columns (tcgen05
  *                     kind::tf32, accumulators in TMEM; S never leaves the SM);
- *                     loss[0] = mean_i (lse_i - <u_i,u_p(i)>/T) over the local rows.  One kernel launch: the
- *                     last CTA of every row tile finishes its rows, the last CTA of the launch the mean.
+ *                     loss[0] = mean_i (lse_i - <u_i,u_p(i)>/T) over the local rows.  Two launches: the tile kernel
+ *                     and a rows kernel (lse, positives, mean; its last block publishes).
  *   mis_ntxent_bwd    dz_local = grad_out[0] * grad_scale * sum_r' dL_r'/dz_local  (SURVEY A.5,
  *                     option L: uses the all-gathered lse instead of a D-wide gradient exchange).
  *                     S is recomputed tile by tile; W = P + P^T is rounded to TF32 and stays in
@@ -224,12 +224,14 @@ int mis_ntxent_bwd(const float* u_all, const float* lse_all, const void* z_rows,
  *                    abort word
  *
  * forward  = prep kernel (normalise, round to TF32, store the local rows into every rank's matrix, raise
- *            flag[0][rank] on every rank) + ONE tile kernel: its TMA producers wait per column tile for the flag of the
- *            rank that owns those rows (tiles are walked starting at the local rows), the last CTA of every row tile
- *            forms lse / positives / row losses and stores the lse rows into every rank's vector, the last CTA of the
- *            launch forms the mean loss, raises flag[1][rank] on every rank and publishes the epoch.
- * backward = transpose + ONE tile kernel (D <= 256): its epilogue warps wait once for the lse flags of all ranks (S tiles
- *            are already being computed meanwhile); the last CTA of every row tile applies the normalisation Jacobian.
+ *            flag[0][rank] on every rank) + the tile kernel, whose TMA producers wait per column tile for the flag of the
+ *            rank that owns those rows (tiles are walked starting at the local rows) + a rows kernel that forms lse /
+ *            positives / row losses, stores the lse rows into every rank's vector, and whose last block forms the mean
+ *            loss, raises flag[1][rank] on every rank and publishes the epoch.
+ * backward = transpose + the tile kernel (one launch per 256 columns of D), whose epilogue warps wait once for the lse
+ *            flags of all ranks (S tiles are already being computed meanwhile) + the normalisation-Jacobian kernel.
+ *            (Folding the row kernels into the tile kernels' last CTAs was tried: the tails -- one CTA of 13 warps per
+ *            128 rows chasing L2 round trips -- cost more than the two launches they saved, DESIGN.md.)
  * Epoch and buffer parity are read from the DEVICE-side counter, so both calls can be captured into CUDA graphs and
  * replayed.  Buffers alternate with the epoch's parity; that is sufficient for safe reuse as long as a rank's backward of
  * epoch k is enqueued before its forward of epoch k+1 (one evaluation outstanding -- loss.py enforces it).

@@ -59,23 +59,20 @@ struct PeerCtl {
   uint32_t pad;
 };
 
-// what the last CTA of a row tile needs to finish the rows (the former fwd_rows / bwd_finalize kernels)
-struct Finish {
-  unsigned int* counters;    // [row_tiles] arrivals per row tile, then [1] finished row tiles; zero on entry, left zero
-  int fold;                  // 0: partials only (backward of D > 256: a separate finalize kernel follows)
-  // forward
+// arguments of the kernel that finishes the forward rows (lse, positives, row losses, mean) and publishes them
+struct RowsArgs {
+  const float* partial;      // [nparts][rows] row-sum partials of the tile kernel
+  int nparts, rows, rows_valid, D, row0;
+  float inv_T;
   const float* u_all[2];     // per parity: gathered matrix (positives)
   float* lse_dst[2][kMaxPeers];  // per parity, per rank: gathered lse vector (dst[.][rank] is the local copy)
   int lse_off;               // row offset of this rank inside the gathered vectors
   float* row_loss;           // [rows] scratch
   float* loss;               // [1]
-  // backward
-  const void* z_rows;
-  const float* rinv;
-  void* dz;
-  int z_bf16;
-  float scale;               // grad_scale / (T * rows)
-  const float* grad_out;     // may be null (= 1)
+  unsigned int* counter;     // blocks that have finished (zero on entry, left zero)
+  PeerCtl* ctl;              // local control block, null for a single rank
+  PeerCtl* ctl_peers[kMaxPeers];
+  int world, rank;
 };
 
 struct TileArgs {
@@ -94,7 +91,6 @@ struct TileArgs {
   int world, rank, rows_per_rank;
   int epoch_add;           // forward: 1 (the epoch being produced), backward: 0 (the epoch completed last)
   long long timeout_clk;   // SM clocks a consumer waits for a peer before it traps
-  Finish fin;
 };
 
 struct Bars {
@@ -494,7 +490,6 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
     if (!kBwd) {
       // each group writes its own partial row sums: partial[(2*split + grp)][row]
       a.partial[(size_t)(2 * split + grp) * a.rows + row_tile * kTile + r_in] = (rs0 + rs1) + (rs2 + rs3);
-      __threadfence();
     } else {
       mbar_wait(&bars.du_full, 0);
       tc_fence_after();
@@ -507,7 +502,6 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
         for (int j = 0; j < 8; ++j)
           reinterpret_cast<uint4*>(dst + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
-      __threadfence();
     }
   }
 
@@ -517,100 +511,6 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
   }
 
-  // ===================== the last CTA of a row tile finishes its rows (no separate kernel) =====================
-  const Finish& fin = a.fin;
-  if (!fin.fold) return;
-  __shared__ int s_flag;
-  __shared__ float s_red[kThreads / 32];
-  if (tid == 0) {
-    __threadfence();
-    s_flag = atomicAdd(&fin.counters[row_tile], 1u) == gridDim.y - 1;
-  }
-  __syncthreads();
-  if (!s_flag) return;
-  __threadfence();
-  const int nsplit = (int)gridDim.y;
-  const int row_tiles = (int)gridDim.x;
-  if (!kBwd) {
-    // lse_i = 1/T + log(sum of the split partials); pos_i = <u_i, u_p(i)> / T; row loss = lse_i - pos_i (warp per row)
-    const float* u_all = fin.u_all[par];
-    for (int r = warp; r < kTile; r += kThreads / 32) {
-      const int i = row_tile * kTile + r;
-      if (i >= a.rows_valid) {       // padding row: a finite lse for the peers' c_j, no loss term
-        if (lane == 0) {
-          for (int q = 0; q < a.world; ++q) fin.lse_dst[par][q][fin.lse_off + i] = 0.f;
-          fin.row_loss[i] = 0.f;
-        }
-        continue;
-      }
-      float sacc = 0.f;
-      for (int k = lane; k < 2 * nsplit; k += 32) sacc += ldcg_f32(a.partial + (size_t)k * a.rows + i);
-      sacc = warp_sum(sacc);
-      const float lse = a.inv_T + logf(sacc);
-      const float* ui = u_all + (size_t)(a.row0 + i) * a.D;
-      const float* up = u_all + (size_t)(a.row0 + (i + (a.rows_valid >> 1)) % a.rows_valid) * a.D;
-      float dot = 0.f;
-      for (int d = lane; d < a.D; d += 32) dot = fmaf(ui[d], up[d], dot);
-      dot = warp_sum(dot);
-      if (lane == 0) {
-        for (int q = 0; q < a.world; ++q) fin.lse_dst[par][q][fin.lse_off + i] = lse;    // every rank's gathered lse
-        fin.row_loss[i] = lse - dot * a.inv_T;
-      }
-    }
-  } else {
-    // dz_i = (dU_i - u_i <u_i,dU_i>) * rinv_i with dU_i = scale * sum of the split partials (the -2 u_p(i) one-hot term
-    // is already inside W); warp per row
-    const float g = fin.scale * (fin.grad_out ? fin.grad_out[0] : 1.f);
-    for (int r = warp; r < kTile; r += kThreads / 32) {
-      const int i = row_tile * kTile + r;
-      if (i >= a.rows_valid) continue;            // padding row: z / dz hold the valid rows only
-      const float rv = fin.rinv[i];
-      auto z_at = [&](int d) {
-        return fin.z_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(fin.z_rows)[(size_t)i * a.D + d])
-                          : static_cast<const float*>(fin.z_rows)[(size_t)i * a.D + d];
-      };
-      auto du_at = [&](int d) {
-        float sacc = 0.f;
-        for (int sp = 0; sp < nsplit; ++sp) sacc += ldcg_f32(a.partial + ((size_t)sp * a.rows + i) * a.D + d);
-        return g * sacc;
-      };
-      float dot = 0.f;
-      for (int d = lane; d < a.D; d += 32) dot = fmaf(z_at(d) * rv, du_at(d), dot);
-      dot = warp_sum(dot);
-      for (int d = lane; d < a.D; d += 32) {
-        const float v = (du_at(d) - z_at(d) * rv * dot) * rv;
-        if (fin.z_bf16) static_cast<__nv_bfloat16*>(fin.dz)[(size_t)i * a.D + d] = __float2bfloat16_rn(v);
-        else static_cast<float*>(fin.dz)[(size_t)i * a.D + d] = v;
-      }
-    }
-  }
-  // ---- the CTA that finishes the last row tile: mean loss, lse flags to every rank, epoch, counters back to zero ----
-  if (a.world > 1 && !kBwd) __threadfence_system();
-  else __threadfence();
-  __syncthreads();
-  if (tid == 0) s_flag = atomicAdd(&fin.counters[row_tiles], 1u) == (unsigned)row_tiles - 1;
-  __syncthreads();
-  if (!s_flag) return;
-  __threadfence();
-  if (!kBwd) {
-    float acc = 0.f;
-    for (int r = tid; r < a.rows; r += kThreads) acc += ldcg_f32(fin.row_loss + r);   // fixed order: deterministic
-    acc = warp_sum(acc);
-    if (lane == 0) s_red[warp] = acc;
-    __syncthreads();
-    if (tid == 0) {
-      float tot = 0.f;
-      for (int w = 0; w < kThreads / 32; ++w) tot += s_red[w];
-      fin.loss[0] = tot / (float)a.rows_valid;
-    }
-  }
-  if (tid <= row_tiles) fin.counters[tid] = 0u;          // (row_tiles < kThreads is checked on the host)
-  if (tid == 0 && a.ctl && !kBwd) {
-    __threadfence_system();
-    for (int q = 0; q < a.world; ++q)
-      if (a.world > 1) st_release_sys(&a.ctl_peers[q]->flag[1][a.rank], epoch);
-    a.ctl->epoch = epoch;                                // this forward is complete: the backward reads it back
-  }
 }
 
 // ---- small kernels ------------------------------------------------------------------------------
@@ -685,8 +585,83 @@ __global__ void transpose_kernel(const float* __restrict__ u0, const float* __re
   for (int i = threadIdx.y; i < 32; i += blockDim.y) ut[(size_t)(d0 + i) * cols + c0 + threadIdx.x] = tile[threadIdx.x][i];
 }
 
-// dz_i = (dU_i - u_i <u_i,dU_i>) * rinv_i with dU_i = scale * sum_splits partial; one warp per row.  Only for D > 256,
-// where the backward runs one tile-kernel launch per 256-column slice of dU (smaller D: folded into the tile kernel).
+// Finishes the forward rows: lse_i = 1/T + log(sum of the split partials); pos_i = <u_i,u_p(i)>/T; row loss
+// lse_i - pos_i; the lse rows go to every rank's gathered vector.  One warp per row, all loads of a row issued before
+// the first use.  The LAST block forms the mean loss (fixed order: deterministic), raises flag[1][rank] = epoch on
+// every rank, publishes the epoch (PeerCtl::epoch: the backward and the next forward read it) and re-arms the counter.
+__global__ void __launch_bounds__(256) fwd_rows_kernel(const RowsArgs a) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const uint32_t epoch = a.ctl ? a.ctl->epoch + 1u : 0u;
+  const int par = (int)(epoch & 1u);
+  if (i < a.rows) {
+    if (i >= a.rows_valid) {        // padding row: a finite lse for the peers' c_j, no loss term
+      if (lane == 0) {
+        for (int q = 0; q < a.world; ++q) a.lse_dst[par][q][a.lse_off + i] = 0.f;
+        a.row_loss[i] = 0.f;
+      }
+    } else {
+      const float* u_all = a.u_all[par];
+      const float* ui = u_all + (size_t)(a.row0 + i) * a.D;
+      const float* up = u_all + (size_t)(a.row0 + (i + (a.rows_valid >> 1)) % a.rows_valid) * a.D;
+      float sacc = 0.f;
+      for (int k = lane; k < a.nparts; k += 32) sacc += a.partial[(size_t)k * a.rows + i];
+      float dot = 0.f;
+      for (int d0 = lane; d0 < a.D; d0 += 32 * 4) {
+        float x[4], y[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int d = d0 + 32 * e;
+          x[e] = d < a.D ? ui[d] : 0.f;
+          y[e] = d < a.D ? up[d] : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dot = fmaf(x[e], y[e], dot);
+      }
+      sacc = warp_sum(sacc);
+      dot = warp_sum(dot);
+      if (lane == 0) {
+        const float lse = a.inv_T + logf(sacc);
+        for (int q = 0; q < a.world; ++q) a.lse_dst[par][q][a.lse_off + i] = lse;     // every rank's gathered lse
+        a.row_loss[i] = lse - dot * a.inv_T;
+      }
+    }
+  }
+  __shared__ bool last;
+  __shared__ float red[8];
+  if (a.world > 1) __threadfence_system();
+  else __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float acc = 0.f;
+  for (int r0 = threadIdx.x; r0 < a.rows; r0 += 8 * 256) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = r0 + e * 256 < a.rows ? __ldcg(a.row_loss + r0 + e * 256) : 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += v[e];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    a.loss[0] = tot / (float)a.rows_valid;
+    *a.counter = 0u;                                   // ready for the next call on this scratch buffer
+    if (a.ctl) {
+      __threadfence_system();
+      for (int q = 0; q < a.world; ++q) st_release_sys(&a.ctl_peers[q]->flag[1][a.rank], epoch);
+      a.ctl->epoch = epoch;                            // this forward is complete
+    }
+  }
+}
+
+// dz_i = (dU_i - u_i <u_i,dU_i>) * rinv_i with dU_i = scale * sum_splits partial (the -2 u_p(i) one-hot term is already
+// inside W); one warp per row, eight elements per lane in flight per step.
 template <typename T>
 __global__ void bwd_finalize_kernel(const float* __restrict__ partial, int nsplit, const T* __restrict__ z_rows,
                                     const float* __restrict__ rinv, int D, int rows, int rows_valid, float scale,
@@ -696,12 +671,40 @@ __global__ void bwd_finalize_kernel(const float* __restrict__ partial, int nspli
   if (i >= rows_valid) return;
   const float g = scale * (grad_out ? grad_out[0] : 1.f);
   const float r = rinv[i];
-  auto du_at = [&](int d) {
-    float s = 0.f;
-    for (int sp = 0; sp < nsplit; ++sp) s += partial[((size_t)sp * rows + i) * D + d];
-    return g * s;
-  };
+  constexpr int kE = 8;
   float dot = 0.f;
+  if (D <= 32 * kE) {                 // the common case: the whole row stays in registers, one pass
+    float du[kE], zz[kE];
+#pragma unroll
+    for (int e = 0; e < kE; ++e) {
+      const int d = lane + 32 * e;
+      du[e] = 0.f;
+      zz[e] = d < D ? load_as_f32(z_rows, (size_t)i * D + d) : 0.f;
+      if (d < D)
+        for (int sp = 0; sp < nsplit; ++sp) du[e] += partial[((size_t)sp * rows + i) * D + d];
+    }
+#pragma unroll
+    for (int e = 0; e < kE; ++e) {
+      du[e] *= g;
+      dot = fmaf(zz[e] * r, du[e], dot);
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int e = 0; e < kE; ++e) {
+      const int d = lane + 32 * e;
+      if (d < D) {
+        const float v = (du[e] - zz[e] * r * dot) * r;
+        if constexpr (sizeof(T) == 4) dz[(size_t)i * D + d] = v;
+        else dz[(size_t)i * D + d] = __float2bfloat16_rn(v);
+      }
+    }
+    return;
+  }
+  auto du_at = [&](int d) {
+    float sacc = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) sacc += partial[((size_t)sp * rows + i) * D + d];
+    return g * sacc;
+  };
   for (int d = lane; d < D; d += 32) dot = fmaf(load_as_f32(z_rows, (size_t)i * D + d) * r, du_at(d), dot);
   dot = warp_sum(dot);
   for (int d = lane; d < D; d += 32) {
@@ -932,28 +935,40 @@ static int ntxent_fwd_impl(const float* u0, const float* u1, int cols, int D, in
   a.world = ex.world; a.rank = ex.rank; a.rows_per_rank = rows;      // (padded)
   a.epoch_add = 1;
   a.timeout_clk = ex.timeout_clk;
-  a.fin.fold = 1;
-  a.fin.counters = reinterpret_cast<unsigned int*>(sc);
-  a.fin.row_loss = reinterpret_cast<float*>(sc + kCounterBytes);
-  a.fin.loss = loss;
-  a.fin.u_all[0] = u0;
-  a.fin.u_all[1] = u1 ? u1 : u0;
   if (ex.world > 1) {
     a.ctl = ex.ctl_peers[ex.rank];
-    for (int r = 0; r < ex.world; ++r) {
-      a.ctl_peers[r] = ex.ctl_peers[r];
-      a.fin.lse_dst[0][r] = ex.lse_peers[0][r];
-      a.fin.lse_dst[1][r] = ex.lse_peers[1][r];
-    }
-    a.fin.lse_off = row0;
-  } else {
-    a.fin.lse_dst[0][0] = a.fin.lse_dst[1][0] = lse_local;
-    a.fin.lse_off = 0;
+    for (int r = 0; r < ex.world; ++r) a.ctl_peers[r] = ex.ctl_peers[r];
   }
-  MIS_CUDA_TRY(cudaMemsetAsync(sc, 0, kCounterBytes, st));                      // scratch arrives uninitialised
   auto* fn = &ntxent_tile_kernel<false>;
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map0, map1, map0, a);
+  MIS_CUDA_TRY(cudaGetLastError());
+
+  RowsArgs ra = {};
+  ra.partial = partial;
+  ra.nparts = 2 * p.nsplit;
+  ra.rows = rows; ra.rows_valid = rows_valid; ra.D = D; ra.row0 = row0;
+  ra.inv_T = inv_T;
+  ra.u_all[0] = u0;
+  ra.u_all[1] = u1 ? u1 : u0;
+  ra.row_loss = reinterpret_cast<float*>(sc + kCounterBytes);
+  ra.loss = loss;
+  ra.counter = reinterpret_cast<unsigned int*>(sc);
+  ra.world = ex.world; ra.rank = ex.rank;
+  if (ex.world > 1) {
+    ra.ctl = ex.ctl_peers[ex.rank];
+    for (int r = 0; r < ex.world; ++r) {
+      ra.ctl_peers[r] = ex.ctl_peers[r];
+      ra.lse_dst[0][r] = ex.lse_peers[0][r];
+      ra.lse_dst[1][r] = ex.lse_peers[1][r];
+    }
+    ra.lse_off = row0;
+  } else {
+    ra.lse_dst[0][0] = ra.lse_dst[1][0] = lse_local;
+    ra.lse_off = 0;
+  }
+  MIS_CUDA_TRY(cudaMemsetAsync(sc, 0, sizeof(unsigned int), st));                 // scratch arrives uninitialised
+  fwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ra);
   MIS_CUDA_TRY(cudaGetLastError());
   return MIS_OK;
 }
@@ -1008,15 +1023,6 @@ static int ntxent_bwd_impl(const float* u0, const float* u1, const float* lse0, 
   a.epoch_add = 0;
   a.timeout_clk = ex.timeout_clk;
   a.ctl = ctl;
-  a.fin.fold = D <= 256 ? 1 : 0;
-  a.fin.counters = reinterpret_cast<unsigned int*>(sc);
-  a.fin.z_rows = z_rows;
-  a.fin.rinv = rinv_rows;
-  a.fin.dz = dz;
-  a.fin.z_bf16 = z_dtype == MIS_DTYPE_BF16 ? 1 : 0;
-  a.fin.scale = scale;
-  a.fin.grad_out = grad_out;
-  if (a.fin.fold) MIS_CUDA_TRY(cudaMemsetAsync(sc, 0, kCounterBytes, st));
   auto* fn = &ntxent_tile_kernel<true>;
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   for (int d0 = 0; d0 < D; d0 += ds) {
@@ -1024,7 +1030,7 @@ static int ntxent_bwd_impl(const float* u0, const float* u1, const float* lse0, 
     fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map0, map1, map_ut, a);
     MIS_CUDA_TRY(cudaGetLastError());
   }
-  if (!a.fin.fold) {
+  {
     const int wpb = 8;
     const dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
     if (z_dtype == MIS_DTYPE_F32)

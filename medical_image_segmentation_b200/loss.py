@@ -135,9 +135,11 @@ class CudaKernels:
         """How the loss's kernels reach the GPU (reported by bench.py)."""
         if os.environ.get("MIS_NTXENT_GRAPH") == "1":
             if world == 1:
-                return "graph: one CUDA graph replay per step (prep, forward tile kernel, transpose, backward tile kernel)"
-            return ("graph: one CUDA graph replay per autograd phase (forward: prep + tile kernel; backward: transpose + "
-                    "tile kernel); epoch and buffer parity are read from device memory")
+                return ("graph: one CUDA graph replay per step (prep, forward tile + rows kernels, transpose, backward tile + "
+                        "Jacobian kernels)")
+            return ("graph: one CUDA graph replay per autograd phase (forward: prep + tile + rows kernels; backward: "
+                    "transpose + tile + Jacobian kernels; the peers' flags are awaited inside the tile kernels); epoch and "
+                    "buffer parity are read from device memory")
         return "eager"
 
     @staticmethod
@@ -211,13 +213,12 @@ class CudaKernels:
 
     @staticmethod
     def _n_bwd(D: int) -> int:
-        """Kernels of one backward: transpose + one tile kernel per 256-column slice of dU (+ a finalize kernel when the
-        Jacobian is not folded into the tile kernel, D > 256)."""
-        return 2 if D <= 256 else 2 + D // 256
+        """Kernels of one backward: transpose + one tile kernel per 256-column slice of dU + the Jacobian kernel."""
+        return 2 + max(1, -(-D // 256))
 
     @staticmethod
     def _n_fwd_bwd(D: int) -> int:
-        return 2 + CudaKernels._n_bwd(D)         # prep + forward tile kernel + backward
+        return 3 + CudaKernels._n_bwd(D)         # prep + forward tile kernel + forward rows kernel + backward
 
     @staticmethod
     def _peer_buffers(ex, z):
@@ -253,7 +254,7 @@ class CudaKernels:
         captured once into a CUDA graph over static buffers and replayed (epoch and buffer parity are device-side)."""
         z = z.contiguous()
         CudaKernels._peer_buffers(ex, z)
-        CudaKernels.launches += 2
+        CudaKernels.launches += 3
         if os.environ.get("MIS_NTXENT_GRAPH", "0") == "1":
             if ex.graph is None:
                 ex.graph = _PeerGraph(ex, z, inv_T)
@@ -287,7 +288,7 @@ class CudaKernels:
             rc = _lib.lib.mis_ntxent_fwd(u_all.data_ptr(), cols, D, row0, rows, inv_T, lse.data_ptr(), loss.data_ptr(),
                                          scratch.data_ptr(), scratch.numel(), _stream(u_all))
         _lib.check(rc, "mis_ntxent_fwd")
-        CudaKernels.launches += 1
+        CudaKernels.launches += 2
         return lse, loss
 
     @staticmethod
