@@ -1,21 +1,25 @@
-"""Turn the ncu reports / launch lists under gpurun_out/ into the tracked summaries under profiles/."""
+"""Turn the ncu reports / launch lists under gpurun_out/ into the tracked summaries under profiles/.
+
+    python scripts/summarize_profiles.py r02
+"""
 import collections, csv, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 G = os.path.join(ROOT, "gpurun_out")
 
-KEYS = ['gpu__time_duration.sum', 'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
-        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
-        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__occupancy_limit_shared_mem',
-        'launch__shared_mem_per_block_dynamic', 'launch__cluster_size', 'launch__grid_size', 'launch__block_size',
-        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
-        'sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+KEYS = ['gpu__time_duration.sum', 'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+        'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers', 'launch__shared_mem_per_block_dynamic', 'launch__cluster_size',
+        'launch__grid_size', 'launch__block_size', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_tma.avg.pct_of_peak_sustained_active',
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio']
+        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio']
 
 
 def raw(rep):
@@ -32,45 +36,39 @@ def table(f, v, u):
     f.write("\n")
 
 
+def to_bytes(x, unit):
+    return float(x) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+
+
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-    traffic = {}
-    rep = os.path.join(G, f"aug_{tag}_final.ncu-rep")
-    if os.path.exists(rep):
-        with open(os.path.join(OUT, f"{tag}_aug_final_ncu.md"), "w") as f:
-            f.write(f"# K1 aug_tile_kernel (warp-tile kernel, the default), final build of {tag}: `ncu --set full --clock-control none`\n\n"
-                    "Command: `python scripts/prof_aug.py 1024 224 0` = the bench workload (1024 slices 512x512 u16 -> 2048 views 224x224 bf16).\n"
-                    "(The band kernel it replaced is summarised in r01_aug_band_kernel_ncu.md.)\n"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+    traffic_path = os.path.join(OUT, "aug_traffic.json")
+    traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+    for key, rep, cmd in (("B4096_s224", f"aug_{tag}_final.ncu-rep", "python scripts/prof_aug.py 4096 224 0"),
+                          ("B1024_s224", f"aug_{tag}_b1024.ncu-rep", "python scripts/prof_aug.py 1024 224 0")):
+        rep = os.path.join(G, rep)
+        if not os.path.exists(rep):
+            continue
+        with open(os.path.join(OUT, f"{tag}_aug_strip_{key}_ncu.md"), "w") as f:
+            f.write(f"# K1 aug_strip_kernel (the default variant), build of {tag}: `ncu --set full --clock-control none`\n\n"
+                    f"Command: `{cmd}` ({key[1:].split('_')[0]} slices 512x512 u16 -> views 224x224 bf16; blur / solarize off as in bench.py).\n"
                     "Times under ncu are cold-cache/serialised; bench.py's CUDA-event time is the number of record.\n\n")
             for v, u in raw(rep):
-                f.write(f"## {v.get('Kernel Name', '')[:80]}\n\n")
+                f.write(f"## {v.get('Kernel Name', '')[:90]}\n\n")
                 table(f, v, u)
-                def to_bytes(x, unit):
-                    m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-                    return float(x) * m[unit]
                 rd = to_bytes(v['dram__bytes_read.sum'], u['dram__bytes_read.sum'])
                 wr = to_bytes(v['dram__bytes_write.sum'], u['dram__bytes_write.sum'])
-                traffic["B1024_s224"] = {"dram_bytes_per_launch": rd + wr, "read": rd, "write": wr, "source": os.path.basename(rep)}
-    if traffic:
-        with open(os.path.join(OUT, "aug_traffic.json"), "w") as f:
-            json.dump(traffic, f, indent=1)
+                traffic[key] = {"dram_bytes_per_launch": rd + wr, "read": rd, "write": wr, "kernel": "aug_strip_kernel",
+                                "source": os.path.basename(rep), "command": cmd}
+    with open(traffic_path, "w") as f:
+        json.dump(traffic, f, indent=1)
     rep = os.path.join(G, f"ntxent_{tag}_final.ncu-rep")
     if os.path.exists(rep):
-        with open(os.path.join(OUT, f"{tag}_ntxent_final_ncu.md"), "w") as f:
-            f.write(f"# K2/K3 ntxent_tile_kernel, final build of {tag}: `ncu --set full --clock-control none`\n\n"
-                    "Command: `python scripts/prof_loss.py 4096 128 3` (2N = 8192 rows, D = 128; forward = <0>, backward = <1>).\n\n")
+        with open(os.path.join(OUT, f"{tag}_ntxent_ncu.md"), "w") as f:
+            f.write(f"# K2/K3 ntxent_tile_kernel, build of {tag}: `ncu --set full --clock-control none`\n\n"
+                    "Command: `python scripts/prof_loss.py 4096 128 3` (2N = 8192 rows, D = 128, one rank; forward = <0>, backward = <1>).\n\n")
             for v, u in raw(rep):
-                f.write(f"## {v.get('Kernel Name', '')[:80]}\n\n")
-                table(f, v, u)
-    rep = os.path.join(G, f"ntxent_shard_{tag}.ncu-rep")
-    if os.path.exists(rep):
-        with open(os.path.join(OUT, f"{tag}_ntxent_shard_ncu.md"), "w") as f:
-            f.write(f"# K2/K3 ntxent_tile_kernel at the cfg3 shard shape, build of {tag}: `ncu --set full --clock-control none`\n\n"
-                    "Command: `python scripts/prof_loss_shard.py 1024 8192 128 3` (one rank's 1024 rows against the 8192 gathered rows of a\n"
-                    "global batch of 4096 on 8 GPUs, D = 128; forward = <0>, backward = <1>).  2.1 / 4.3 GFLOP per launch: the kernels\n"
-                    "last 11 / 18 us and are bound by pipeline fill and launch latency, not by the tensor pipe.\n\n")
-            for v, u in raw(rep):
-                f.write(f"## {v.get('Kernel Name', '')[:80]}\n\n")
+                f.write(f"## {v.get('Kernel Name', '')[:90]}\n\n")
                 table(f, v, u)
     lst = os.path.join(G, f"launches_{tag}.csv")
     if os.path.exists(lst):
@@ -81,12 +79,11 @@ def main():
             agg.setdefault(name, []).append(float(r[-1]))
         tot = sum(sum(v) for v in agg.values())
         with open(os.path.join(OUT, f"{tag}_bench_launch_list.md"), "w") as f:
-            f.write(f"# Launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e` ({tag})\n\n"
-                    "`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: compare shares).\n\n"
+            f.write(f"# Launch list of `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-weak` ({tag}, cfg3 at N = 1: 4096 slices)\n\n"
+                    "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` (cold-cache, serialised: compare shares).\n\n"
                     "| kernel | launches | avg us | share of GPU time |\n|---|---|---|---|\n")
             for k, v in agg.items():
                 f.write(f"| {k} | {len(v)} | {sum(v) / len(v) / 1e3:.2f} | {100 * sum(v) / tot:.1f} % |\n")
-    print("profiles written:", sorted(os.listdir(OUT)))
 
 
 if __name__ == "__main__":
