@@ -234,7 +234,8 @@ int mis_ntxent_bwd(const float* u_all, const float* lse_all, const void* z_rows,
  *            128 rows chasing L2 round trips -- cost more than the two launches they saved, DESIGN.md.)
  * Epoch and buffer parity are read from the DEVICE-side counter, so both calls can be captured into CUDA graphs and
  * replayed.  Buffers alternate with the epoch's parity; that is sufficient for safe reuse as long as a rank's backward of
- * epoch k is enqueued before its forward of epoch k+1 (one evaluation outstanding -- loss.py enforces it).
+ * epoch k is enqueued before its forward of epoch k+1 (loss.py issues the backward kernels right behind the forward's
+ * whenever a gradient is required, so this holds by construction; forwards without a backward may follow each other).
  * A consumer waits `timeout_s` seconds for a peer's flag; after that the kernel sets the abort word and TRAPS (the step
  * fails with a CUDA error instead of continuing on stale rows).  Use a time-out of the order of the NCCL watchdog's.
  * rows: any even number (padded per rank as for mis_ntxent_fwd; at most 414 * 128 per rank); every peer buffer is

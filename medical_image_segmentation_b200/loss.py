@@ -18,7 +18,6 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-import weakref
 
 import torch
 import torch.distributed as dist
@@ -77,52 +76,46 @@ class _LocalGraph:
 
 
 class _PeerGraph:
-    """Forward and backward of the multi-rank loss, each captured into a CUDA graph over static buffers.  The first
-    evaluation runs eagerly (it is a real, collective evaluation on every rank), the second is captured and replayed."""
+    """The multi-rank loss AND its gradient (grad_out = 1) captured into ONE CUDA graph over static buffers: prep with
+    peer stores, forward tile + rows kernels, transpose, backward tile kernel(s) (which wait for the peers' log-sum-exp
+    flags themselves) and the Jacobian kernel.  The first evaluation runs eagerly (a real, collective evaluation on every
+    rank); the second is captured and replayed.  Epoch and buffer parity live in device memory, so a replay is a new
+    evaluation.  A forward under ``torch.no_grad()`` has its own, forward-only graph."""
 
     def __init__(self, ex, z: torch.Tensor, inv_T: float):
         self.ex, self.inv_T = ex, float(inv_T)
         self.z = torch.empty_like(z)
         self.loss = torch.empty((1,), dtype=torch.float32, device=z.device)
         self.dz = torch.empty_like(z)
-        self.gout = torch.ones((1,), dtype=torch.float32, device=z.device)
-        self.fwd_graph = self.bwd_graph = None
-        self.fwd_calls = self.bwd_calls = 0
+        self.ones = torch.ones((1,), dtype=torch.float32, device=z.device)
+        self.graphs = {False: None, True: None}          # with_grad -> captured graph
+        self.calls = {False: 0, True: 0}
+        self.in_flight = 0                               # results whose backward() has not consumed self.dz yet
 
     def matches(self, z: torch.Tensor, inv_T: float) -> bool:
         return z.shape == self.z.shape and z.dtype == self.z.dtype and float(inv_T) == self.inv_T
 
-    def forward(self, z: torch.Tensor):
+    def _launch(self, with_grad: bool):
+        CudaKernels._launch_fwd_peer(self.z, self.ex, self.inv_T, self.loss)
+        if with_grad:
+            CudaKernels._launch_bwd_peer(self.z, self.ex, self.inv_T, self.ones, self.dz)
+
+    def run(self, z: torch.Tensor, with_grad: bool):
         self.z.copy_(z)
-        if self.fwd_calls == 0:
-            CudaKernels._launch_fwd_peer(self.z, self.ex, self.inv_T, self.loss)
+        if self.calls[with_grad] == 0:
+            self._launch(with_grad)
         else:
-            if self.fwd_graph is None:
+            if self.graphs[with_grad] is None:
                 torch.cuda.current_stream(z.device).synchronize()
-                self.fwd_graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.fwd_graph):
-                    CudaKernels._launch_fwd_peer(self.z, self.ex, self.inv_T, self.loss)
-            self.fwd_graph.replay()
-        self.fwd_calls += 1
-        return self.z, self.loss.clone(), self
-
-    def backward(self, grad_out: torch.Tensor):
-        self.gout.copy_(grad_out.reshape(1))
-        if self.bwd_calls == 0:
-            CudaKernels._launch_bwd_peer(self.z, self.ex, self.inv_T, self.gout, self.dz)
-        else:
-            if self.bwd_graph is None:
-                torch.cuda.current_stream(self.z.device).synchronize()
-                self.bwd_graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.bwd_graph):
-                    CudaKernels._launch_bwd_peer(self.z, self.ex, self.inv_T, self.gout, self.dz)
-            self.bwd_graph.replay()
-        self.bwd_calls += 1
-        return self.dz.clone()
-
-
-class _Pending:
-    """Marks a multi-rank forward whose backward has not run (dies with its autograd graph)."""
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch(with_grad)
+                self.graphs[with_grad] = g
+            self.graphs[with_grad].replay()
+        self.calls[with_grad] += 1
+        if with_grad:
+            self.in_flight += 1
+        return self.loss.clone(), (self.dz if with_grad else None), self
 
 
 class CudaKernels:
@@ -137,9 +130,9 @@ class CudaKernels:
             if world == 1:
                 return ("graph: one CUDA graph replay per step (prep, forward tile + rows kernels, transpose, backward tile + "
                         "Jacobian kernels)")
-            return ("graph: one CUDA graph replay per autograd phase (forward: prep + tile + rows kernels; backward: "
-                    "transpose + tile + Jacobian kernels; the peers' flags are awaited inside the tile kernels); epoch and "
-                    "buffer parity are read from device memory")
+            return ("graph: one CUDA graph replay per step (prep with peer stores, forward tile + rows kernels, transpose, "
+                    "backward tile + Jacobian kernels; the peers' flags are awaited inside the tile kernels; epoch and buffer "
+                    "parity are read from device memory)")
         return "eager"
 
     @staticmethod
@@ -248,31 +241,39 @@ class CudaKernels:
         _lib.check(rc, "mis_ntxent_bwd_peer")
 
     @staticmethod
-    def fwd_peer(z: torch.Tensor, ex, inv_T: float):
-        """Forward with the NVLink exchange fused into the kernels: one ABI call (mis_ntxent_fwd_peer = prep kernel with
-        peer stores + ONE tile kernel that waits for the peers' rows itself).  With ``MIS_NTXENT_GRAPH=1`` the call is
-        captured once into a CUDA graph over static buffers and replayed (epoch and buffer parity are device-side)."""
-        z = z.contiguous()
+    def eval_peer(z: torch.Tensor, ex, inv_T: float, with_grad: bool):
+        """Loss (and, with ``with_grad``, dL/dz for grad_out = 1) with the NVLink exchange fused into the kernels:
+        mis_ntxent_fwd_peer (prep kernel with peer stores + ONE tile kernel that waits for the peers' rows itself + rows
+        kernel) then mis_ntxent_bwd_peer (transpose + tile kernel(s) that wait for the peers' log-sum-exp flags + Jacobian
+        kernel), issued back to back on the caller's stream -- every rank issues backward(k) before forward(k+1), which
+        is what makes the two-deep buffer parity sufficient.  With ``MIS_NTXENT_GRAPH=1`` the whole evaluation is ONE
+        CUDA graph replay over static buffers.  Returns (loss, dz or None, graph holder or None)."""
+        if not z.is_cuda:
+            raise RuntimeError("nt_xent_loss has no CPU path: embeddings must be CUDA tensors")
+        z = z.detach().contiguous()
         CudaKernels._peer_buffers(ex, z)
-        CudaKernels.launches += 3
+        CudaKernels.launches += 3 + (CudaKernels._n_bwd(z.shape[1]) if with_grad else 0)
         if os.environ.get("MIS_NTXENT_GRAPH", "0") == "1":
             if ex.graph is None:
                 ex.graph = _PeerGraph(ex, z, inv_T)
-            if ex.graph.matches(z, inv_T):
-                return ex.graph.forward(z)
+            if ex.graph.matches(z, inv_T) and ex.graph.in_flight == 0:
+                return ex.graph.run(z, with_grad)
         loss = torch.empty((1,), dtype=torch.float32, device=z.device)
         CudaKernels._launch_fwd_peer(z, ex, inv_T, loss)
-        return z, loss, None
+        dz = None
+        if with_grad:
+            dz = torch.empty_like(z)
+            CudaKernels._launch_bwd_peer(z, ex, inv_T, CudaKernels._ones(z.device), dz)
+        return loss, dz, None
+
+    _ones_cache: dict = {}
 
     @staticmethod
-    def bwd_peer(z, ex, inv_T: float, grad_out: torch.Tensor, graph):
-        CudaKernels.launches += CudaKernels._n_bwd(z.shape[1])
-        g = grad_out if (grad_out.dtype == torch.float32 and grad_out.is_contiguous()) else grad_out.to(torch.float32).contiguous()
-        if graph is not None:
-            return graph.backward(g)
-        dz = torch.empty_like(z)
-        CudaKernels._launch_bwd_peer(z, ex, inv_T, g.reshape(1), dz)
-        return dz
+    def _ones(device) -> torch.Tensor:
+        t = CudaKernels._ones_cache.get(device)
+        if t is None:
+            t = CudaKernels._ones_cache[device] = torch.ones((1,), dtype=torch.float32, device=device)
+        return t
 
     @staticmethod
     def scratch(rows: int, cols: int, D: int, device) -> torch.Tensor:
@@ -334,20 +335,13 @@ class _NTXent(torch.autograd.Function):
         if distributed and kernels is CudaKernels:
             ex = peer.get_exchange(group, rows, z.shape[1], z.device)
             if ex is not None:
-                # One evaluation outstanding: the backward reads the device-side epoch of the LAST forward, and buffer
-                # parity alone makes reuse safe only if backward(k) is enqueued before forward(k+1).  Every rank runs the
-                # same autograd program, so every rank raises here together (no silent change of transport).
-                if ex.pending is not None and ex.pending() is not None:
-                    raise RuntimeError(
-                        "nt_xent_loss: a second multi-rank forward was issued before the backward of the previous one. "
-                        "The NVLink exchange supports one evaluation in flight; run backward first, wrap evaluations that "
-                        "need no gradient in torch.no_grad(), or set MIS_NTXENT_EXCHANGE=nccl.")
-                z, loss, graph = kernels.fwd_peer(z, ex, inv_T)
-                if ctx.needs_input_grad[0]:
-                    ctx.token = _Pending()
-                    ex.pending = weakref.ref(ctx.token)
-                ctx.save_for_backward(z)
-                ctx.meta = ("peer", inv_T, ex, kernels, graph)
+                # forward AND backward kernels are issued here (the gradient for grad_out = 1); backward() only scales.
+                # So no evaluation is ever left half-way through the exchange, whatever the caller does with the loss.
+                loss, dz, holder = kernels.eval_peer(z, ex, inv_T, bool(ctx.needs_input_grad[0]))
+                if dz is not None:
+                    ctx.save_for_backward(dz)
+                ctx.meta = None
+                ctx.holder = holder
                 return loss.reshape(())
         z, u, rinv = kernels.prep(z)
         u_all = _all_gather_rows(u, group) if distributed else u
@@ -365,12 +359,6 @@ class _NTXent(torch.autograd.Function):
             if ctx.holder is not None:
                 ctx.holder.in_flight -= 1
             return out, None, None, None
-        if ctx.meta[0] == "peer":
-            (z,) = ctx.saved_tensors
-            _, inv_T, ex, kernels, graph = ctx.meta
-            dz = kernels.bwd_peer(z, ex, inv_T, grad_out, graph)
-            ex.pending = None
-            return dz, None, None, None
         z, u_all, rinv, lse = ctx.saved_tensors
         inv_T, group, distributed, rank, kernels, scratch = ctx.meta
         lse_all = _all_gather_rows(lse, group) if distributed else lse

@@ -67,8 +67,7 @@ class PeerExchange:
         self.l_peers = [arr(*([b + o for b in bases] + pad)) for o in self.off_l]
         self.scratch = None                              # kernel scratch, rinv (allocated by loss.py)
         self.rinv = None
-        self.pending = None                              # weakref to the autograd ctx whose backward has not run yet
-        self.graph = None                                # captured forward / backward (MIS_NTXENT_GRAPH=1)
+        self.graph = None                                # captured evaluation (MIS_NTXENT_GRAPH=1)
 
     def device_epoch(self) -> int:
         """Forwards completed on this rank (synchronises the device)."""

@@ -28,6 +28,30 @@ for (B, D, T) in ((64, 64, 0.1), (256, 128, 0.1), (128, 256, 0.2), (256, 128, 0.
     good = fro <= 1e-3 and lrel <= 1e-3
     ok &= good
     print(f"rank {rank}/{world} B={B} D={D} T={T}: loss rel {lrel:.2e} grad fro rel {fro:.2e} {'OK' if good else 'FAIL'}", flush=True)
+# evaluation patterns: a forward under no_grad between two training evaluations, a scaled loss, and two forwards whose
+# backwards run later in one autograd pass (each evaluation issues its own backward kernels right behind its forward)
+B, D, T = 128, 128, 0.1
+g = torch.Generator().manual_seed(23)
+za = [torch.randn(2 * B, D, generator=g) for _ in range(world)]
+zb = [torch.randn(2 * B, D, generator=g) for _ in range(world)]
+la, ga = L.ntxent_rank_sharded(za, T)
+lb, gb = L.ntxent_rank_sharded(zb, T)
+from medical_image_segmentation_b200 import nt_xent_rows
+for it in range(3):
+    xa = za[rank].cuda().requires_grad_(True)
+    xb = zb[rank].cuda().requires_grad_(True)
+    with torch.no_grad():
+        l0 = nt_xent_rows(xb, T, dist.group.WORLD)
+    l1 = nt_xent_rows(xa, T, dist.group.WORLD)
+    l2 = nt_xent_rows(xb, T, dist.group.WORLD)
+    (3.0 * l1 + l2).backward()
+    e = [abs(l0.item() - lb[rank]) / abs(lb[rank]), abs(l1.item() - la[rank]) / abs(la[rank]), abs(l2.item() - lb[rank]) / abs(lb[rank]),
+         np.linalg.norm(xa.grad.cpu().double().numpy() - 3.0 * ga[rank].numpy()) / np.linalg.norm(3.0 * ga[rank].numpy()),
+         np.linalg.norm(xb.grad.cpu().double().numpy() - gb[rank].numpy()) / np.linalg.norm(gb[rank].numpy())]
+    good = max(e) <= 1e-3
+    ok &= good
+    print(f"rank {rank}/{world} patterns pass {it}: no_grad loss {e[0]:.1e}, losses {e[1]:.1e} {e[2]:.1e}, grads {e[3]:.1e} {e[4]:.1e} "
+          f"{'OK' if good else 'FAIL'}", flush=True)
 from medical_image_segmentation_b200 import peer
 print(f"rank {rank}: exchange mode {peer.mode()}, peer exchanges in use: {len(peer._cache)}, disabled: {peer._disabled_reason}", flush=True)
 try:
