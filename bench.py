@@ -358,7 +358,7 @@ def run_b200(args):
     aug_only = args.config == "cfg5"
 
     def step_device():
-        params = t.to_view_major(t.next_params(B, H, W))      # host RNG replay, same stream as the reference
+        params = t.next_params(B, H, W, view_major=True)       # host RNG replay, same stream as the reference
         t.apply(x_dev, params, out)
         if aug_only:
             return None
@@ -442,7 +442,7 @@ def run_b200(args):
         ow = out[:2 * Bw] if B >= Bw else torch.empty((2 * Bw, 1, s, s), dtype=torch.bfloat16, device=dev)
 
         def step_weak():
-            p = t.to_view_major(t.next_params(Bw, H, W))
+            p = t.next_params(Bw, H, W, view_major=True)
             t.apply(xw, p, ow)
             zw.grad = None
             nt_xent_rows(zw, args.temperature, group).backward()

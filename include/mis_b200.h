@@ -96,6 +96,12 @@ int mis_draw_two_view_params(uint8_t* rng_state, int64_t rng_state_len, int n_im
  * order of torch.cat([view1, view2]) (byol_pytorch.py:207) that mis_aug_two_view's output planes follow.  Host only. */
 int mis_params_to_view_major(const MisViewParams* in, int n_images, MisViewParams* out);
 
+/* Host-side check of a table before it is handed to mis_aug_two_view (the kernel trusts it): every record must address a
+ * slice 0 <= img < n_images and a box inside H x W, and a record with MIS_VIEW_BLUR a finite positive blur_sigma.
+ * *bad_index = first offending record or -1; *flags_or = OR of the flag words (of the records before bad_index). */
+int mis_view_params_check(const MisViewParams* params, int n_views, int n_images, int H, int W, uint32_t* flags_or,
+                          int* bad_index);
+
 /* Single-view "Resize((s,s)) + ColorJitter(brightness, contrast)" records (the Decathlon flavour of the chain,
  * lightning_module.py:684-693): box = whole image, no flip, jitter always applied; consumes randperm(4) and one
  * uniform per non-zero magnitude per image exactly like torchvision's ColorJitter.make_params

@@ -35,6 +35,8 @@ EXPORTS = {
     "mis_draw_two_view_params": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mis_params_to_view_major": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "mis_view_params_check": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32),
+                                        C.POINTER(C.c_int)]),
     "mis_draw_resize_jitter_params": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                                 C.c_float, C.c_void_p]),
     "mis_aug_two_view": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int,

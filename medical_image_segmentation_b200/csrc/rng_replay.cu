@@ -275,3 +275,27 @@ extern "C" int mis_params_to_view_major(const MisViewParams* in, int n_images, M
   }
   return MIS_OK;
 }
+
+// K1 trusts its table; this is the host-side check of one (a few microseconds for thousands of records, in place of a
+// dozen numpy passes): every record addresses a slice of the batch and a box inside it, a blurred view has a usable sigma.
+extern "C" int mis_view_params_check(const MisViewParams* p, int n_views, int n_images, int H, int W, uint32_t* flags_or,
+                                     int* bad_index) {
+  MIS_REQUIRE((p || n_views == 0) && n_views >= 0 && flags_or && bad_index, MIS_ERR_INVALID_ARG,
+              "mis_view_params_check: bad arguments");
+  uint32_t f = 0;
+  *bad_index = -1;
+  for (int k = 0; k < n_views; ++k) {
+    const MisViewParams& r = p[k];
+    const bool box_ok = r.img >= 0 && r.img < n_images && r.top >= 0 && r.left >= 0 && r.h >= 1 && r.w >= 1 &&
+                        (int64_t)r.top + r.h <= H && (int64_t)r.left + r.w <= W;
+    const bool blur_ok = !(r.flags & MIS_VIEW_BLUR) || (r.blur_sigma > 0.f && r.blur_sigma <= 3.4e38f);
+    if (!box_ok || !blur_ok) {
+      *bad_index = k;
+      *flags_or = f;
+      return MIS_OK;
+    }
+    f |= r.flags;
+  }
+  *flags_or = f;
+  return MIS_OK;
+}

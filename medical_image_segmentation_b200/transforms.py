@@ -98,6 +98,7 @@ class FusedTwoViewTransforms:
         self.generator = generator
         self._pool = None                     # one helper thread drawing the NEXT batch's parameters
         self._pending = None                  # ((B, H, W), future)
+        self._norm_cache = {}
         self._x_stage: torch.Tensor | None = None      # device staging buffer of host batches
         self._x_host_ring = []                          # (pinned host batch, event after its copies): alive while in flight
         self.last_h2d_bytes = 0
@@ -112,18 +113,19 @@ class FusedTwoViewTransforms:
         """Image-major records [2*i+v], drawn like B calls of the reference's __call__."""
         return draw_two_view_params(B, H, W, self.blur_prob, self.solarize_prob, generator=self.generator)
 
-    def next_params(self, B: int, H: int, W: int) -> np.ndarray:
+    def next_params(self, B: int, H: int, W: int, view_major: bool = False) -> np.ndarray:
         """``draw_params`` with the draw of the FOLLOWING batch started on a helper thread (``prefetch_params=True``):
         the host RNG replay (~0.4 ms per 1024 slices) then overlaps the GPU work of the current batch.  The records are
         the same, in the same order, as back-to-back ``draw_params`` calls -- as long as nothing else consumes torch's
         global CPU generator between calls (the helper thread reads and writes its state); pass ``generator=`` to the
-        constructor to draw from a private generator instead."""
+        constructor to draw from a private generator instead.  ``view_major=True`` returns ``to_view_major(...)`` of
+        the table (reordered on the helper thread as well)."""
         if not self.prefetch_params:
-            return self.draw_params(B, H, W)
+            return self._draw(B, H, W, view_major)
         if self._pool is None:
             from concurrent.futures import ThreadPoolExecutor
             self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mis-params")
-        key = (B, H, W)
+        key = (B, H, W, bool(view_major))
         params = None
         if self._pending is not None:
             pkey, fut = self._pending
@@ -131,10 +133,23 @@ class FusedTwoViewTransforms:
             got = fut.result()                       # always joined: the generator is never touched concurrently
             if pkey == key:
                 params = got
+            elif pkey[:3] == key[:3]:                # same draw, other order: reorder instead of drawing again
+                params = self.to_view_major(got) if view_major else self._to_image_major(got)
         if params is None:
-            params = self.draw_params(B, H, W)
-        self._pending = (key, self._pool.submit(self.draw_params, B, H, W))
+            params = self._draw(B, H, W, view_major)
+        self._pending = (key, self._pool.submit(self._draw, B, H, W, view_major))
         return params
+
+    def _draw(self, B: int, H: int, W: int, view_major: bool) -> np.ndarray:
+        p = self.draw_params(B, H, W)
+        return self.to_view_major(p) if view_major else p
+
+    @staticmethod
+    def _to_image_major(vm: np.ndarray) -> np.ndarray:
+        B = vm.shape[0] // 2
+        out = np.empty_like(vm)
+        out[0::2], out[1::2] = vm[:B], vm[B:]
+        return out
 
     def drain_prefetch(self) -> None:
         """Wait for (and drop) a parameter draw in flight, e.g. before re-seeding the generator."""
@@ -164,8 +179,7 @@ class FusedTwoViewTransforms:
             raise ValueError(f"expected [B,C,H,W], got {tuple(x.shape)}")
         x = x.contiguous()
         B, Cc, H, W = x.shape
-        mean = _as_float_seq(self.mean, Cc, "mean")
-        std = _as_float_seq(self.std, Cc, "std")
+        mean_c, std_c = self._norm_args(Cc)
         n_views = int(params_view_major.shape[0])
         assert params_view_major.dtype == VIEW_PARAMS_DTYPE
         s = self.crop_size
@@ -183,13 +197,11 @@ class FusedTwoViewTransforms:
             assert out.is_cuda and out.is_contiguous() and out.dtype == self.out_dtype
             assert tuple(out.shape) == (n_views, Cc, s, s)
         dev = self._stage_params(params_view_major, x.device)
-        mean_c = (C.c_float * Cc)(*mean)
-        std_c = (C.c_float * Cc)(*std)
         with _on_device(x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
             rc = _lib.lib.mis_aug_two_view(
                 x.data_ptr(), B, Cc, H, W, Cc * H * W, dev.data_ptr(), n_views,
-                self.window[0], self.window[1], C.cast(mean_c, C.c_void_p), C.cast(std_c, C.c_void_p),
+                self.window[0], self.window[1], mean_c, std_c,
                 out.data_ptr(), s, MIS_DTYPE_F32 if self.out_dtype == torch.float32 else MIS_DTYPE_BF16,
                 self.use_tma, C.c_void_p(stream))
             _lib.check(rc, "mis_aug_two_view")
@@ -197,49 +209,55 @@ class FusedTwoViewTransforms:
             if extra & MIS_VIEW_BLUR:      # GaussianBlur(23) -> solarize -> normalise for the views that drew a blur
                 rc = _lib.lib.mis_aug_blur_views(
                     out.data_ptr(), MIS_DTYPE_F32 if self.out_dtype == torch.float32 else MIS_DTYPE_BF16, dev.data_ptr(),
-                    n_views, Cc, s, C.cast(mean_c, C.c_void_p), C.cast(std_c, C.c_void_p), C.c_void_p(stream))
+                    n_views, Cc, s, mean_c, std_c, C.c_void_p(stream))
                 _lib.check(rc, "mis_aug_blur_views")
                 self.launches += 1
         return out
 
+    def _norm_args(self, Cc: int):
+        """mean / std as C float arrays (cached per channel count; the arrays stay alive with the transform)."""
+        got = self._norm_cache.get(Cc)
+        if got is None:
+            mean = (C.c_float * Cc)(*_as_float_seq(self.mean, Cc, "mean"))
+            std = (C.c_float * Cc)(*_as_float_seq(self.std, Cc, "std"))
+            got = self._norm_cache[Cc] = (mean, std, C.cast(mean, C.c_void_p), C.cast(std, C.c_void_p))
+        return got[2], got[3]
+
     @staticmethod
     def _validate_table(p: np.ndarray, B: int, H: int, W: int) -> int:
-        """The kernel trusts the table: check every record addresses a slice of the batch and a box inside it.
-        Returns the OR of all flag words."""
+        """The kernel trusts the table: check every record addresses a slice of the batch and a box inside it
+        (mis_view_params_check, a native pass of a few microseconds).  Returns the OR of all flag words."""
         if p.shape[0] == 0:
             return 0
-        img, top, left, h, w = (p[k].astype(np.int64) for k in ("img", "top", "left", "h", "w"))
-        bad = (img < 0) | (img >= B) | (top < 0) | (left < 0) | (h < 1) | (w < 1) | (top + h > H) | (left + w > W)
-        if bad.any():
-            k = int(np.flatnonzero(bad)[0])
-            raise ValueError(f"view record {k} is outside the batch: img {int(img[k])} of {B}, box (top {int(top[k])}, left "
-                             f"{int(left[k])}, h {int(h[k])}, w {int(w[k])}) in {H}x{W}")
-        sig = p["blur_sigma"][(p["flags"] & MIS_VIEW_BLUR) != 0]
-        if sig.size and not (np.isfinite(sig).all() and (sig > 0).all()):
-            raise ValueError("a record with MIS_VIEW_BLUR needs a positive blur_sigma")
-        return int(np.bitwise_or.reduce(p["flags"]))
+        p = np.ascontiguousarray(p)
+        flags, bad = C.c_uint32(0), C.c_int(-1)
+        _lib.check(_lib.lib.mis_view_params_check(p.ctypes.data, p.shape[0], B, H, W, C.byref(flags), C.byref(bad)),
+                   "mis_view_params_check")
+        if bad.value >= 0:
+            r = p[bad.value]
+            if (r["flags"] & MIS_VIEW_BLUR) and not (np.isfinite(r["blur_sigma"]) and r["blur_sigma"] > 0):
+                raise ValueError(f"view record {bad.value}: a record with MIS_VIEW_BLUR needs a positive blur_sigma")
+            raise ValueError(f"view record {bad.value} is outside the batch: img {int(r['img'])} of {B}, box (top "
+                             f"{int(r['top'])}, left {int(r['left'])}, h {int(r['h'])}, w {int(r['w'])}) in {H}x{W}")
+        return int(flags.value)
 
     def _stage_params(self, params: np.ndarray, device) -> torch.Tensor:
         """Copy the table through one of three persistent pinned buffers (no per-call cudaHostAlloc)."""
         nbytes = params.nbytes
         if len(self._staging) < 3:
-            host = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
-            self._staging.append([host, torch.empty_like(host, device=device), torch.cuda.Event(), host.numpy()])
-            slot = self._staging[-1]
+            slot = [None, None, torch.cuda.Event(), None]
+            self._staging.append(slot)
         else:
             slot = self._staging[self._staging_idx % 3]
             self._staging_idx += 1
             slot[2].synchronize()                     # the copy that last used this buffer has finished
-            if slot[0].numel() < nbytes or slot[1].device != torch.device(device):
-                slot[0] = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-                slot[1] = torch.empty(nbytes, dtype=torch.uint8, device=device)
-                slot[3] = slot[0].numpy()
+        if slot[0] is None or slot[0].numel() != nbytes or slot[1].device != torch.device(device):
+            slot[0] = torch.empty(nbytes, dtype=torch.uint8).pin_memory()     # exact size: whole-tensor copies below
+            slot[1] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            slot[3] = slot[0].numpy()
         host, dev, ev, host_np = slot
-        host_np[:nbytes] = params.view(np.uint8).reshape(-1)
-        if nbytes == host.numel():
-            dev.copy_(host, non_blocking=True)
-        else:
-            dev[:nbytes].copy_(host[:nbytes], non_blocking=True)
+        host_np[:] = params.view(np.uint8).reshape(-1)
+        dev.copy_(host, non_blocking=True)
         ev.record(torch.cuda.current_stream(device))
         return dev
 

@@ -142,6 +142,16 @@ def test_prefetched_parameter_stream_is_the_same_stream():
     torch.manual_seed(5)
     assert b.next_params(4, 64, 64).tobytes() == x.tobytes()
     b.drain_prefetch()
+    # view_major=True: the helper thread also reorders; switching the order mid-stream keeps the same draws
+    torch.manual_seed(17)
+    ref = [a.draw_params(6, 96, 80) for _ in range(4)]
+    torch.manual_seed(17)
+    got = [b.next_params(6, 96, 80, view_major=True), b.next_params(6, 96, 80, view_major=True),
+           b.next_params(6, 96, 80), b.next_params(6, 96, 80, view_major=True)]
+    b.drain_prefetch()
+    for k, (r, g) in enumerate(zip(ref, got)):
+        want = r if k == 2 else a.to_view_major(r)
+        assert want.tobytes() == g.tobytes(), k
 
 
 def test_ffcv_flavour_parameter_records():
