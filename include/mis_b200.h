@@ -192,17 +192,21 @@ int64_t mis_aug_algorithmic_bytes(const MisViewParams* params_host, int n_views,
  *                     and a rows kernel (lse, positives, mean; its last block publishes).
  *   mis_ntxent_bwd    dz_local = grad_out[0] * grad_scale * sum_r' dL_r'/dz_local  (SURVEY A.5,
  *                     option L: uses the all-gathered lse instead of a D-wide gradient exchange).
- *                     S is recomputed tile by tile; W = P + P^T is rounded to TF32 and stays in
- *                     TMEM as the A operand of the second MMA; dU (128 x D fp32) stays in TMEM for
- *                     the whole column walk.  grad_out may be NULL (= 1).  dz has z's dtype.
+ *                     S is recomputed tile by tile and W = P + P^T (minus the positives) is rounded to TF32.
+ *                     D <= 256: W stays in TMEM as the A operand of the second MMA and dU (128 x D fp32) stays in
+ *                     TMEM for the whole column walk.  D > 256 (a multiple of 256): the W tiles are written to the
+ *                     scratch ([rows, cols] fp32 -- 4 bytes against 2 * D flops per element) and dU = W . U_all is
+ *                     one tcgen05 GEMM over all of D, so S is computed once whatever the width.
+ *                     grad_out may be NULL (= 1).  dz has z's dtype.
  *
  * `rows` is the number of embedding rows the rank really has (any even number: a per-GPU batch of 96 gives 192).
  * Every rank's block of the gathered matrix is padded to P = mis_ntxent_padded_rows(rows) (the next multiple of 128):
  * u / u_all hold P (resp. world * P) rows, rinv / lse P (world * P) floats, and `cols`, `row0` are in PADDED
  * coordinates (cols = world * P, row0 = rank * P).  The padding rows are zero vectors, masked as columns inside the
  * tile kernels and skipped as rows; z and dz hold the valid rows only.
- * D a multiple of 32 (backward: D <= 256, or a multiple of 256 -- wider embeddings are walked in 256-column slices
- * of dU, recomputing S per slice); T >= 0.025.  `scratch` must hold mis_ntxent_scratch_bytes(rows, cols, D) bytes.
+ * D a multiple of 32 (backward: D <= 256, or a multiple of 256); T >= 0.025.  `scratch` must hold
+ * mis_ntxent_scratch_bytes(rows, cols, D) bytes (for D > 256 that includes the rows x cols W matrix: 0.5 GB per rank
+ * at 4096 x 32768).
  * ------------------------------------------------------------------------------------------ */
 int mis_ntxent_padded_rows(int rows);
 int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D);

@@ -85,6 +85,7 @@ struct TileArgs {
   const float* lse[2];     // per parity: [cols] all-gathered log-sum-exp (backward): c_j = exp(1/T - lse_j) on the fly
   float inv_T;
   float* partial;          // fwd: [nsplit][rows]   bwd: [nsplit][rows][D]
+  float* w_out;            // backward for D > 256 (kWOut): W = P + P^T - positives, TF32-rounded, [rows][cols] row-major
   // multi-rank exchange (world == 1: ctl == nullptr, parity 0)
   PeerCtl* ctl;            // local control block
   PeerCtl* ctl_peers[kMaxPeers];
@@ -214,7 +215,10 @@ __device__ __forceinline__ void wait_peer_flag(const uint32_t* f, uint32_t epoch
 }
 __device__ __forceinline__ float ldcg_f32(const float* p) { return __ldcg(p); }
 
-template <bool kBwd>
+// kWOut (backward, D > 256): the W tiles are written to HBM instead of feeding the dU MMAs from TMEM; dU = W . U_all is
+// then one plain GEMM (wu_gemm_kernel) -- at D = 2048 a W element costs 4 bytes of traffic against 2 * D flops, so
+// materialising it is cheap, whereas walking dU in 256-column slices recomputed S once per slice.
+template <bool kBwd, bool kWOut = false>
 __global__ void __launch_bounds__(kThreads, 1)
 ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_constant__ CUtensorMap map_u1,
                    const __grid_constant__ CUtensorMap map_ut, const __grid_constant__ TileArgs a) {
@@ -253,7 +257,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(map_u);
-    if (kBwd) prefetch_tmap(&map_ut);
+    if (kBwd && !kWOut) prefetch_tmap(&map_ut);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -343,9 +347,9 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
       };
       for (int t = 0; t < T; ++t) {
         push_s(t);
-        if (kBwd && t >= 1) push_g(t - 1);
+        if (kBwd && !kWOut && t >= 1) push_g(t - 1);
       }
-      if (kBwd) push_g(T - 1);
+      if (kBwd && !kWOut) push_g(T - 1);
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ========================================
@@ -383,7 +387,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
       }
       for (int t = 0; t < T; ++t) {
         const int buf = t & 1;
-        if (!kBwd && t >= 2) {     // forward: S[buf] is free once the epilogue of tile t-2 has read it
+        if ((!kBwd || kWOut) && t >= 2) {     // no dU MMAs: S[buf] is free once the epilogue of tile t-2 has read it
           mbar_wait(&bars.epi_done[buf], ((t - 2) >> 1) & 1);
           tc_fence_after();
         }
@@ -403,9 +407,9 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
           advance();
         }
         tc_commit(&bars.tmem_full[buf]);
-        if (kBwd && t >= 1) mma_g(t - 1);
+        if (kBwd && !kWOut && t >= 1) mma_g(t - 1);
       }
-      if (kBwd) {
+      if (kBwd && !kWOut) {
         mma_g(T - 1);
         tc_commit(&bars.du_full);
       }
@@ -481,16 +485,21 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
             }
           }
         }
-        if (kBwd) tmem_st32(taddr, v);
+        if (kBwd && !kWOut) tmem_st32(taddr, v);
+        if (kWOut) {               // one 128-byte line of this thread's row
+          uint4* dst = reinterpret_cast<uint4*>(a.w_out + (size_t)(row_tile * kTile + r_in) * a.cols + col0 + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
       }
-      if (kBwd) tmem_wait_st();
+      if (kBwd && !kWOut) tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&bars.epi_done[buf]);
     }
     if (!kBwd) {
       // each group writes its own partial row sums: partial[(2*split + grp)][row]
       a.partial[(size_t)(2 * split + grp) * a.rows + row_tile * kTile + r_in] = (rs0 + rs1) + (rs2 + rs3);
-    } else {
+    } else if (!kWOut) {
       mbar_wait(&bars.du_full, 0);
       tc_fence_after();
       float* dst = a.partial + ((size_t)split * a.rows + row_tile * kTile + r_in) * a.D + a.d0;
@@ -511,6 +520,118 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
   }
 
+}
+
+// ---- dU = W . U_all for wide embeddings (D > 256) -----------------------------------------------------------------
+// Plain TF32 GEMM on tcgen05: one CTA = 128 rows x 256 columns of dU, accumulator in TMEM, K = a range of the gathered
+// rows walked in 32-wide k-blocks through a 4-stage ring (A = W box 128 x 32, B = U^T box 256 x 32, both K-major,
+// 128-byte swizzle).  warp 0 / warp 6: TMA producers (A / B; one thread sustains one box per ~455 clk, a k-block of MMAs
+// lasts ~740), warp 1: MMA issuer, warps 2-5: epilogue (TMEM -> partial[split][rows][D]).
+struct GemmArgs {
+  int rows, D;               // padded rows of this rank, embedding width
+  int kblocks, kb_per_split; // k-blocks (32 gathered rows each) in total / per grid.z slice
+  float* partial;            // [ksplit][rows][D]
+};
+constexpr int kGemmThreads = 224;
+constexpr int kGemmN = 256;
+constexpr int kGemmStages = 4;
+constexpr int kGemmStageBytes = (kTile + kGemmN) * 128;   // 48 KB
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+wu_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_ut,
+               const __grid_constant__ GemmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Bars& bars = *reinterpret_cast<Bars*>(smem + kRingBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tile = blockIdx.x, row_tile = blockIdx.y, split = blockIdx.z;   // the n-tiles of a row tile are co-scheduled:
+                                                                              // they read the same W boxes (L2 hits)
+  const int kb0 = split * a.kb_per_split;
+  const int nkb = min(a.kb_per_split, a.kblocks - kb0);
+  if (warp == 0 && lane == 0) prefetch_tmap(&map_w);
+  if (warp == 6 && lane == 0) prefetch_tmap(&map_ut);
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kGemmStages; ++i) {
+        mbar_init(&bars.full[i], 1);
+        mbar_init(&bars.empty[i], 1);
+      }
+      mbar_init(&bars.du_full, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_ptr)),
+                 "r"(kGemmN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_ptr;
+
+  if (warp == 0 || warp == 6) {
+    if (lane == 0) {
+      const bool is_a = warp == 0;
+      int stage = 0, phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&bars.empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kGemmStageBytes;
+        const int k0 = (kb0 + kb) * kKBlock;
+        if (is_a) {
+          mbar_arrive_expect_tx(&bars.full[stage], (uint32_t)kGemmStageBytes);
+          tma_load_2d(sa, &map_w, k0, row_tile * kTile, &bars.full[stage]);
+        } else {
+          tma_load_2d(sa + kTile * 128, &map_ut, k0, n_tile * kGemmN, &bars.full[stage]);
+        }
+        if (++stage == kGemmStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kTile, kGemmN);
+      int stage = 0, phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&bars.full[stage], phase);
+        tc_fence_after();
+        const uint8_t* sa = smem + stage * kGemmStageBytes;
+        const uint64_t ad = make_desc(sa), bd = make_desc(sa + kTile * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_ss(tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+        tc_commit(&bars.empty[stage]);
+        if (++stage == kGemmStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      tc_commit(&bars.du_full);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r_in = quad * 32 + lane;
+    const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+    mbar_wait(&bars.du_full, 0);
+    tc_fence_after();
+    float* dst = a.partial + ((size_t)split * a.rows + row_tile * kTile + r_in) * a.D + n_tile * kGemmN;
+#pragma unroll 1
+    for (int c = 0; c < kGemmN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem + tlane + (uint32_t)(c * 32), v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<uint4*>(dst + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kGemmN) : "memory");
+  }
 }
 
 // ---- small kernels ------------------------------------------------------------------------------
@@ -804,6 +925,16 @@ static Plan make_plan(int rows, int cols) {
 }
 static inline size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
 
+// wide embeddings (D > 256): K-splits of the dU = W . U_all GEMM, enough for one CTA per SM
+static int gemm_ksplit(int rows, int cols, int D) {
+  const int ctas = (rows / kTile) * (D / kGemmN);
+  int ks = ctas >= 148 ? 1 : (148 + ctas - 1) / ctas;
+  if (ks > 16) ks = 16;
+  const int kblocks = cols / kKBlock;
+  if (ks > kblocks) ks = kblocks;
+  return ks;
+}
+
 static inline int pad_rows(int rows) { return (rows + kTile - 1) / kTile * kTile; }
 
 // `rows` = the embedding rows a rank really has (any even number); its block of the gathered matrix is padded to
@@ -856,7 +987,13 @@ extern "C" int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D) {
   size_t b = 0;
   b += al256(kCounterBytes + (size_t)cols * 4);       // arrival counters + per-row loss terms
   b += al256((size_t)D * cols * 4);                   // U^T
-  b += al256((size_t)p.nsplit * rows * D * 4);        // dU partials (also covers the forward's row-sum partials)
+  size_t np = (size_t)p.nsplit;
+  if (D > 256) {                                      // wide embeddings: W is materialised, dU partials per GEMM K-split
+    np = (size_t)gemm_ksplit(rows, cols, D);
+    if (np * D < (size_t)2 * p.nsplit) np = ((size_t)2 * p.nsplit + D - 1) / D;   // forward row-sum partials [2 nsplit][rows]
+  }
+  b += al256(np * rows * D * 4);                      // dU partials (also covers the forward's row-sum partials)
+  if (D > 256) b += al256((size_t)rows * cols * 4);   // W
   return (int64_t)b;
 }
 
@@ -1005,8 +1142,8 @@ static int ntxent_bwd_impl(const float* u0, const float* u1, const float* lse0, 
   CUtensorMap map0, map1, map_ut;
   if (int rc = make_map(&map0, u0, (uint64_t)D, (uint64_t)cols, kTile)) return rc;
   if (int rc = make_map(&map1, u1 ? u1 : u0, (uint64_t)D, (uint64_t)cols, kTile)) return rc;
-  const int ds = D <= 256 ? D : 256;     // dU lives in TMEM columns 256..511: at most 256 columns per launch;
-                                         // wider embeddings recompute S once per 256-column slice
+  const int ds = D <= 256 ? D : 256;     // dU lives in TMEM columns 256..511: at most 256 columns in the fused kernel;
+                                         // wider embeddings take the W-materialised path below (256-column GEMM tiles)
   if (int rc = make_map(&map_ut, ut, (uint64_t)cols, (uint64_t)D, (uint32_t)ds)) return rc;
   const float scale = grad_scale * inv_T / (float)rows_valid;
   TileArgs a = {};
@@ -1023,21 +1160,44 @@ static int ntxent_bwd_impl(const float* u0, const float* u1, const float* lse0, 
   a.epoch_add = 0;
   a.timeout_clk = ex.timeout_clk;
   a.ctl = ctl;
-  auto* fn = &ntxent_tile_kernel<true>;
-  MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  for (int d0 = 0; d0 < D; d0 += ds) {
-    a.d0 = d0;
+  int nsum = p.nsplit;                   // partial buffers the Jacobian kernel adds up
+  if (D <= 256) {
+    auto* fn = &ntxent_tile_kernel<true, false>;
+    MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    a.d0 = 0;
     fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map0, map1, map_ut, a);
+    MIS_CUDA_TRY(cudaGetLastError());
+  } else {
+    // wide embeddings: W tiles to HBM (S computed once), then dU = W . U_all as one GEMM over all of D
+    const int ks = gemm_ksplit(rows, cols, D);
+    size_t np = (size_t)ks;
+    if (np * D < (size_t)2 * p.nsplit) np = ((size_t)2 * p.nsplit + D - 1) / D;
+    float* wbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(partial) + al256(np * rows * D * 4));
+    a.w_out = wbuf;
+    auto* fn = &ntxent_tile_kernel<true, true>;
+    MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map0, map1, map_ut, a);
+    MIS_CUDA_TRY(cudaGetLastError());
+    CUtensorMap map_w;
+    if (int rc = make_map(&map_w, wbuf, (uint64_t)cols, (uint64_t)rows, kTile)) return rc;
+    GemmArgs g = {};
+    g.rows = rows; g.D = D;
+    g.kblocks = cols / kKBlock;
+    g.kb_per_split = (g.kblocks + ks - 1) / ks;
+    g.partial = partial;
+    nsum = (g.kblocks + g.kb_per_split - 1) / g.kb_per_split;
+    MIS_CUDA_TRY(cudaFuncSetAttribute(wu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    wu_gemm_kernel<<<dim3(D / kGemmN, p.row_tiles, nsum), kGemmThreads, kSmemBytes, st>>>(map_w, map_ut, g);
     MIS_CUDA_TRY(cudaGetLastError());
   }
   {
     const int wpb = 8;
     const dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
     if (z_dtype == MIS_DTYPE_F32)
-      bwd_finalize_kernel<float><<<grid, block, 0, st>>>(partial, p.nsplit, static_cast<const float*>(z_rows), rinv_rows, D,
+      bwd_finalize_kernel<float><<<grid, block, 0, st>>>(partial, nsum, static_cast<const float*>(z_rows), rinv_rows, D,
                                                           rows, rows_valid, scale, grad_out, static_cast<float*>(dz));
     else
-      bwd_finalize_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(partial, p.nsplit, static_cast<const __nv_bfloat16*>(z_rows),
+      bwd_finalize_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(partial, nsum, static_cast<const __nv_bfloat16*>(z_rows),
                                                                   rinv_rows, D, rows, rows_valid, scale, grad_out,
                                                                   static_cast<__nv_bfloat16*>(dz));
     MIS_CUDA_TRY(cudaGetLastError());

@@ -206,8 +206,9 @@ class CudaKernels:
 
     @staticmethod
     def _n_bwd(D: int) -> int:
-        """Kernels of one backward: transpose + one tile kernel per 256-column slice of dU + the Jacobian kernel."""
-        return 2 + max(1, -(-D // 256))
+        """Kernels of one backward: transpose + tile kernel + Jacobian kernel (D <= 256: dU stays in TMEM), or transpose +
+        tile kernel writing W + the dU GEMM + Jacobian kernel (wider embeddings)."""
+        return 3 if D <= 256 else 4
 
     @staticmethod
     def _n_fwd_bwd(D: int) -> int:

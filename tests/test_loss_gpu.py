@@ -129,10 +129,12 @@ def test_ntxent_bf16_embeddings():
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 4e-3
 
 
-def test_ntxent_rank_sharded_layout_single_gpu():
-    """A.5 on one GPU: feed each simulated rank's rows with the all-gathered matrix through the ABI."""
+@pytest.mark.parametrize("W,B,D", [(3, 40, 64), (2, 100, 512), (4, 64, 768)])
+def test_ntxent_rank_sharded_layout_single_gpu(W, B, D):
+    """A.5 on one GPU: feed each simulated rank's rows with the all-gathered matrix through the ABI.  (3, 40, 64): 80
+    rows per rank, every block padded to one 128-row tile; D > 256: the backward that writes W and runs the dU GEMM,
+    with row0 != 0, padded blocks and several K-splits."""
     from medical_image_segmentation_b200.loss import CudaKernels
-    W, B, D = 3, 40, 64                        # 80 rows per rank: every block is padded to one 128-row tile
     g = torch.Generator().manual_seed(3)
     z_locals = [torch.randn(2 * B, D, generator=g) for _ in range(W)]
     ref_losses, ref_grads = L.ntxent_rank_sharded(z_locals, 0.1)
@@ -140,7 +142,7 @@ def test_ntxent_rank_sharded_layout_single_gpu():
     u_all = torch.cat([p[1] for p in preps])
     rows = 2 * B
     rp = CudaKernels.padded_rows(rows)
-    assert rp == 128 and u_all.shape[0] == W * rp
+    assert rp % 128 == 0 and u_all.shape[0] == W * rp
     scratch = CudaKernels.scratch(rows, W * rp, D, "cuda")
     outs = [CudaKernels.fwd(u_all, r * rp, rows, 10.0, scratch) for r in range(W)]
     lse_all = torch.cat([o[0] for o in outs])
