@@ -195,6 +195,16 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+            return
+        # nvidia-smi attaches to every GPU of the box while it starts (~1 s on an 8-GPU node) and that slows kernel launches
+        # of all ranks; wait for its first sample so the timed region sees only the steady 50 ms polling
+        self.first = ""
+        try:
+            import select
+            if select.select([self.proc.stdout], [], [], 15.0)[0]:
+                self.first = self.proc.stdout.readline()
+        except Exception:
+            pass
 
     def stop(self):
         if self.proc is None:
@@ -206,6 +216,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
+        out = getattr(self, "first", "") + (out or "")
         sm, smax, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in out.strip().splitlines():
@@ -367,6 +378,14 @@ def run_b200(args):
         loss.backward()
         return loss
 
+    # ---- the clock sampler runs from here to the end of the timed steps: its start-up (nvidia-smi attaches to every GPU
+    #      of the box, ~1 s) must not fall into the timed region, and the process must not sit idle right before it --------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                  # polls clocks / throttle reasons every 50 ms from here on
+    if world > 1:
+        dist.barrier()
+
     # ---- per-kernel breakdown first (it also brings clocks, allocator and exchange buffers to steady state) ---------
     bsteps = max(5, min(args.steps, 50))
     torch.manual_seed(7)
@@ -420,9 +439,6 @@ def run_b200(args):
     n_warm = max(args.warmup, 3)
     for _ in range(n_warm):
         step_device()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = CudaKernels.launches + t.launches
     ms_total = timed(step_device, args.steps)
     gpu_launches = CudaKernels.launches + t.launches - launches0      # kernels of libmis_b200.so enqueued in the timed region

@@ -298,6 +298,22 @@ int64_t mis_ema_chunks(int64_t n_elements);
 int mis_ema_update(const MisEmaEntry* table_dev, int n_tensors, int64_t total_chunks, float m, float one_minus_m,
                    void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Weighted kNN prediction of the online evaluator -- KNNOnlineEvaluator.predict (train/callback/knn.py:38-70):
+ * sim = query . bank^T (tcgen05 TF32 GEMM over hi/lo-split operands: fp32-grade similarities, fp32 accumulate) ->
+ * the k most similar bank rows per query (exact radix
+ * select; ties at the k-th similarity go to the lower bank index) -> votes exp(sim / T) summed per class ->
+ * pred_labels[b, :] = the classes by descending score (equal scores: ascending class), what `argsort(descending=True)`
+ * returns up to the order of equal scores.  pred_scores ([n_query, num_classes], may be NULL) receives the scores.
+ * query [n_query, D], bank [n_bank, D]: fp32 row-major, 16-byte aligned, L2-normalised by the caller (knn.py:100,129);
+ * bank_labels [n_bank] int64; D a multiple of 32; 1 <= k <= min(n_bank, 1024); num_classes <= 8192.
+ * scratch: mis_knn_scratch_bytes(n_query, n_bank, D) bytes (the padded similarity matrix and the split operands).
+ * ------------------------------------------------------------------------------------------ */
+int64_t mis_knn_scratch_bytes(int n_query, int n_bank, int D);
+int mis_knn_predict(const float* query, const float* bank, const int64_t* bank_labels, int n_query, int n_bank, int D,
+                    int k, float inv_T, int num_classes, int64_t* pred_labels, float* pred_scores, void* scratch,
+                    int64_t scratch_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Exact per-channel moments of uint16 slices: the statistics behind the normalisation constants.
  * Replaces the float64 streaming sums of compute_mean_and_std

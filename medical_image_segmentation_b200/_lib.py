@@ -67,6 +67,9 @@ EXPORTS = {
                                      C.c_void_p, C.c_int64, C.c_void_p]),
     "mis_ema_chunks": (C.c_int64, [C.c_int64]),
     "mis_ema_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
+    "mis_knn_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "mis_knn_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "mis_u16_moments": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "mis_byol_loss_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),

@@ -979,6 +979,31 @@ using namespace mis::ntx;
 
 extern "C" int mis_ntxent_padded_rows(int rows) { return rows <= 0 ? 0 : pad_rows(rows); }
 
+// out[pad128(M), pad256(N)] = A[M, K] . B[N, K]^T (fp32 containers, TF32 MMA, fp32 accumulate) with wu_gemm_kernel;
+// rows / columns beyond M / N are read as zeros by TMA and come out as zeros.  Used by the kNN evaluator (knn.cu).
+namespace mis {
+int launch_gemm_tf32_nt(const float* A, int M, const float* B, int N, int K, float* out, cudaStream_t st) {
+  MIS_REQUIRE(A && B && out && M > 0 && N > 0 && K >= kKBlock && K % kKBlock == 0, MIS_ERR_INVALID_ARG,
+              "gemm_tf32_nt: bad arguments (M %d N %d K %d)", M, N, K);
+  MIS_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+              MIS_ERR_INVALID_ARG, "gemm_tf32_nt: operands must be 16-byte aligned");
+  const int Mp = pad_rows(M), Np = (N + kGemmN - 1) / kGemmN * kGemmN;
+  MIS_REQUIRE(Mp / kTile <= 65535, MIS_ERR_UNSUPPORTED, "gemm_tf32_nt: at most %d rows per call", 65535 * kTile);
+  CUtensorMap map_a, map_b;
+  if (int rc = make_map(&map_a, A, (uint64_t)K, (uint64_t)M, kTile)) return rc;
+  if (int rc = make_map(&map_b, B, (uint64_t)K, (uint64_t)N, kGemmN)) return rc;
+  GemmArgs g = {};
+  g.rows = Mp; g.D = Np;
+  g.kblocks = K / kKBlock;
+  g.kb_per_split = g.kblocks;
+  g.partial = out;
+  MIS_CUDA_TRY(cudaFuncSetAttribute(wu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  wu_gemm_kernel<<<dim3(Np / kGemmN, Mp / kTile, 1), kGemmThreads, kSmemBytes, st>>>(map_a, map_b, g);
+  MIS_CUDA_TRY(cudaGetLastError());
+  return MIS_OK;
+}
+}  // namespace mis
+
 extern "C" int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D) {
   if (rows <= 0 || cols <= 0 || D <= 0) return -1;
   rows = pad_rows(rows);
