@@ -70,6 +70,16 @@ def main():
             for v, u in raw(rep):
                 f.write(f"## {v.get('Kernel Name', '')[:90]}\n\n")
                 table(f, v, u)
+    rep = os.path.join(G, f"ntxent_{tag}_wide.ncu-rep")
+    if os.path.exists(rep):
+        with open(os.path.join(OUT, f"{tag}_ntxent_wide_ncu.md"), "w") as f:
+            f.write(f"# NT-Xent with wide embeddings, build of {tag}: `ncu --set full --clock-control none`\n\n"
+                    "Command: `python scripts/prof_loss.py 8192 2048 1` (2N = 16384 rows, D = 2048, one rank -- the per-GPU shape of "
+                    "cfg4 on two GPUs is 16384 x 32768; forward = ntxent_tile_kernel<0, 0>, backward = ntxent_tile_kernel<1, 1> "
+                    "writing W + wu_gemm_kernel computing dU = W . U_all).\n\n")
+            for v, u in raw(rep):
+                f.write(f"## {v.get('Kernel Name', '')[:90]}\n\n")
+                table(f, v, u)
     lst = os.path.join(G, f"launches_{tag}.csv")
     if os.path.exists(lst):
         rows = [r for r in csv.reader(open(lst)) if len(r) > 10 and r[0].isdigit()]
