@@ -147,6 +147,15 @@ int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H, int W, int
                      int use_tma, void* stream);
 
 /* The variant mis_aug_two_view runs for this shape and selector: 0 strip, 3 warp-tile, 1 TMA band, 2 cp.async band. */
+/* mis_aug_two_view with an explicit launch order: CTA b of the kernel works on view view_order[b] (a permutation of
+ * 0..n_views-1 in device memory; NULL = identity).  The output does not depend on it; mis_view_cost_order (host) returns
+ * the most-expensive-first order that lets the SMs drain together.  Honoured by kernel variant 0, ignored by the others. */
+int mis_aug_two_view_ordered(const uint16_t* src, int n_images, int C, int H, int W, int64_t img_stride,
+                             const MisViewParams* params, int n_views, const int32_t* view_order, float win_lo,
+                             float win_hi, const float* mean, const float* std, void* out, int s, int out_dtype,
+                             int use_tma, void* stream);
+int mis_view_cost_order(const MisViewParams* params_host, int n_views, int32_t* order_host);
+
 int mis_aug_kernel_variant(int C, int H, int W, int64_t img_stride, int s, int use_tma);
 
 /* GaussianBlur(23) + RandomSolarize(128) + Normalize for the views whose record carries MIS_VIEW_BLUR

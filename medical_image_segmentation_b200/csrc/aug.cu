@@ -1057,6 +1057,14 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
                                 const MisViewParams* params, int n_views, float win_lo, float win_hi,
                                 const float* mean, const float* std, void* out, int s, int out_dtype, int use_tma,
                                 void* stream) {
+  return mis_aug_two_view_ordered(src, n_images, C, H, W, img_stride, params, n_views, nullptr, win_lo, win_hi, mean, std,
+                                  out, s, out_dtype, use_tma, stream);
+}
+
+extern "C" int mis_aug_two_view_ordered(const uint16_t* src, int n_images, int C, int H, int W, int64_t img_stride,
+                                        const MisViewParams* params, int n_views, const int32_t* view_order, float win_lo,
+                                        float win_hi, const float* mean, const float* std, void* out, int s,
+                                        int out_dtype, int use_tma, void* stream) {
   using namespace mis::aug;
   MIS_REQUIRE(src && params && mean && std && out, MIS_ERR_INVALID_ARG, "mis_aug_two_view: null pointer");
   MIS_REQUIRE(n_images > 0 && n_views >= 0 && H > 0 && W > 0, MIS_ERR_INVALID_ARG,
@@ -1090,6 +1098,7 @@ extern "C" int mis_aug_two_view(const uint16_t* src, int n_images, int C, int H,
     t.H = H;
     t.W = W;
     t.params = params;
+    t.order = view_order;
     t.win_lo = win_lo;
     t.win_scale = 1.0f / (win_hi - win_lo);
     for (int c = 0; c < C; ++c) {

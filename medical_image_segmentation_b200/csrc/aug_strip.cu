@@ -515,9 +515,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) aug_strip_kernel(cons
   const int nwarps = nthreads >> 5;
   const int sy = warp / a.nsx;
   const int sx = warp - sy * a.nsx;
-  const int plane = blockIdx.x;                 // view * C + c
-  const int view = a.C == 1 ? plane : plane / a.C;
-  const int chan = plane - view * a.C;
+  const int vb = a.C == 1 ? (int)blockIdx.x : (int)blockIdx.x / a.C;
+  const int chan = (int)blockIdx.x - vb * a.C;
+  const int view = a.order ? a.order[vb] : vb;   // most expensive views first (mis_view_cost_order)
+  const int plane = view * a.C + chan;
   const int s = a.s;
   Misc& misc = *reinterpret_cast<Misc*>(smem + a.off_misc);
   float4* const sched = reinterpret_cast<float4*>(smem + a.off_sched);

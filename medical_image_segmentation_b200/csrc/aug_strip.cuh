@@ -14,6 +14,7 @@ struct StripArgs {
   int64_t img_stride;
   int C, H, W;
   const MisViewParams* params;
+  const int32_t* order;    // launch order (CTA b works on view order[b]) or null
   float win_lo, win_scale;
   float mean[4], inv_std[4];
   void* out;

@@ -80,6 +80,8 @@ struct TileArgs {
   int rows_valid;            // embedding rows a rank really has; rows [rows_valid, rows) of every rank's block are padding:
                              // masked as columns, skipped as rows
   int col_tiles, tiles_per_split;
+  int split_fast;          // 1: grid = (splits, row tiles) -- the column splits of a row tile are co-scheduled, so fewer row
+                           // tiles are live at a time (wide embeddings: their streamed operands then stay inside the L2)
   float k1;                // log2(e) / T
   int d0, ds;              // backward: columns [d0, d0 + ds) of dU are produced by this launch (ds <= 256)
   const float* lse[2];     // per parity: [cols] all-gathered log-sum-exp (backward): c_j = exp(1/T - lse_j) on the fly
@@ -239,7 +241,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap map_u0, const __grid_cons
   uint8_t* const ring = smem + (res_a ? 64 * 1024 : 0);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row_tile = blockIdx.x, split = blockIdx.y;
+  const int row_tile = a.split_fast ? blockIdx.y : blockIdx.x, split = a.split_fast ? blockIdx.x : blockIdx.y;
   const int t_begin = split * a.tiles_per_split;
   const int T = min(a.tiles_per_split, a.col_tiles - t_begin);
   const int KB = a.D / kKBlock;
@@ -912,12 +914,18 @@ static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_
 struct Plan {
   int row_tiles, col_tiles, tiles_per_split, nsplit;
 };
-static Plan make_plan(int rows, int cols) {
+static Plan make_plan(int rows, int cols, int D) {
   Plan p;
   p.row_tiles = rows / kTile;
   p.col_tiles = cols / kTile;
   int target = 148 / p.row_tiles;
   if (target < 1) target = 1;
+  // wide embeddings stream the row tile as well (128 x D x 4 bytes per column tile): keep the row tiles that are live at
+  // once (148 / splits of them) within ~40 MB so that they and the column tiles they share stay in the L2
+  if (D > 256) {
+    const int need = (int)((148.0 * kTile * D * 4 + 40e6 - 1) / 40e6);
+    if (target < need) target = need;
+  }
   if (target > p.col_tiles) target = p.col_tiles;
   p.tiles_per_split = (p.col_tiles + target - 1) / target;
   p.nsplit = (p.col_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
@@ -1008,7 +1016,7 @@ extern "C" int64_t mis_ntxent_scratch_bytes(int rows, int cols, int D) {
   if (rows <= 0 || cols <= 0 || D <= 0) return -1;
   rows = pad_rows(rows);
   cols = pad_rows(cols);
-  const Plan p = make_plan(rows, cols);
+  const Plan p = make_plan(rows, cols, D);
   size_t b = 0;
   b += al256(kCounterBytes + (size_t)cols * 4);       // arrival counters + per-row loss terms
   b += al256((size_t)D * cols * 4);                   // U^T
@@ -1080,7 +1088,7 @@ static int ntxent_fwd_impl(const float* u0, const float* u1, int cols, int D, in
               (long long)mis_ntxent_scratch_bytes(rows, cols, D));
   const int rows_valid = rows;
   rows = pad_rows(rows);
-  const Plan p = make_plan(rows, cols);
+  const Plan p = make_plan(rows, cols, D);
   uint8_t* sc = static_cast<uint8_t*>(scratch);
   float* partial = reinterpret_cast<float*>(sc + al256(kCounterBytes + (size_t)cols * 4) + al256((size_t)D * cols * 4));
 
@@ -1103,7 +1111,8 @@ static int ntxent_fwd_impl(const float* u0, const float* u1, int cols, int D, in
   }
   auto* fn = &ntxent_tile_kernel<false>;
   MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map0, map1, map0, a);
+  a.split_fast = D > 256;
+  fn<<<a.split_fast ? dim3(p.nsplit, p.row_tiles) : dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map0, map1, map0, a);
   MIS_CUDA_TRY(cudaGetLastError());
 
   RowsArgs ra = {};
@@ -1155,7 +1164,7 @@ static int ntxent_bwd_impl(const float* u0, const float* u1, const float* lse0, 
               (long long)mis_ntxent_scratch_bytes(rows, cols, D));
   const int rows_valid = rows;
   rows = pad_rows(rows);
-  const Plan p = make_plan(rows, cols);
+  const Plan p = make_plan(rows, cols, D);
   uint8_t* sc = static_cast<uint8_t*>(scratch);
   float* ut = reinterpret_cast<float*>(sc + al256(kCounterBytes + (size_t)cols * 4));
   float* partial = reinterpret_cast<float*>(sc + al256(kCounterBytes + (size_t)cols * 4) + al256((size_t)D * cols * 4));
@@ -1199,9 +1208,10 @@ static int ntxent_bwd_impl(const float* u0, const float* u1, const float* lse0, 
     if (np * D < (size_t)2 * p.nsplit) np = ((size_t)2 * p.nsplit + D - 1) / D;
     float* wbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(partial) + al256(np * rows * D * 4));
     a.w_out = wbuf;
+    a.split_fast = 1;
     auto* fn = &ntxent_tile_kernel<true, true>;
     MIS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    fn<<<dim3(p.row_tiles, p.nsplit), kThreads, kSmemBytes, st>>>(map0, map1, map_ut, a);
+    fn<<<dim3(p.nsplit, p.row_tiles), kThreads, kSmemBytes, st>>>(map0, map1, map_ut, a);
     MIS_CUDA_TRY(cudaGetLastError());
     CUtensorMap map_w;
     if (int rc = make_map(&map_w, wbuf, (uint64_t)cols, (uint64_t)rows, kTile)) return rc;

@@ -196,19 +196,19 @@ class FusedTwoViewTransforms:
         else:
             assert out.is_cuda and out.is_contiguous() and out.dtype == self.out_dtype
             assert tuple(out.shape) == (n_views, Cc, s, s)
-        dev = self._stage_params(params_view_major, x.device)
+        params_dev, order_dev, _keep = self._stage_params(params_view_major, x.device, with_order=True)
         with _on_device(x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
-            rc = _lib.lib.mis_aug_two_view(
-                x.data_ptr(), B, Cc, H, W, Cc * H * W, dev.data_ptr(), n_views,
+            rc = _lib.lib.mis_aug_two_view_ordered(
+                x.data_ptr(), B, Cc, H, W, Cc * H * W, params_dev, n_views, order_dev,
                 self.window[0], self.window[1], mean_c, std_c,
                 out.data_ptr(), s, MIS_DTYPE_F32 if self.out_dtype == torch.float32 else MIS_DTYPE_BF16,
                 self.use_tma, C.c_void_p(stream))
-            _lib.check(rc, "mis_aug_two_view")
+            _lib.check(rc, "mis_aug_two_view_ordered")
             self.launches += 1
             if extra & MIS_VIEW_BLUR:      # GaussianBlur(23) -> solarize -> normalise for the views that drew a blur
                 rc = _lib.lib.mis_aug_blur_views(
-                    out.data_ptr(), MIS_DTYPE_F32 if self.out_dtype == torch.float32 else MIS_DTYPE_BF16, dev.data_ptr(),
+                    out.data_ptr(), MIS_DTYPE_F32 if self.out_dtype == torch.float32 else MIS_DTYPE_BF16, params_dev,
                     n_views, Cc, s, mean_c, std_c, C.c_void_p(stream))
                 _lib.check(rc, "mis_aug_blur_views")
                 self.launches += 1
@@ -241,9 +241,13 @@ class FusedTwoViewTransforms:
                              f"{int(r['top'])}, left {int(r['left'])}, h {int(r['h'])}, w {int(r['w'])}) in {H}x{W}")
         return int(flags.value)
 
-    def _stage_params(self, params: np.ndarray, device) -> torch.Tensor:
-        """Copy the table through one of three persistent pinned buffers (no per-call cudaHostAlloc)."""
-        nbytes = params.nbytes
+    def _stage_params(self, params: np.ndarray, device, with_order: bool = False):
+        """Copy the table (and, with ``with_order``, the most-expensive-first launch order of its views, computed
+        straight into the pinned buffer) through one of three persistent pinned buffers: one H2D copy per call, no
+        per-call cudaHostAlloc.  Returns (device table pointer, device order pointer or None, keep-alive tensor)."""
+        rec_bytes = params.nbytes
+        n = params.shape[0]
+        nbytes = rec_bytes + (4 * n if with_order else 0)
         if len(self._staging) < 3:
             slot = [None, None, torch.cuda.Event(), None]
             self._staging.append(slot)
@@ -256,10 +260,12 @@ class FusedTwoViewTransforms:
             slot[1] = torch.empty(nbytes, dtype=torch.uint8, device=device)
             slot[3] = slot[0].numpy()
         host, dev, ev, host_np = slot
-        host_np[:] = params.view(np.uint8).reshape(-1)
+        host_np[:rec_bytes] = params.view(np.uint8).reshape(-1)
+        if with_order:
+            _lib.check(_lib.lib.mis_view_cost_order(host.data_ptr(), n, host.data_ptr() + rec_bytes), "mis_view_cost_order")
         dev.copy_(host, non_blocking=True)
         ev.record(torch.cuda.current_stream(device))
-        return dev
+        return dev.data_ptr(), (dev.data_ptr() + rec_bytes if with_order else None), dev
 
     def stage_needed_rows(self, x_host: torch.Tensor, params: np.ndarray, device=None,
                           min_gap_bytes: int = 256 << 10) -> torch.Tensor:

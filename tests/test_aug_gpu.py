@@ -464,3 +464,25 @@ def test_host_batch_stages_only_the_rows_the_crops_read():
     tb(xh)
     assert torch.equal(ta.views_buffer, tb.views_buffer)
     assert want <= tb.last_h2d_bytes <= full
+
+
+def test_launch_order_does_not_change_the_output():
+    """apply() launches the views most-expensive-first (mis_view_cost_order); the plain ABI call launches them in table
+    order: same bytes."""
+    import ctypes as C
+    from medical_image_segmentation_b200 import _lib
+    imgs = synth.batch_512(8, seed=21)
+    t = _mk(224)
+    torch.manual_seed(11)
+    p = t.to_view_major(t.draw_params(8, 512, 512))
+    x = torch.from_numpy(imgs).cuda()
+    got = t.apply(x, p).clone()
+    dev = torch.from_numpy(np.ascontiguousarray(p).view(np.uint8).copy()).cuda()
+    out = torch.zeros_like(got)
+    mean, std = (C.c_float * 1)(t.mean[0]), (C.c_float * 1)(t.std[0])
+    rc = _lib.lib.mis_aug_two_view(x.data_ptr(), 8, 1, 512, 512, 512 * 512, dev.data_ptr(), 16, 0.0, 65535.0,
+                                   C.cast(mean, C.c_void_p), C.cast(std, C.c_void_p), out.data_ptr(), 224, 0, 0,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(got.view(torch.int16), out.view(torch.int16))

@@ -169,3 +169,22 @@ def test_ffcv_flavour_parameter_records():
     for k in ("img", "top", "left", "h", "w"):
         assert np.array_equal(a[k], b[k])
     assert np.array_equal(a["flags"] & 1, b["flags"] & 1) and np.array_equal(a["flags"] & 16, b["flags"] & 16)
+
+
+def test_view_cost_order_is_a_stable_descending_permutation():
+    """mis_view_cost_order: most expensive (largest crop area) views first, ties in table order."""
+    import ctypes as C
+    from medical_image_segmentation_b200 import FusedTwoViewTransforms, _lib
+    t = FusedTwoViewTransforms(64, (0.2,), (0.2,))
+    torch.manual_seed(4)
+    p = np.ascontiguousarray(t.to_view_major(t.draw_params(300, 512, 512)))
+    order = np.empty(p.shape[0], np.int32)
+    assert _lib.lib.mis_view_cost_order(p.ctypes.data, p.shape[0], order.ctypes.data) == 0
+    assert np.array_equal(np.sort(order), np.arange(p.shape[0]))
+    area = p["h"].astype(np.int64) * p["w"]
+    bucket = 1023 - area * 1023 // area.max()
+    b = bucket[order]
+    assert (np.diff(b) >= 0).all()                                   # non-increasing area at the sort's resolution
+    same = np.diff(b) == 0
+    assert (np.diff(order)[same] > 0).all()                          # stable inside a bucket
+    assert _lib.lib.mis_view_cost_order(None, 0, None) == 0
