@@ -92,6 +92,14 @@ int mis_draw_two_view_params(uint8_t* rng_state, int64_t rng_state_len, int n_im
                              int H, int W, const float* blur_prob, const float* solarize_prob,
                              MisViewParams* out, int* n_done);
 
+/* The same draw with a callback for the one value this library cannot restate bit for bit: when a crop box depends on
+ * the last bit of the reference's float32 torch.exp, exp_f32(x, exp_ctx) is asked for it (the caller evaluates torch.exp
+ * on a one-element float32 tensor, exactly the reference's call, v2/_geometry.py:284) and the draw carries on -- *n_done
+ * is then always n_images.  exp_f32 == NULL gives the hand-back protocol of mis_draw_two_view_params. */
+int mis_draw_two_view_params_cb(uint8_t* rng_state, int64_t rng_state_len, int n_images, int img0,
+                                int H, int W, const float* blur_prob, const float* solarize_prob,
+                                MisViewParams* out, int* n_done, float (*exp_f32)(float, void*), void* exp_ctx);
+
 /* Reorders the records of mis_draw_two_view_params from image-major [2*i + v] to view-major [v*n_images + i], the row
  * order of torch.cat([view1, view2]) (byol_pytorch.py:207) that mis_aug_two_view's output planes follow.  Host only. */
 int mis_params_to_view_major(const MisViewParams* in, int n_images, MisViewParams* out);
@@ -165,7 +173,7 @@ int mis_aug_kernel_variant(int C, int H, int W, int64_t img_stride, int s, int u
  * post-colour image of such a view as uint16 (round(x*65535)) in the first 2*s*s bytes of the view's output plane and
  * this call finishes those planes in place; other views are not touched.  Call it right after mis_aug_two_view on the
  * same stream with the same `out`, params, C, s, out_dtype, mean, std whenever a record has MIS_VIEW_BLUR.
- * s a multiple of 8 in [16, 224]. */
+ * s a multiple of 8 in [16, 256] (above 224 the plane is processed as two bands of 128 output rows). */
 int mis_aug_blur_views(void* out, int out_dtype, const MisViewParams* params, int n_views, int C, int s,
                        const float* mean, const float* std, void* stream);
 

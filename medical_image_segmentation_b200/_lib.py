@@ -34,6 +34,8 @@ EXPORTS = {
     "mis_last_error": (C.c_char_p, []),
     "mis_draw_two_view_params": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mis_draw_two_view_params_cb": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mis_params_to_view_major": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "mis_view_params_check": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32),
                                         C.POINTER(C.c_int)]),

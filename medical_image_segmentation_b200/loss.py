@@ -357,8 +357,9 @@ class _NTXent(torch.autograd.Function):
         if ctx.meta is None:
             (dz,) = ctx.saved_tensors
             out = dz * grad_out.to(dz.dtype)
-            if ctx.holder is not None:
+            if ctx.holder is not None:                   # the captured graph's static dz is free again (once per result)
                 ctx.holder.in_flight -= 1
+                ctx.holder = None
             return out, None, None, None
         z, u_all, rinv, lse = ctx.saved_tensors
         inv_T, group, distributed, rank, kernels, scratch = ctx.meta

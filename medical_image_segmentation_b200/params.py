@@ -90,6 +90,14 @@ def draw_two_view_params_torch(n_images: int, H: int, W: int, blur_prob=(0.0, 0.
     return out
 
 
+@C.CFUNCTYPE(C.c_float, C.c_float, C.c_void_p)
+def _torch_exp_f32(x, _ctx):
+    """torch.exp on a one-element float32 tensor: the reference's own evaluation of the aspect ratio
+    (torchvision v2/_geometry.py:284).  Called by the native replay for the rare draw whose crop box depends on its last
+    bit (SLEEF's vector expf and libm's differ there)."""
+    return float(torch.exp(torch.tensor([x], dtype=torch.float32))[0])
+
+
 def draw_two_view_params(n_images: int, H: int, W: int, blur_prob=(0.0, 0.0), solarize_prob=(0.0, 0.0),
                          out: np.ndarray | None = None, generator: torch.Generator | None = None) -> np.ndarray:
     """2*n_images records (image-major: [2*i+v]) drawn from torch's global CPU generator, or from ``generator`` (a
@@ -106,13 +114,14 @@ def draw_two_view_params(n_images: int, H: int, W: int, blur_prob=(0.0, 0.0), so
     blob = state.numpy()
     done = 0
     while done < n_images:
-        rc = _lib.lib.mis_draw_two_view_params(blob.ctypes.data, blob.nbytes, n_images - done, done, H, W,
-                                               C.cast(bp, C.c_void_p), C.cast(sp, C.c_void_p),
-                                               out[2 * done:].ctypes.data, C.byref(n_done))
-        _lib.check(rc, "mis_draw_two_view_params")
+        rc = _lib.lib.mis_draw_two_view_params_cb(blob.ctypes.data, blob.nbytes, n_images - done, done, H, W,
+                                                  C.cast(bp, C.c_void_p), C.cast(sp, C.c_void_p),
+                                                  out[2 * done:].ctypes.data, C.byref(n_done),
+                                                  C.cast(_torch_exp_f32, C.c_void_p), None)
+        _lib.check(rc, "mis_draw_two_view_params_cb")
         done += n_done.value
         if done < n_images:
-            # this image's crop box depends on the last bit of torch.exp: let torch draw it
+            # (only without the callback) this image's crop box depends on the last bit of torch.exp: let torch draw it
             set_state(state)
             out[2 * done:2 * done + 2] = draw_two_view_params_torch(1, H, W, blur_prob, solarize_prob, img0=done,
                                                                     generator=generator)

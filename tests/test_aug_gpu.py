@@ -294,6 +294,27 @@ def test_three_channel_batch_matches_oracle():
     assert (o[:, 0] - o[:, 1]).abs().max().item() <= 2e-4 and (o[:, 0] - o[:, 2]).abs().max().item() <= 2e-4
 
 
+@pytest.mark.parametrize("crop", [256, 232])
+def test_blur_above_224_runs_in_two_bands(crop):
+    """Crops whose fp32 plane exceeds one SM's shared memory are blurred as two 128-row bands, in place: every pixel
+    against the oracle, bf16 == round(fp32)."""
+    imgs = synth.batch_512(3, seed=31)
+    x = torch.from_numpy(imgs).cuda()
+    from medical_image_segmentation_b200.transforms import FusedTwoViewTransforms
+    tf = FusedTwoViewTransforms(crop, (MEAN,), (STD,), blur_prob=(1.0, 1.0), solarize_prob=(0.0, 0.5), out_dtype=torch.float32)
+    tb = FusedTwoViewTransforms(crop, (MEAN,), (STD,), blur_prob=(1.0, 1.0), solarize_prob=(0.0, 0.5))
+    torch.manual_seed(5)
+    tf(x)
+    torch.manual_seed(5)
+    tb(x)
+    assert torch.equal(tf.views_buffer.to(torch.bfloat16), tb.views_buffer)
+    out, p = tf.views_buffer.cpu().numpy(), tf.last_params
+    assert all(int(r["flags"]) & 8 for r in p)
+    for i in range(3):
+        for v in range(2):
+            _check_view(out[v * 3 + i, 0], imgs[i], p[2 * i + v], crop, f"two-band blur img {i} view {v}")
+
+
 def test_solarize_and_blur_flags_on_hand_made_records():
     """Every combination of flip / jitter order / blur / solarize on one slice, against the oracle (the solarize
     threshold is the reference's 128 on the 0..255 scale = 128/255 here)."""

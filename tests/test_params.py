@@ -74,26 +74,62 @@ def test_view_major_reorder():
     assert list(q["top"]) == [0, 2, 4, 1, 3, 5]
 
 
-def test_handback_images_are_drawn_by_torch_and_stay_bit_exact(monkeypatch):
-    """~2.6e-4 of the images have a crop box within rounding distance of a .5 boundary; the native code hands
-    them back and torch draws them.  Check the path fires and that the stream stays aligned afterwards."""
+def _handback_draw(n_images, H, W):
+    """The hand-back protocol of mis_draw_two_view_params (no callback): native until an image's box depends on the
+    last bit of torch.exp, that image by the pure-torch replay, then native again.  Returns (records, handed-back images)."""
+    import ctypes as C
+    from medical_image_segmentation_b200 import _lib
+    out = np.zeros(2 * n_images, VIEW_PARAMS_DTYPE)
+    zero = (C.c_float * 2)(0.0, 0.0)
+    n_done = C.c_int(0)
+    state = torch.get_rng_state()
+    blob = state.numpy()
+    done, handed = 0, []
+    while done < n_images:
+        rc = _lib.lib.mis_draw_two_view_params(blob.ctypes.data, blob.nbytes, n_images - done, done, H, W,
+                                               C.cast(zero, C.c_void_p), C.cast(zero, C.c_void_p),
+                                               out[2 * done:].ctypes.data, C.byref(n_done))
+        assert rc == 0
+        done += n_done.value
+        if done < n_images:
+            torch.set_rng_state(state)
+            out[2 * done:2 * done + 2] = P.draw_two_view_params_torch(1, H, W, img0=done)
+            handed.append(done)
+            state = torch.get_rng_state()
+            blob = state.numpy()
+            done += 1
+    torch.set_rng_state(state)
+    return out, handed
+
+
+def test_exp_sensitive_images_stay_bit_exact(monkeypatch):
+    """~2.6e-4 of the images have a crop box within rounding distance of a .5 boundary, where the last bit of the
+    reference's float32 torch.exp decides.  Two protocols: the product path asks torch for that one value through a
+    callback and never leaves native code; the plain ABI call hands the image back and torch draws it.  Both must give
+    the records of the pure-torch replay and leave the stream aligned."""
     calls = []
-    orig = P.draw_two_view_params_torch
+    real = P._torch_exp_f32
 
-    def counting(*a, **k):
-        calls.append(k.get("img0"))
-        return orig(*a, **k)
-
-    monkeypatch.setattr(P, "draw_two_view_params_torch", counting)
     torch.manual_seed(123)
-    p = P.draw_two_view_params(30000, 512, 512)
-    assert len(calls) >= 1
-    i = calls[0]
+    legacy, handed = _handback_draw(30000, 512, 512)
+    after_legacy = torch.rand(3)
+    assert len(handed) >= 1
     torch.manual_seed(123)
-    P.draw_two_view_params(i, 512, 512)          # no hand-back before image i by construction
-    ref = orig(3, 512, 512, img0=i)              # pure torch replay of image i and its two successors
+    p = P.draw_two_view_params(30000, 512, 512)                    # callback protocol
+    assert torch.equal(after_legacy, torch.rand(3))
+    assert p.tobytes() == legacy.tobytes()
+    i = handed[0]
+    torch.manual_seed(123)
+    P.draw_two_view_params(i, 512, 512)          # position the stream at image i
+    ref = P.draw_two_view_params_torch(3, 512, 512, img0=i)        # pure torch replay of image i and its two successors
     for name in VIEW_PARAMS_DTYPE.names:
         assert np.array_equal(ref[name], p[name][2 * i:2 * i + 6]), name
+    # a rewind across a generator refill (624 words): hand-backs at every position of the state array
+    for seed in range(40):
+        torch.manual_seed(1000 + seed)
+        a, _ = _handback_draw(4000, 512, 512)
+        torch.manual_seed(1000 + seed)
+        assert P.draw_two_view_params(4000, 512, 512).tobytes() == a.tobytes(), seed
 
 
 def test_resize_jitter_params_match_torchvision_colorjitter():
