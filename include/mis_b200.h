@@ -164,6 +164,17 @@ int mis_aug_two_view_ordered(const uint16_t* src, int n_images, int C, int H, in
                              int use_tma, void* stream);
 int mis_view_cost_order(const MisViewParams* params_host, int n_views, int32_t* order_host);
 
+/* The whole host side of one batch in one call: mis_view_params_check on the host table -> table + launch order into
+ * the caller's pinned block (>= n_views * (sizeof(MisViewParams) + 4) bytes) -> one cudaMemcpyAsync to `staging_dev` ->
+ * mis_aug_two_view_ordered -> mis_aug_blur_views when a record carries MIS_VIEW_BLUR.  *bad_index >= 0 (and nothing
+ * launched) when a record is invalid; *n_launches = kernels enqueued.  The caller must not reuse the pinned block
+ * before the copy has completed (record an event on `stream` after the call). */
+int mis_aug_two_view_staged(const uint16_t* src, int n_images, int C, int H, int W, int64_t img_stride,
+                            const MisViewParams* params_host, int n_views, void* staging_pinned, void* staging_dev,
+                            int64_t staging_bytes, float win_lo, float win_hi, const float* mean, const float* std,
+                            void* out, int s, int out_dtype, int use_tma, uint32_t* flags_or, int* bad_index,
+                            int* n_launches, void* stream);
+
 int mis_aug_kernel_variant(int C, int H, int W, int64_t img_stride, int s, int use_tma);
 
 /* GaussianBlur(23) + RandomSolarize(128) + Normalize for the views whose record carries MIS_VIEW_BLUR

@@ -44,6 +44,8 @@ int launch_rgb_color(void* out, int out_f32, const MisViewParams* params, int n_
 }  // namespace mis
 
 #include "aug_tile.cuh"
+#include <cstring>
+
 #include "common.cuh"
 
 namespace mis {
@@ -1226,4 +1228,42 @@ extern "C" int64_t mis_aug_algorithmic_bytes(const MisViewParams* p, int n_views
   int64_t total = 0;
   for (int v = 0; v < n_views; ++v) total += 2 * (int64_t)C * p[v].h * p[v].w + ob * C * s * s;
   return total;
+}
+
+// One host round trip per batch: check the table, copy it and its launch order into the caller's pinned block, one H2D
+// copy, K1, and the blur kernel when a record asks for it (the Python side of a step is as long as its GPU side at small
+// per-GPU batches, so every separate ctypes / torch call counts).
+extern "C" int mis_aug_two_view_staged(const uint16_t* src, int n_images, int C, int H, int W, int64_t img_stride,
+                                       const MisViewParams* params_host, int n_views, void* staging_pinned,
+                                       void* staging_dev, int64_t staging_bytes, float win_lo, float win_hi,
+                                       const float* mean, const float* std, void* out, int s, int out_dtype, int use_tma,
+                                       uint32_t* flags_or, int* bad_index, int* n_launches, void* stream) {
+  MIS_REQUIRE((params_host || n_views == 0) && staging_pinned && staging_dev && flags_or && bad_index && n_launches,
+              MIS_ERR_INVALID_ARG, "mis_aug_two_view_staged: null pointer");
+  MIS_REQUIRE(n_views >= 0 && staging_bytes >= (int64_t)n_views * (int64_t)(sizeof(MisViewParams) + 4), MIS_ERR_INVALID_ARG,
+              "mis_aug_two_view_staged: staging block of %lld bytes for %d views", (long long)staging_bytes, n_views);
+  *n_launches = 0;
+  if (int rc = mis_view_params_check(params_host, n_views, n_images, H, W, flags_or, bad_index)) return rc;
+  if (*bad_index >= 0 || n_views == 0) return MIS_OK;          // the caller reports the offending record
+  const uint32_t extra = *flags_or & (MIS_VIEW_BLUR | MIS_VIEW_SOLARIZE);
+  MIS_REQUIRE(!extra || mis_aug_kernel_variant(C, H, W, img_stride, s, use_tma) == 0, MIS_ERR_UNSUPPORTED,
+              "GaussianBlur / RandomSolarize are fused into the strip kernel only (use_tma=0, 8 <= crop <= 256, at most "
+              "5.5x downscaling); this call would run K1 variant %d", mis_aug_kernel_variant(C, H, W, img_stride, s, use_tma));
+  const size_t rec_bytes = (size_t)n_views * sizeof(MisViewParams);
+  uint8_t* hp = static_cast<uint8_t*>(staging_pinned);
+  memcpy(hp, params_host, rec_bytes);
+  if (int rc = mis_view_cost_order(params_host, n_views, reinterpret_cast<int32_t*>(hp + rec_bytes))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MIS_CUDA_TRY(cudaMemcpyAsync(staging_dev, staging_pinned, rec_bytes + (size_t)n_views * 4, cudaMemcpyHostToDevice, st));
+  const MisViewParams* pd = static_cast<const MisViewParams*>(staging_dev);
+  const int32_t* od = reinterpret_cast<const int32_t*>(static_cast<const uint8_t*>(staging_dev) + rec_bytes);
+  if (int rc = mis_aug_two_view_ordered(src, n_images, C, H, W, img_stride, pd, n_views, od, win_lo, win_hi, mean, std, out,
+                                        s, out_dtype, use_tma, stream))
+    return rc;
+  *n_launches = 1 + (C == 3 ? 1 : 0);
+  if (*flags_or & MIS_VIEW_BLUR) {
+    if (int rc = mis_aug_blur_views(out, out_dtype, pd, n_views, C, s, mean, std, stream)) return rc;
+    ++*n_launches;
+  }
+  return MIS_OK;
 }

@@ -99,6 +99,7 @@ class FusedTwoViewTransforms:
         self._pool = None                     # one helper thread drawing the NEXT batch's parameters
         self._pending = None                  # ((B, H, W), future)
         self._norm_cache = {}
+        self._c_flags, self._c_bad, self._c_nl = C.c_uint32(0), C.c_int(-1), C.c_int(0)
         self._x_stage: torch.Tensor | None = None      # device staging buffer of host batches
         self._x_host_ring = []                          # (pinned host batch, event after its copies): alive while in flight
         self.last_h2d_bytes = 0
@@ -183,36 +184,45 @@ class FusedTwoViewTransforms:
         n_views = int(params_view_major.shape[0])
         assert params_view_major.dtype == VIEW_PARAMS_DTYPE
         s = self.crop_size
-        flags_any = self._validate_table(params_view_major, B, H, W)
-        extra = flags_any & (MIS_VIEW_BLUR | MIS_VIEW_SOLARIZE)
-        if extra:
-            variant = _lib.lib.mis_aug_kernel_variant(Cc, H, W, Cc * H * W, s, self.use_tma)
-            if variant != 0:
-                raise NotImplementedError(
-                    "GaussianBlur / RandomSolarize are fused into the strip kernel only (use_tma=0, one channel, "
-                    f"8 <= crop <= 256, at most 5.5x downscaling); this call would run K1 variant {variant}")
         if out is None:
             out = torch.empty((n_views, Cc, s, s), dtype=self.out_dtype, device=x.device)
         else:
             assert out.is_cuda and out.is_contiguous() and out.dtype == self.out_dtype
             assert tuple(out.shape) == (n_views, Cc, s, s)
-        params_dev, order_dev, _keep = self._stage_params(params_view_major, x.device, with_order=True)
+        if n_views == 0:
+            return out
+        p = params_view_major if params_view_major.flags.c_contiguous else np.ascontiguousarray(params_view_major)
+        # check + staging copy + launch order + H2D + K1 (+ blur kernel) in one native call (mis_aug_two_view_staged)
+        host, dev, ev = self._staging_slot(p.nbytes + 4 * n_views, x.device)
+        flags, bad, nl = self._c_flags, self._c_bad, self._c_nl
         with _on_device(x.device):
-            stream = torch.cuda.current_stream(x.device).cuda_stream
-            rc = _lib.lib.mis_aug_two_view_ordered(
-                x.data_ptr(), B, Cc, H, W, Cc * H * W, params_dev, n_views, order_dev,
-                self.window[0], self.window[1], mean_c, std_c,
-                out.data_ptr(), s, MIS_DTYPE_F32 if self.out_dtype == torch.float32 else MIS_DTYPE_BF16,
-                self.use_tma, C.c_void_p(stream))
-            _lib.check(rc, "mis_aug_two_view_ordered")
-            self.launches += 1
-            if extra & MIS_VIEW_BLUR:      # GaussianBlur(23) -> solarize -> normalise for the views that drew a blur
-                rc = _lib.lib.mis_aug_blur_views(
-                    out.data_ptr(), MIS_DTYPE_F32 if self.out_dtype == torch.float32 else MIS_DTYPE_BF16, params_dev,
-                    n_views, Cc, s, mean_c, std_c, C.c_void_p(stream))
-                _lib.check(rc, "mis_aug_blur_views")
-                self.launches += 1
+            stream = torch.cuda.current_stream(x.device)
+            rc = _lib.lib.mis_aug_two_view_staged(
+                x.data_ptr(), B, Cc, H, W, Cc * H * W, p.ctypes.data, n_views, host.data_ptr(), dev.data_ptr(),
+                host.numel(), self.window[0], self.window[1], mean_c, std_c, out.data_ptr(), s,
+                MIS_DTYPE_F32 if self.out_dtype == torch.float32 else MIS_DTYPE_BF16, self.use_tma,
+                C.byref(flags), C.byref(bad), C.byref(nl), C.c_void_p(stream.cuda_stream))
+            ev.record(stream)
+        _lib.check(rc, "mis_aug_two_view_staged")
+        if bad.value >= 0:
+            self._validate_table(p, B, H, W)             # raises the ValueError that names the record
+        self.launches += nl.value
         return out
+
+    def _staging_slot(self, nbytes: int, device):
+        """One of three persistent (pinned, device) block pairs for the table and its launch order: no per-call
+        cudaHostAlloc; a block is reused only after the copy that last read it has completed."""
+        if len(self._staging) < 3:
+            slot = [None, None, torch.cuda.Event()]
+            self._staging.append(slot)
+        else:
+            slot = self._staging[self._staging_idx % 3]
+            self._staging_idx += 1
+            slot[2].synchronize()
+        if slot[0] is None or slot[0].numel() < nbytes or slot[1].device != torch.device(device):
+            slot[0] = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            slot[1] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return slot
 
     def _norm_args(self, Cc: int):
         """mean / std as C float arrays (cached per channel count; the arrays stay alive with the transform)."""
@@ -240,32 +250,6 @@ class FusedTwoViewTransforms:
             raise ValueError(f"view record {bad.value} is outside the batch: img {int(r['img'])} of {B}, box (top "
                              f"{int(r['top'])}, left {int(r['left'])}, h {int(r['h'])}, w {int(r['w'])}) in {H}x{W}")
         return int(flags.value)
-
-    def _stage_params(self, params: np.ndarray, device, with_order: bool = False):
-        """Copy the table (and, with ``with_order``, the most-expensive-first launch order of its views, computed
-        straight into the pinned buffer) through one of three persistent pinned buffers: one H2D copy per call, no
-        per-call cudaHostAlloc.  Returns (device table pointer, device order pointer or None, keep-alive tensor)."""
-        rec_bytes = params.nbytes
-        n = params.shape[0]
-        nbytes = rec_bytes + (4 * n if with_order else 0)
-        if len(self._staging) < 3:
-            slot = [None, None, torch.cuda.Event(), None]
-            self._staging.append(slot)
-        else:
-            slot = self._staging[self._staging_idx % 3]
-            self._staging_idx += 1
-            slot[2].synchronize()                     # the copy that last used this buffer has finished
-        if slot[0] is None or slot[0].numel() != nbytes or slot[1].device != torch.device(device):
-            slot[0] = torch.empty(nbytes, dtype=torch.uint8).pin_memory()     # exact size: whole-tensor copies below
-            slot[1] = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            slot[3] = slot[0].numpy()
-        host, dev, ev, host_np = slot
-        host_np[:rec_bytes] = params.view(np.uint8).reshape(-1)
-        if with_order:
-            _lib.check(_lib.lib.mis_view_cost_order(host.data_ptr(), n, host.data_ptr() + rec_bytes), "mis_view_cost_order")
-        dev.copy_(host, non_blocking=True)
-        ev.record(torch.cuda.current_stream(device))
-        return dev.data_ptr(), (dev.data_ptr() + rec_bytes if with_order else None), dev
 
     def stage_needed_rows(self, x_host: torch.Tensor, params: np.ndarray, device=None,
                           min_gap_bytes: int = 256 << 10) -> torch.Tensor:
