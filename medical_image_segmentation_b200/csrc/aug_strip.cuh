@@ -23,6 +23,7 @@ struct StripArgs {
   int nsx, nsy, rp;        // strips of 32 output columns, vertical parts, output rows per part
   int rowbuf;              // floats per intermediate-row buffer of a warp
   int dbl;                 // 1: two row buffers per warp (no second warp barrier per output row)
+  int pf_groups;           // L2 prefetch distance of the streams, in groups of G source rows
   int raw_all;             // 1 (C == 3): resample + flip only; every plane is left as uint16 for mis rgb colour kernel
   uint32_t off_sched, off_fmask, off_row, off_misc;   // byte offsets into dynamic shared memory (parked tiles at 0)
 };
