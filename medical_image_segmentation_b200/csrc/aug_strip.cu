@@ -827,7 +827,7 @@ static bool make_plan(int H, int W, int s, Plan* best) {
     for (int dbl = 1; dbl >= 0; --dbl) {
       Plan p = {};
       p.nsx = nsx; p.nsy = nsy; p.rp = rp; p.rowbuf = rowbuf; p.dbl = dbl; p.threads = threads;
-      p.big = threads > 448;
+      p.big = threads > 768 ? 2 : (threads > 448 ? 1 : 0);   // 0: (448, 2) 72 regs; 1: (768, 1) 85 regs; 2: (1024, 1) 64 regs
       size_t off = al16(park);
       p.off_sched = (uint32_t)off; off += (size_t)sched_cap * 16;
       p.off_fmask = (uint32_t)off; off += al16((size_t)(sched_cap / 32 + 2) * 4);
@@ -835,7 +835,7 @@ static bool make_plan(int H, int W, int s, Plan* best) {
       p.off_misc = (uint32_t)off; off += sizeof(Misc);
       p.smem = off;
       if (p.smem > kSmPerBlock) continue;
-      const int regs = p.big ? 64 : 72;
+      const int regs = p.big == 2 ? 64 : (p.big == 1 ? 85 : 72);
       int ctas = (int)(kSmPerSm / (p.smem + 1024));
       const int by_threads = 2048 / threads, by_regs = 65536 / (regs * threads);
       ctas = ctas < by_threads ? ctas : by_threads;
@@ -846,10 +846,11 @@ static bool make_plan(int H, int W, int s, Plan* best) {
       const int warps = ctas * nwarps;
       // More resident warps win; on a tie fewer parts (less halo, fewer redundant set-ups), then two row buffers.
       // The 1024-thread instantiation has 64 registers per thread and spills the load slots of the wide classes
-      // (a spilled slot serialises the prefetch), so it only competes when the 72-register one cannot reach 20 warps.
-      const int score = p.big ? warps : warps + 1000;
+      // (a spilled slot serialises the prefetch), so it only competes when the 72- / 85-register ones cannot reach 20
+      // warps (256^2: one CTA per SM either way; 24 warps without spills beat 32 with).
+      const int score = p.big == 2 ? warps : warps + 1000;
       if (!found || score > best_score) {
-        if (!p.big && warps < 20) continue;
+        if (p.big != 2 && warps < 20) continue;
         *best = p;
         best_score = score;
         found = true;
@@ -921,7 +922,8 @@ int launch_strip(StripArgs a, int n_views, bool window, cudaStream_t stream) {
 
   a.off_sched = p.off_sched; a.off_fmask = p.off_fmask; a.off_row = p.off_row; a.off_misc = p.off_misc;
   const int n_planes = n_views * a.C;
-  if (p.big) return window ? launch_shape<true, 1024, 1>(a, n_planes, p, stream) : launch_shape<false, 1024, 1>(a, n_planes, p, stream);
+  if (p.big == 2) return window ? launch_shape<true, 1024, 1>(a, n_planes, p, stream) : launch_shape<false, 1024, 1>(a, n_planes, p, stream);
+  if (p.big == 1) return window ? launch_shape<true, 768, 1>(a, n_planes, p, stream) : launch_shape<false, 768, 1>(a, n_planes, p, stream);
   return window ? launch_shape<true, 448, 2>(a, n_planes, p, stream) : launch_shape<false, 448, 2>(a, n_planes, p, stream);
 }
 
