@@ -14,8 +14,9 @@
 //     therefore split into hi = tf32(x) and lo = tf32(x - hi) and the GEMM runs over K' = 3 D on the concatenations
 //     [hi | hi | lo] x [hi | lo | hi] (the lo.lo term, 2^-22 relative, is dropped): fp32-grade similarities from the
 //     TF32 tensor cores, at three times a GEMM cost that is negligible next to reading the bank.
-//  2. knn_vote_kernel, one CTA per query: exact k-th largest similarity by an MSB-first radix select over the row (four
-//     8-bit histogram passes, no sort of the row), the k selected (index, similarity) pairs gathered into shared memory
+//  2. knn_vote_kernel, one CTA per query: exact selection of the k largest similarities in two reads of the row (per-thread
+//     maxima give a lower bound of the k-th largest that only ~1.4 k elements reach; those are gathered and sorted; rows
+//     with masses of equal similarities take an MSB-first radix select instead), the k (index, similarity) pairs in shared memory
 //     and ordered by bank index (so that the result does not depend on thread timing), exp(sim / T) votes accumulated per
 //     class in that order, and a bitonic sort of the (score, class) pairs: score descending, class ascending among equal
 //     scores (torch's argsort leaves the order of equal scores -- e.g. all the classes without a vote -- unspecified).
@@ -32,6 +33,7 @@ namespace knn {
 constexpr int kThreads = 512;
 constexpr int kMaxK = 1024;
 constexpr int kMaxClasses = 8192;
+constexpr int kCand = 4096;          // candidate list of the fast selection path (>= 2048: it first holds the thread maxima)
 
 __device__ __forceinline__ uint32_t order_key(float s) {     // larger similarity -> larger key
   const uint32_t u = __float_as_uint(s);
@@ -80,10 +82,101 @@ __global__ void __launch_bounds__(kThreads) knn_vote_kernel(const VoteArgs a) {
   uint64_t* sc = sel + a.k_pad;                                             // [c_pad]  sortable (score, class) pairs
   int* lab_s = reinterpret_cast<int*>(sc + a.c_pad);                        // [k_pad]  label of the j-th selected neighbour
   float* w_s = reinterpret_cast<float*>(lab_s + a.k_pad);                   // [k_pad]  exp(sim / T)
+  uint64_t* cand = reinterpret_cast<uint64_t*>(w_s + a.k_pad);              // [kCand]  (key << 32) | ~index, sortable
   const int tid = threadIdx.x;
   const float* row = a.sim + (size_t)blockIdx.x * a.ld;
   const int n = a.n_bank;
 
+  // ---- selection, fast path: two reads of the row, no atomics on the row --------------------------------------------
+  // Each thread keeps the m largest keys of its share (m = ceil(2k / threads), so the k-th largest of those
+  // threads*m values, T0, is a lower bound of the true k-th largest that only ~1.4 k elements of the row reach); the
+  // elements >= T0 are gathered and sorted (key descending, bank index ascending) and the first k are the neighbours.
+  // A row with more than kCand elements >= T0 (masses of equal similarities) takes the radix select below instead.
+  for (int i = tid; i < a.k_pad; i += kThreads) sel[i] = ~0ull;             // padding sorts last
+  bool fast = false;
+  {
+    const int m = (2 * a.k + kThreads - 1) / kThreads;                      // 1 .. 4
+    uint32_t top[4] = {0u, 0u, 0u, 0u};
+    for (int i = tid; i < n; i += kThreads) {
+      uint32_t key = order_key(row[i]);
+      if (key > top[3]) {                                                   // insertion into the sorted quadruple
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t hi = max(top[j], key);
+          key = min(top[j], key);
+          top[j] = hi;
+        }
+      }
+    }
+    const int nv = kThreads * m;                                            // <= 2048 values, a power of two times m
+    const int nv_pad = 2048;
+    uint32_t* vals = reinterpret_cast<uint32_t*>(cand);                     // the candidate list is not in use yet
+    for (int i = tid; i < nv_pad; i += kThreads) vals[i] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < m) vals[tid * m + j] = top[j];
+    __syncthreads();
+    for (int size = 2; size <= nv_pad; size <<= 1) {                        // descending bitonic sort of the thread maxima
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = tid; i < nv_pad; i += kThreads) {
+          const int j = i ^ stride;
+          if (j > i) {
+            const uint32_t x = vals[i], y = vals[j];
+            const bool down = (i & size) == 0;
+            if ((x < y) == down) {
+              vals[i] = y;
+              vals[j] = x;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    const uint32_t t0 = vals[a.k - 1];                                      // (k <= n guarantees k real values, nv >= 2k)
+    (void)nv;
+    if (tid == 0) ctl[2] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kThreads) {
+      const uint32_t key = order_key(row[i]);
+      if (key >= t0) {
+        const uint32_t slot = atomicAdd(&ctl[2], 1u);
+        if (slot < (uint32_t)kCand) cand[slot] = ((uint64_t)key << 32) | (uint32_t)(~(uint32_t)i);
+      }
+    }
+    __syncthreads();
+    const int nc = (int)ctl[2];
+    fast = nc <= kCand;                                                     // CTA-uniform
+    if (fast) {
+      int nc_pad = 1;
+      while (nc_pad < nc) nc_pad <<= 1;
+      for (int i = nc + tid; i < nc_pad; i += kThreads) cand[i] = 0ull;     // padding sorts last (descending)
+      __syncthreads();
+      for (int size = 2; size <= nc_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int i = tid; i < nc_pad; i += kThreads) {
+            const int j = i ^ stride;
+            if (j > i) {
+              const uint64_t x = cand[i], y = cand[j];
+              const bool down = (i & size) == 0;
+              if ((x < y) == down) {
+                cand[i] = y;
+                cand[j] = x;
+              }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      for (int j = tid; j < a.k; j += kThreads) {                           // larger key first, lower bank index among equal keys
+        const uint32_t idx = ~(uint32_t)cand[j];
+        sel[j] = ((uint64_t)idx << 32) | __float_as_uint(row[idx]);
+      }
+    }
+    __syncthreads();
+  }
+
+  if (!fast) {
   // ---- k-th largest key: MSB-first radix select -------------------------------------------------------------------
   uint32_t prefix = 0, mask = 0;
   int remaining = a.k;
@@ -115,7 +208,6 @@ __global__ void __launch_bounds__(kThreads) knn_vote_kernel(const VoteArgs a) {
 
   // ---- gather the selected pairs ----------------------------------------------------------------------------------
   if (tid == 0) ctl[2] = 0, ctl[3] = 0;
-  for (int i = tid; i < a.k_pad; i += kThreads) sel[i] = ~0ull;             // padding sorts last
   __syncthreads();
   for (int i = tid; i < n; i += kThreads) {
     const float s = row[i];
@@ -150,6 +242,8 @@ __global__ void __launch_bounds__(kThreads) knn_vote_kernel(const VoteArgs a) {
     }
   }
   __syncthreads();
+
+  }
 
   // ---- order the pairs by bank index (bitonic, ascending; padding = ~0 sorts last) ----------------------------------
   for (int size = 2; size <= a.k_pad; size <<= 1) {
@@ -273,7 +367,7 @@ extern "C" int mis_knn_predict(const float* query, const float* bank, const int6
   a.labels = bank_labels;
   a.pred = pred_labels;
   a.scores = pred_scores;
-  const size_t smem = (256 + 8) * 4 + (size_t)a.k_pad * 8 + (size_t)a.c_pad * 8 + (size_t)a.k_pad * 8;
+  const size_t smem = (256 + 8) * 4 + (size_t)a.k_pad * 8 + (size_t)a.c_pad * 8 + (size_t)a.k_pad * 8 + (size_t)kCand * 8;
   MIS_CUDA_TRY(cudaFuncSetAttribute(knn_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   knn_vote_kernel<<<dim3((unsigned)n_query), kThreads, smem, st>>>(a);
   MIS_CUDA_TRY(cudaGetLastError());

@@ -69,6 +69,22 @@ def test_large_bank_and_ties():
         assert np.quantile(err, 0.99) <= 1e-3 and (err <= 1e-3).mean() >= 0.98, (k, err.max())
 
 
+def test_masses_of_equal_similarities_take_the_radix_path():
+    """6000 identical bank rows (more than the fast path's candidate list holds): every similarity ties, the k lowest
+    bank indices are the neighbours, exactly as the oracle's stable ordering selects them."""
+    gen = torch.Generator().manual_seed(9)
+    base = torch.nn.functional.normalize(torch.randn(1, 64, generator=gen), dim=1)
+    bank = base.repeat(6000, 1)
+    bank[::1000] = torch.nn.functional.normalize(torch.randn(6, 64, generator=gen), dim=1)   # a few distinct rows
+    labels = torch.arange(6000) % 11
+    query = torch.nn.functional.normalize(torch.randn(40, 64, generator=gen), dim=1)
+    for k in (1, 50, 700):
+        pred, scores = _run(query.numpy(), bank.numpy(), labels.numpy(), k, 0.2, 11)
+        want, _, _ = K.knn_scores(query.numpy(), bank.numpy(), labels.numpy(), k, 0.2, 11)
+        err = np.abs(scores - want).max(axis=1) / want.max(axis=1)
+        assert err.max() <= 1e-3, (k, err.max())
+
+
 def test_errors():
     from medical_image_segmentation_b200 import KNNOnlineEvaluator
     q, b, l = torch.randn(4, 64).cuda(), torch.randn(10, 64).cuda(), torch.zeros(10, dtype=torch.long).cuda()
