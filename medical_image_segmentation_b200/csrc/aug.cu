@@ -1078,7 +1078,7 @@ extern "C" int mis_aug_two_view_ordered(const uint16_t* src, int n_images, int C
   MIS_REQUIRE(C == 1 || (use_tma == 0 && mis::augc::rgb_supported(s) && mis::augs::strip_supported(C, H, W, img_stride, s)),
               MIS_ERR_UNSUPPORTED,
               "mis_aug_two_view: 3-channel input runs on the strip kernel + colour kernel only: variant 0, crop a multiple "
-              "of 8 up to 192, even W, at most 5.5x downscaling (got s=%d, H=%d, W=%d, variant %d)", s, H, W, use_tma);
+              "of 8 up to 256, even W, at most 5.5x downscaling (got s=%d, H=%d, W=%d, variant %d)", s, H, W, use_tma);
   MIS_REQUIRE(s >= 8 && s <= kBandRows * kMaxBands, MIS_ERR_UNSUPPORTED, "mis_aug_two_view: crop size %d not in [8,256]", s);
   MIS_REQUIRE((W & 1) == 0 && (img_stride & 1) == 0, MIS_ERR_UNSUPPORTED,
               "mis_aug_two_view: W (%d) and img_stride must be even", W);

@@ -25,6 +25,7 @@ struct RgbArgs {
   void* out;
   const MisViewParams* params;
   int s, out_f32;
+  int stream;                // 1: planes too large for shared memory (s > 192), read and finished in place
   float mean[4], inv_std[4];
 };
 
@@ -104,18 +105,25 @@ __global__ void __launch_bounds__(kThreads, 1) rgb_color_kernel(const RgbArgs a)
   const size_t esz = a.out_f32 ? 4 : 2;
   uint8_t* const base = static_cast<uint8_t*>(a.out) + (size_t)view * 3 * n * esz;
 
-  // ---- the three uint16 planes -> shared memory (the output overwrites them in global memory) ---------------------
-  for (int c = 0; c < 3; ++c) {
-    const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)c * n * esz);
-    uint4* dst = reinterpret_cast<uint4*>(sm16 + (size_t)c * n);
-    for (int i = tid; i < n / 8; i += kThreads) dst[i] = src[i];
+  // ---- the three uint16 planes: staged in shared memory (the output overwrites them in global memory), or -- crops
+  //      above 192, whose planes exceed one SM's shared memory -- read in place (a.stream) --------------------------------
+  const uint16_t* pl[3];
+  if (!a.stream) {
+    for (int c = 0; c < 3; ++c) {
+      const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)c * n * esz);
+      uint4* dst = reinterpret_cast<uint4*>(sm16 + (size_t)c * n);
+      for (int i = tid; i < n / 8; i += kThreads) dst[i] = src[i];
+      pl[c] = sm16 + (size_t)c * n;
+    }
+    __syncthreads();
+  } else {
+    for (int c = 0; c < 3; ++c) pl[c] = reinterpret_cast<const uint16_t*>(base + (size_t)c * n * esz);
   }
-  __syncthreads();
   auto load_px = [&](int i) {
     Px p;
-    p.r = (float)sm16[i] * (1.f / 65535.f);
-    p.g = (float)sm16[n + i] * (1.f / 65535.f);
-    p.b = (float)sm16[2 * n + i] * (1.f / 65535.f);
+    p.r = (float)pl[0][i] * (1.f / 65535.f);
+    p.g = (float)pl[1][i] * (1.f / 65535.f);
+    p.b = (float)pl[2][i] * (1.f / 65535.f);
     return p;
   };
 
@@ -137,8 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) rgb_color_kernel(const RgbArgs a)
   }
   const bool gray = (P.flags & MIS_VIEW_GRAY) != 0, sol = (P.flags & MIS_VIEW_SOLARIZE) != 0;
   const bool raw = (P.flags & MIS_VIEW_BLUR) != 0;
-  for (int i = tid; i < n; i += kThreads) {
-    Px p = load_px(i);
+  auto finish = [&](int i, Px p) {
     if (jitter) p = apply_ops(p, P, 0, 4, cadd);
     if (gray) {
       const float gsc = gray_of(p);
@@ -158,10 +165,25 @@ __global__ void __launch_bounds__(kThreads, 1) rgb_color_kernel(const RgbArgs a)
         else reinterpret_cast<__nv_bfloat16*>(plane)[i] = __float2bfloat16_rn(x);
       }
     }
+  };
+  if (!a.stream || !a.out_f32 || raw) {
+    // staged planes, or a result as wide as the uint16 it replaces: pixel i only overwrites its own three inputs
+    for (int i = tid; i < n; i += kThreads) finish(i, load_px(i));
+  } else {
+    // fp32 result in place: pixel i's result covers the uint16 inputs 2i and 2i+1 of its plane.  Chunks of kThreads
+    // pixels from the top down, every pixel of a chunk loaded before any is stored: a chunk [a, b) then only overwrites
+    // inputs in [a, 2b), its own (already in registers) and those of chunks finished before.
+    for (int c0 = ((n - 1) / kThreads) * kThreads; c0 >= 0; c0 -= kThreads) {
+      const int i = c0 + tid;
+      Px p = {0.f, 0.f, 0.f};
+      if (i < n) p = load_px(i);
+      __syncthreads();
+      if (i < n) finish(i, p);
+    }
   }
 }
 
-bool rgb_supported(int s) { return (s & 7) == 0 && (size_t)6 * s * s <= 227 * 1024 - 256; }
+bool rgb_supported(int s) { return (s & 7) == 0 && s <= 256; }
 
 int launch_rgb_color(void* out, int out_f32, const MisViewParams* params, int n_views, int s, const float* mean,
                      const float* inv_std, cudaStream_t stream) {
@@ -174,7 +196,8 @@ int launch_rgb_color(void* out, int out_f32, const MisViewParams* params, int n_
     a.mean[c] = mean[c];
     a.inv_std[c] = inv_std[c];
   }
-  const size_t smem = (size_t)6 * s * s;
+  a.stream = (size_t)6 * s * s > 227 * 1024 - 256;
+  const size_t smem = a.stream ? 0 : (size_t)6 * s * s;
   MIS_CUDA_TRY(cudaFuncSetAttribute(rgb_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rgb_color_kernel<<<dim3((unsigned)n_views), kThreads, smem, stream>>>(a);
   MIS_CUDA_TRY(cudaGetLastError());

@@ -5,7 +5,7 @@ arguments, ``__call__(x) -> [view1, view2]``.  Differences, all forced by moving
 per-sample CPU callable to a per-batch GPU kernel:
 
 * ``x`` is a *batch* ``[B, C, H, W]`` (or ``[B, H, W]``), C = 1 (16-bit slices, the fused single-kernel path) or C = 3
-  (saturation / hue / RandomGrayscale live; a resample kernel plus a colour kernel, crop a multiple of 8 up to 192), of
+  (saturation / hue / RandomGrayscale live; a resample kernel plus a colour kernel, crop a multiple of 8 up to 256), of
   raw ``torch.uint16`` slices -- on the GPU, or
   on the host (then it is copied through pinned memory first).  The reference feeds one decoded
   image at a time to DataLoader workers.

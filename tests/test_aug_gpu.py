@@ -257,13 +257,15 @@ def test_three_channel_input_matches_reference_golden(tag):
     assert worst < 2e-4
 
 
-def test_three_channel_batch_matches_oracle():
-    """3-channel batch at the reference's RADIOLOGY / IMAGENET_FFCV crop (112), default ctor arguments (blur, solarize),
+@pytest.mark.parametrize("H,W,crop", [(200, 232, 112), (320, 288, 224), (256, 300, 256)])
+def test_three_channel_batch_matches_oracle(H, W, crop):
+    """3-channel batch at the reference's RADIOLOGY / IMAGENET_FFCV crop (112) and at crops whose three planes exceed one
+    SM's shared memory (224, 256: colour ops in place, blur in two bands), default ctor arguments (blur, solarize),
     bf16 == round(fp32), gray-replicated slices (what the reference's beton stores, pytorch_datasets.py:144) give three
     equal planes."""
     from medical_image_segmentation_b200.transforms import FusedTwoViewTransforms
     mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
-    B, H, W, crop = 4, 200, 232, 112
+    B = 4
     imgs = np.stack([synth.batch_512(3, seed=60 + i, H=H, W=W) for i in range(B)])      # [B,3,H,W]
     x = torch.from_numpy(imgs).cuda()
     tf = FusedTwoViewTransforms(crop, mean, std, out_dtype=torch.float32)
@@ -353,7 +355,7 @@ def test_argument_errors_mirror_reference_style():
     with pytest.raises(NotImplementedError):          # odd width
         t(torch.zeros(1, 1, 64, 63, dtype=torch.uint16).cuda())
     from medical_image_segmentation_b200.transforms import FusedTwoViewTransforms
-    with pytest.raises(NotImplementedError):          # 3 channels: crop must be a multiple of 8 (and <= 192)
+    with pytest.raises(NotImplementedError):          # 3 channels: crop must be a multiple of 8
         FusedTwoViewTransforms(36, (0.5,) * 3, (0.2,) * 3)(torch.zeros(1, 3, 64, 64, dtype=torch.uint16).cuda())
     with pytest.raises(NotImplementedError):          # 2 channels
         FusedTwoViewTransforms(32, (0.5,) * 2, (0.2,) * 2)(torch.zeros(1, 2, 64, 64, dtype=torch.uint16).cuda())
