@@ -252,10 +252,12 @@ class FusedTwoViewTransforms:
         return int(flags.value)
 
     def stage_needed_rows(self, x_host: torch.Tensor, params: np.ndarray, device=None,
-                          min_gap_bytes: int = 256 << 10) -> torch.Tensor:
+                          min_gap_bytes: int = 256 << 10, out: torch.Tensor | None = None) -> torch.Tensor:
         """Host batch -> device, copying only the rows the records read (mis_h2d_needed_rows); ranges closer than
         ``min_gap_bytes`` are merged into one copy (a copy costs ~200 KB of PCIe time to set up).  Returns the full-size
-        device buffer K1 reads; rows no record touches are stale.  ``self.last_h2d_bytes`` = bytes put on the wire."""
+        device buffer K1 reads; rows no record touches are stale.  ``self.last_h2d_bytes`` = bytes put on the wire.
+        The copies go to torch's current stream; ``out`` names the device buffer (e.g. one of two, filled on a copy
+        stream while the previous batch is being processed), default: one buffer owned by the transform."""
         if x_host.dtype != torch.uint16 or x_host.is_cuda or x_host.dim() != 4:
             raise TypeError("stage_needed_rows expects a host torch.uint16 [B,C,H,W] batch")
         x_host = x_host.contiguous()
@@ -263,12 +265,18 @@ class FusedTwoViewTransforms:
             x_host = x_host.pin_memory()
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         B, Cc, H, W = x_host.shape
-        if self._x_stage is None or self._x_stage.shape != x_host.shape or self._x_stage.device != device:
-            self._x_stage = torch.empty(x_host.shape, dtype=torch.uint16, device=device)
+        if out is not None:
+            if out.dtype != torch.uint16 or out.shape != x_host.shape or out.device != device or not out.is_contiguous():
+                raise ValueError("stage_needed_rows: `out` must be a contiguous torch.uint16 device tensor of the batch's shape")
+            stage = out
+        else:
+            if self._x_stage is None or self._x_stage.shape != x_host.shape or self._x_stage.device != device:
+                self._x_stage = torch.empty(x_host.shape, dtype=torch.uint16, device=device)
+            stage = self._x_stage
         p = np.ascontiguousarray(params)
         nbytes = C.c_int64(0)
         with _on_device(device):
-            rc = _lib.lib.mis_h2d_needed_rows(x_host.data_ptr(), self._x_stage.data_ptr(), B, Cc, H, W, Cc * H * W,
+            rc = _lib.lib.mis_h2d_needed_rows(x_host.data_ptr(), stage.data_ptr(), B, Cc, H, W, Cc * H * W,
                                               p.ctypes.data, p.shape[0], int(min_gap_bytes),
                                               C.c_void_p(torch.cuda.current_stream(device).cuda_stream), C.byref(nbytes))
         _lib.check(rc, "mis_h2d_needed_rows")
@@ -280,7 +288,7 @@ class FusedTwoViewTransforms:
         self._x_host_ring = [(h, e) for (h, e) in self._x_host_ring if not e.query()]
         self._x_host_ring.append((x_host, ev))
         self.last_h2d_bytes = int(nbytes.value)
-        return self._x_stage
+        return stage
 
     def __call__(self, x) -> list[torch.Tensor]:
         if isinstance(x, np.ndarray):
