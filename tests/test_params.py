@@ -224,3 +224,38 @@ def test_view_cost_order_is_a_stable_descending_permutation():
     same = np.diff(b) == 0
     assert (np.diff(order)[same] > 0).all()                          # stable inside a bucket
     assert _lib.lib.mis_view_cost_order(None, 0, None) == 0
+
+
+def test_native_table_check_reports_the_first_bad_record():
+    """mis_view_params_check (what apply() runs before the kernel trusts a table): boxes outside the slice, slices
+    outside the batch and a blurred view without a usable sigma are reported by index; flags are OR-ed up to there."""
+    import ctypes as C
+    from medical_image_segmentation_b200 import FusedTwoViewTransforms, _lib
+    t = FusedTwoViewTransforms(64, (0.2,), (0.2,), blur_prob=(1.0, 0.1), solarize_prob=(0.0, 0.2))
+    torch.manual_seed(8)
+    p = np.ascontiguousarray(t.to_view_major(t.draw_params(50, 256, 320)))
+
+    def check(tab, B=50, H=256, W=320):
+        flags, bad = C.c_uint32(0), C.c_int(-2)
+        assert _lib.lib.mis_view_params_check(tab.ctypes.data, tab.shape[0], B, H, W, C.byref(flags), C.byref(bad)) == 0
+        return flags.value, bad.value
+
+    flags, bad = check(p)
+    assert bad == -1 and flags == int(np.bitwise_or.reduce(p["flags"])) and (flags & 8)
+    for field, value, k in (("top", 256, 7), ("left", -1, 0), ("h", 0, 99), ("w", 321, 42), ("img", 50, 13), ("img", -1, 60)):
+        q = p.copy()
+        q[field][k] = value
+        assert check(q)[1] == k, (field, value)
+    q = p.copy()
+    k = int(np.flatnonzero(q["flags"] & 8)[3])
+    q["blur_sigma"][k] = 0.0
+    assert check(q)[1] == k
+    q["blur_sigma"][k] = np.inf
+    assert check(q)[1] == k
+    assert check(p, B=49)[1] == int(np.flatnonzero(p["img"] >= 49)[0])
+    assert check(p[:0]) == (0, -1)
+    # the Python face of it
+    with pytest.raises(ValueError):
+        q = p.copy()
+        q["top"][3] = 250
+        FusedTwoViewTransforms._validate_table(q, 50, 256, 320)
