@@ -3,15 +3,20 @@
 // The 2N x 2N similarity matrix is never written to HBM.  One CTA owns a 128-row tile of the
 // local rows and walks a range of 128-column tiles of the all-gathered matrix:
 //
-//   warp 0   TMA producer: 128B-swizzled K-major boxes of U (and, for the backward, of U^T) into a
-//            shared-memory ring, one mbarrier pair per stage;
+//   warps 0, 10-12  TMA producers: 128B-swizzled K-major boxes of U (and, for the backward, of U^T) into a
+//            shared-memory ring, one mbarrier pair per stage; in a multi-rank forward they wait, per column
+//            tile, for the flag of the rank that owns those rows (stored over NVLink by its prep kernel);
 //   warp 1   MMA issuer (one thread): S = U_I . U_J^T with tcgen05.mma kind::tf32, accumulator in
-//            TMEM (double buffered, 2 x 128 columns); backward only: dU_I += W . U_J with the A
+//            TMEM (double buffered, 2 x 128 columns); backward, D <= 256: dU_I += W . U_J with the A
 //            operand W read straight from TMEM and dU_I (128 x D fp32) resident in TMEM columns
 //            256.. for the whole column walk;
-//   warps 2-5 epilogue, lane == row (tcgen05.ld 32x32b): exp2 with the fixed max 1/T, diagonal mask;
-//            forward: thread-local row sums (no shuffles);  backward: W_ij = E_ij (c_i + c_j) rounded
-//            to TF32 and stored back over S with tcgen05.st, so the tile never leaves the SM.
+//   warps 2-9 two epilogue groups (alternate tiles), lane == row (tcgen05.ld 32x32b): exp2 with the fixed max
+//            1/T, diagonal / padding masks; forward: thread-local row sums (no shuffles);  backward:
+//            W_ij = E_ij (c_i + c_j) rounded to TF32 and stored back over S with tcgen05.st, so the tile never
+//            leaves the SM -- or, for D > 256 (kWOut), written to HBM once, after which wu_gemm_kernel computes
+//            dU = W . U_all as one tcgen05 GEMM over all of D (no per-slice recompute of S).
+// Small kernels around them: prep (normalise, TF32 rounding, peer stores), fwd_rows (lse, positives, mean loss, lse peer
+// stores + flags), transpose (U^T for the K-major boxes of the backward), bwd_finalize (split sum + normalisation Jacobian).
 //
 // Math (oracle/loss_oracle.py):  u = z/max(|z|,1e-12), S = u u^T / T,
 //   lse_i = log sum_{j != i} exp S_ij,   L_r = mean_{i in rank r} (lse_i - S_{i,p(i)}),
